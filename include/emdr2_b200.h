@@ -1,0 +1,111 @@
+/*
+ * emdr2_b200 — C ABI of the B200-native retrieve-and-read hot path.
+ *
+ * Plain C, no torch types: device/host pointers, sizes, an opaque handle and a cudaStream_t passed
+ * as void*.  Every entry point returns 0 on success or a negative EMDR2_E* code; the message of the
+ * last failure on the calling thread is available from emdr2_last_error().  Nothing throws across
+ * the ABI and nothing calls exit().  All GPU work is enqueued on the caller's stream; the library
+ * never calls cudaDeviceSynchronize() and never copies between host and device except in the
+ * *_host convenience entry point that says so.
+ *
+ * What each entry point replaces in the reference (DevSinghSachan/emdr2 @ edb8cf67):
+ *
+ *   emdr2_mips_create / destroy   DistributedBruteForceIndex.__init__ / reset_index
+ *                                 (megatron/data/emdr2_index.py:200-230) and
+ *                                 FaissMIPSIndex._set_mips_index (:111-140)
+ *   emdr2_mips_set_shard          DistributedBruteForceIndex.add_embed_data (:241-266): one row
+ *                                 range of the torch.chunk split (:252) resident on one GPU, plus
+ *                                 the row -> doc-id map (:258-260)
+ *   emdr2_mips_search             DistributedBruteForceIndex.search_mips_index (:268-305) for one
+ *                                 shard: Q·Eᵀ (:281) + top-k (:295) + id mapping (:298-303), and
+ *                                 FaissMIPSIndex.search_mips_index (:182-197, IndexFlatIP.search)
+ *   emdr2_mips_merge              the gather of per-GPU score slabs into C[nq,N] followed by the
+ *                                 global torch.topk (:284-295); here a k-way merge of per-shard
+ *                                 top-k lists (the payload of one all-gather)
+ *   emdr2_mips_search_host        FaissMIPSIndex.search_mips_index's host round trip (:188,196):
+ *                                 numpy queries in, numpy (distances, ids) out
+ *
+ * Ranking contract (the reference leaves tie order undefined — torch.topk on fp16 scores, FAISS heap
+ * order): score[q,i] = sum_j Q[q,j]*E[i,j] accumulated in fp32 on the tensor cores; results are the
+ * first k rows under (score descending, then row ascending inside a shard / id ascending across
+ * merged lists).  A caller that stores each shard's rows in ascending id order therefore gets a
+ * global (score desc, id asc) ranking for any number of shards.  Rows whose score is NaN are never
+ * returned.  If fewer than k rows exist the tail is filled with score = -inf, id = -1 (FAISS
+ * convention).
+ */
+#ifndef EMDR2_B200_H_
+#define EMDR2_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EMDR2_API __attribute__((visibility("default")))
+#else
+#define EMDR2_API
+#endif
+
+#define EMDR2_OK 0
+#define EMDR2_EINVAL (-1)   /* bad argument (null pointer, unsupported shape, misalignment) */
+#define EMDR2_ECUDA (-2)    /* a CUDA runtime/driver call failed */
+#define EMDR2_ENOMEM (-3)   /* host or device allocation failed */
+#define EMDR2_ESTATE (-4)   /* call sequence error (e.g. search before set_shard) */
+#define EMDR2_EUNSUPPORTED (-5) /* not an sm_100 device / feature not built */
+
+#define EMDR2_DTYPE_FP16 0
+#define EMDR2_DTYPE_BF16 1
+
+/* Limits of the fused scan kernel (one launch). Larger nq is served by looping inside
+ * emdr2_mips_search; larger k is rejected with EMDR2_EINVAL. */
+#define EMDR2_MIPS_MAX_K 64
+#define EMDR2_MIPS_QUERIES_PER_PASS 64
+
+/* Message of the last error raised on the calling thread ("" if none). Never NULL. */
+EMDR2_API const char* emdr2_last_error(void);
+
+/* Library build information: "emdr2_b200 <version> sm_100a nvcc <x.y>". */
+EMDR2_API const char* emdr2_version(void);
+
+/* Create a search handle for embeddings of dimension d (d % 8 == 0, 8 <= d <= 1024) stored as
+ * dtype (EMDR2_DTYPE_*) on CUDA device `device`.  Allocates the handle's small device workspace. */
+EMDR2_API int emdr2_mips_create(int d, int dtype, int device, void** out_handle);
+
+/* Bind one evidence shard: dev_rows is [n, d] row-major, 16-byte aligned, caller-owned device
+ * memory that must stay valid until the next set_shard/destroy.  dev_ids is [n] int64 doc ids on
+ * the device, or NULL meaning id = id_base + row.  n may be 0 (empty shard). */
+EMDR2_API int emdr2_mips_set_shard(void* handle, const void* dev_rows, const int64_t* dev_ids, int64_t n,
+                         int64_t id_base);
+
+/* Top-k inner-product search of dev_q [nq, d] (same dtype as the shard, device memory) against the
+ * bound shard.  Writes dev_scores [nq, k] fp32 and dev_ids [nq, k] int64, sorted best first.
+ * Asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream). 1 <= k <= EMDR2_MIPS_MAX_K. */
+EMDR2_API int emdr2_mips_search(void* handle, const void* dev_q, int nq, int k, float* dev_scores,
+                      int64_t* dev_ids, void* cuda_stream);
+
+/* Same search with HOST buffers: copies host_q to the device, searches, copies the results back and
+ * synchronises the stream before returning (the FAISS-style numpy round trip). */
+EMDR2_API int emdr2_mips_search_host(void* handle, const void* host_q, int nq, int k, float* host_scores,
+                           int64_t* host_ids, void* cuda_stream);
+
+/* k-way merge of `parts` sorted-or-unsorted top-k lists: scores [parts, nq, k] fp32 and
+ * ids [parts, nq, k] int64 in device memory (entries with id < 0 are padding) into
+ * out_scores/out_ids [nq, k] ranked (score desc, id asc).  Handle-free; asynchronous on the stream. */
+EMDR2_API int emdr2_mips_merge(const float* dev_scores, const int64_t* dev_ids, int parts, int nq, int k,
+                     float* dev_out_scores, int64_t* dev_out_ids, void* cuda_stream);
+
+/* Tuning / introspection. Options: "probe" (0/1, seed thresholds from a first probing tile),
+ * "share" (0/1, cross-CTA threshold sharing), "max_ctas" (0 = all SMs).
+ * Stats (of the last search, valid after the stream has been synchronised): "ctas", "tiles",
+ * "stages", "smem_bytes", "appends", "compactions". */
+EMDR2_API int emdr2_mips_set_option(void* handle, const char* name, int64_t value);
+EMDR2_API int emdr2_mips_get_stat(void* handle, const char* name, int64_t* out_value);
+
+EMDR2_API int emdr2_mips_destroy(void* handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMDR2_B200_H_ */
