@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/emdr2_b200.h"
 #include "mips_merge.cuh"
@@ -117,6 +118,12 @@ struct MipsHandle {
   int opt_probe = 1, opt_share = 1, opt_max_ctas = 0, opt_stats = 0;
   uint32_t probe_timeout_ns = 30000;
   int last_ctas = 0, last_tiles = 0;
+
+  // optional per-launch timing of the scan kernel (option "timing"): event pairs recorded on the
+  // caller's stream around every scan launch, summed by get_stat("scan_ns").
+  int opt_timing = 0;
+  std::vector<cudaEvent_t> ev;  // [2 * launches]
+  size_t ev_used = 0;
 };
 
 MipsHandle* as_handle(void* h) {
@@ -134,6 +141,8 @@ void free_workspace(MipsHandle* h) {
   cudaFree(h->stage_q);
   cudaFree(h->stage_scores);
   cudaFree(h->stage_ids);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  h->ev.clear();
 }
 
 }  // namespace
@@ -317,8 +326,22 @@ int emdr2_mips_search(void* handle, const void* dev_q, int nq, int k, float* dev
     a.stats = h->opt_stats ? h->stats : nullptr;
     if (h->opt_stats) CUDA_TRY(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), stream));
 
+    if (h->opt_timing) {
+      if (h->ev_used + 2 > h->ev.size()) {
+        cudaEvent_t e0, e1;
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        h->ev.push_back(e0);
+        h->ev.push_back(e1);
+      }
+      CUDA_TRY(cudaEventRecord(h->ev[h->ev_used], stream));
+    }
     emdr2::launch_mips_scan(tmap_q, h->tmap_e, a, grid, h->smem_bytes, stream);
     CUDA_TRY(cudaGetLastError());
+    if (h->opt_timing) {
+      CUDA_TRY(cudaEventRecord(h->ev[h->ev_used + 1], stream));
+      h->ev_used += 2;
+    }
     CUDA_TRY(emdr2::launch_mips_merge_pool(h->pool_scores, h->pool_ids, h->pool_cnt,
                                            emdr2::kPoolCap, nq_pass, k,
                                            dev_scores + static_cast<size_t>(q0) * k,
@@ -391,6 +414,10 @@ int emdr2_mips_set_option(void* handle, const char* name, int64_t value) {
   else if (!strcmp(name, "max_ctas")) h->opt_max_ctas = static_cast<int>(value);
   else if (!strcmp(name, "stats")) h->opt_stats = value != 0;
   else if (!strcmp(name, "probe_timeout_ns")) h->probe_timeout_ns = static_cast<uint32_t>(value);
+  else if (!strcmp(name, "timing")) {
+    h->opt_timing = value != 0;
+    h->ev_used = 0;
+  }
   else return fail(EMDR2_EINVAL, "unknown option '%s'", name);
   return EMDR2_OK;
 }
@@ -403,6 +430,21 @@ int emdr2_mips_get_stat(void* handle, const char* name, int64_t* out_value) {
   else if (!strcmp(name, "stages")) *out_value = h->num_stages;
   else if (!strcmp(name, "smem_bytes")) *out_value = h->smem_bytes;
   else if (!strcmp(name, "sm_count")) *out_value = h->sm_count;
+  else if (!strcmp(name, "scan_launches")) *out_value = static_cast<int64_t>(h->ev_used / 2);
+  else if (!strcmp(name, "scan_ns")) {
+    // sum of the scan kernel's launch durations since "timing" was switched on (blocks until the
+    // last recorded launch has finished), then restarts the accumulation
+    DeviceGuard guard(h->device);
+    double total_ms = 0.0;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventSynchronize(h->ev[i + 1]));
+      CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+      total_ms += ms;
+    }
+    h->ev_used = 0;
+    *out_value = static_cast<int64_t>(total_ms * 1e6);
+  }
   else if (!strcmp(name, "appends") || !strcmp(name, "compactions") ||
            !strcmp(name, "probe_wait_ns") || !strcmp(name, "probe_wait_sum_ns")) {
     DeviceGuard guard(h->device);

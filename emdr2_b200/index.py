@@ -1,0 +1,216 @@
+"""Host-side mirror of the reference's MIPS index classes, backed by the sm_100a scan kernel.
+
+Drop-in surface (reference megatron/data/emdr2_index.py @ edb8cf67):
+
+* ``B200BruteForceIndex``  stands where ``DistributedBruteForceIndex`` (:200-305) is constructed
+  (megatron/model/emdr2_model.py:419-421): same ``__init__(embed_size, embed_data=None,
+  use_gpu=False)``, ``add_embed_data`` (:241-266), ``search_mips_index`` (:268-305) returning
+  ``(distances float16 [nq,k], indices int32 [nq,k])`` as CUDA tensors sorted best first,
+  ``update_index`` (:232-239) and ``reset_index`` (:221-230).
+* ``B200FaissMIPSIndex``   stands where ``FaissMIPSIndex`` (:103-197) is constructed
+  (tasks/openqa/dense_retriever/evaluation/evaluate.py:49-51): ``search_mips_index`` takes a tensor
+  on any device and returns numpy ``(distances float32, indices int64)`` (:182-197), and honours
+  ``reconstruct=True`` by returning ``(distances, indices, rows [nq,k,d] float32)`` like
+  ``IndexIDMap.search_and_reconstruct``.
+
+What changes behind that surface: the reference keeps one process that owns a chunk on every
+``cuda:i``, materialises C[nq, N] in fp16, runs ``torch.topk`` over it and maps rows to ids with
+3 200 ``.item()`` calls.  Here each *rank* owns one contiguous row range (the ``torch.chunk`` split
+rule, :252-256) in its own GPU's HBM, runs one fused GEMM+top-k scan over it
+(csrc/mips_scan.cu), and — when a process group is given — the per-rank top-k lists are exchanged
+with ONE all-gather of [nq, k] (score, id) pairs and merged on every rank (csrc/mips_merge.cu).
+Scores never touch HBM and the id map is applied inside the kernel.
+
+Ranking contract: fp32-accumulated score, ties by ascending row inside a shard and ascending id in
+the cross-shard merge (include/emdr2_b200.h).  There is no CPU path: constructing an index on a
+machine without a CUDA device raises.
+"""
+import numpy as np
+import torch
+
+from . import mips as _mips
+from .store import EvidenceStore, dict_to_arrays
+
+
+def chunk_range(n, world, rank):
+    """Row range rank ``rank`` owns under torch.chunk(rows, world, dim=0) (emdr2_index.py:252):
+    chunk size ceil(n / world); trailing ranks may be short or empty."""
+    size = -(-n // world) if n else 0
+    lo = min(n, rank * size)
+    return lo, min(n, lo + size)
+
+
+def _dist_info(group):
+    import torch.distributed as dist
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+class B200BruteForceIndex(object):
+    """Brute-force inner-product top-k over evidence embeddings resident in B200 HBM.
+
+    embed_size   embedding dimension d.
+    embed_data   an ``EvidenceStore`` / ``OpenRetreivalDataStore``-like object with ``embed_data``
+                 ({doc_id: float16[d]}), ``embedding_path``, ``load_from_file()`` and ``clear()``.
+    use_gpu      accepted for signature compatibility (the reference ignores it too, :200-205).
+    group        optional torch.distributed group: rows are split across its ranks and
+                 ``search_mips_index`` becomes a collective call (same queries on every rank).
+    dtype        storage/compute dtype of the evidence matrix (float16 like the reference's store,
+                 or bfloat16).
+    """
+
+    #: factory for the per-shard searcher; tests of the host logic substitute a CPU double here.
+    searcher_factory = staticmethod(_mips.ShardSearcher)
+    merge_fn = staticmethod(_mips.merge_topk)
+
+    def __init__(self, embed_size, embed_data=None, use_gpu=False, group=None,
+                 dtype=torch.float16, device=None):
+        self.embed_size = int(embed_size)
+        self.embed_data = embed_data
+        self.use_gpu = use_gpu
+        self.group = group
+        self.dtype = dtype
+        self.world, self.rank = _dist_info(group)
+        if device is None:
+            if not torch.cuda.is_available() and self.searcher_factory is _mips.ShardSearcher:
+                raise RuntimeError("emdr2_b200 has no CPU path: a CUDA (sm_100a) device is required")
+            device = torch.device("cuda", torch.cuda.current_device()) \
+                if torch.cuda.is_available() else torch.device("cpu")
+        self.device = torch.device(device)
+        self.ngpu = self.world           # the reference's name for the number of row chunks (:204)
+        self.evidence_embeds = None      # this rank's [n_local, d] rows
+        self.indices_arr = None          # all doc ids in row order (host, int64), like :258
+        self.local_ids = None            # this rank's doc ids on the device
+        self.num_rows = 0
+        self.row_lo = self.row_hi = 0
+        self._searcher = None
+        self._set_mips_index()
+
+    # ------------------------------------------------------------------ construction / refresh
+    def _set_mips_index(self):
+        if self.embed_data is not None:
+            self.add_embed_data(self.embed_data)
+
+    def reset_index(self):
+        """Drop the resident rows and rebuild from a fresh store object (:221-230)."""
+        self._release()
+        if self.embed_data is not None:
+            path = self.embed_data.embedding_path
+            cls = type(self.embed_data)
+            self.embed_data = cls(path)
+        self._set_mips_index()
+
+    def update_index(self):
+        """Reload the store from disk and rebuild (:232-239); called after each index refresh."""
+        self._release()
+        if self.embed_data is not None:
+            self.embed_data.load_from_file()
+        self._set_mips_index()
+
+    def _release(self):
+        if self._searcher is not None:
+            self._searcher.close()
+        self._searcher = None
+        self.evidence_embeds = None
+        self.local_ids = None
+
+    def add_embed_data(self, all_embed_data):
+        """Dict store -> this rank's resident shard + id map (:241-266)."""
+        ids, rows = dict_to_arrays(all_embed_data.embed_data)
+        all_embed_data.clear()           # the index owns the data now (:263)
+        self.add_arrays(ids, rows)
+
+    def add_arrays(self, ids, rows):
+        """Bind dense arrays: ``ids`` int64 [N] and ``rows`` [N, d] (numpy float16 or a torch tensor)
+        holding ALL rows; this rank keeps only its chunk.  Use ``add_local_shard`` when each rank
+        already holds just its own range (flat store, device-generated data)."""
+        n = int(len(ids))
+        lo, hi = chunk_range(n, self.world, self.rank)
+        if n and rows.shape[1] != self.embed_size:
+            raise ValueError("rows have d=%d, index was built for d=%d" % (rows.shape[1], self.embed_size))
+        local_rows = rows[lo:hi]
+        if isinstance(local_rows, np.ndarray):
+            local_rows = torch.from_numpy(np.ascontiguousarray(local_rows))
+        local_ids = torch.from_numpy(np.ascontiguousarray(np.asarray(ids[lo:hi], dtype=np.int64)))
+        self.indices_arr = np.asarray(ids, dtype=np.int64)
+        self.add_local_shard(local_ids, local_rows, num_rows=n, row_lo=lo)
+
+    def add_local_shard(self, local_ids, local_rows, num_rows=None, row_lo=0):
+        """Bind this rank's own rows (tensor [n_local, d], any device) and ids (int64 [n_local] or
+        None for id = row_lo + 1 + row, the 1-based TSV numbering of orqa_wiki_dataset.py:192)."""
+        self._release()
+        n_local = int(local_rows.shape[0])
+        rows = local_rows.to(device=self.device, dtype=self.dtype).contiguous()
+        if rows.dim() != 2 or (n_local and rows.shape[1] != self.embed_size):
+            raise ValueError("local_rows must be [n, %d]" % self.embed_size)
+        if n_local == 0:
+            rows = rows.reshape(0, self.embed_size)
+        ids = None
+        if local_ids is not None:
+            ids = torch.as_tensor(local_ids, dtype=torch.int64).to(self.device).contiguous()
+        self.evidence_embeds = rows
+        self.local_ids = ids
+        self.row_lo, self.row_hi = int(row_lo), int(row_lo) + n_local
+        self.num_rows = int(num_rows) if num_rows is not None else n_local
+        self.chunksize = -(-self.num_rows // self.world) if self.num_rows else 0
+        self._searcher = self.searcher_factory(self.embed_size, self.dtype, self.device)
+        self._searcher.set_shard(rows, ids, id_base=self.row_lo + 1)
+
+    # ------------------------------------------------------------------ search
+    def search(self, query_embeds, top_k):
+        """Raw result: (scores float32 [nq,k], ids int64 [nq,k]) on this rank's device, ranked
+        (score desc, id asc across shards).  Collective when the index was built with a group."""
+        if self._searcher is None:
+            raise RuntimeError("MIPS index is empty: call add_embed_data/add_arrays first")
+        q = query_embeds.detach().to(device=self.device, dtype=self.dtype)
+        if q.dim() != 2 or q.shape[1] != self.embed_size:
+            raise ValueError("query_embeds must be [nq, %d]" % self.embed_size)
+        scores, ids = self._searcher.search(q, int(top_k))
+        if self.world == 1:
+            return scores, ids
+        import torch.distributed as dist
+        # ONE all-gather: (fp32 score bits, int64 id) packed as [nq, k, 2] int64
+        packed = torch.stack((scores.view(torch.int32).to(torch.int64), ids), dim=-1).contiguous()
+        nq, k = scores.shape
+        gathered = torch.empty((self.world * nq, k, 2), dtype=torch.int64, device=packed.device)
+        dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        gathered = gathered.view(self.world, nq, k, 2)
+        all_scores = gathered[..., 0].to(torch.int32).view(torch.float32).contiguous()
+        all_ids = gathered[..., 1].contiguous()
+        return self.merge_fn(all_scores, all_ids)
+
+    def search_mips_index(self, query_embeds, top_k, reconstruct=True):
+        """(distances float16 [nq,k], indices int32 [nq,k]) like emdr2_index.py:268-305.
+        ``reconstruct`` is accepted and ignored, as in the reference class."""
+        scores, ids = self.search(query_embeds, top_k)
+        return scores.to(torch.float16), ids.to(torch.int32)
+
+    def reconstruct_rows(self, ids):
+        """Rows of the given global doc ids (host lookup through indices_arr); single-rank only."""
+        if self.world != 1:
+            raise RuntimeError("reconstruct is only available on an unsharded index")
+        if self.indices_arr is None:
+            rows = ids - 1
+        else:
+            order = np.argsort(self.indices_arr, kind="stable")
+            pos = np.searchsorted(self.indices_arr[order], ids.cpu().numpy().ravel())
+            rows = torch.from_numpy(order[pos]).view(ids.shape)
+        rows = rows.to(self.device).clamp_(min=0)
+        return self.evidence_embeds[rows.view(-1)].view(tuple(ids.shape) + (self.embed_size,))
+
+
+class B200FaissMIPSIndex(B200BruteForceIndex):
+    """Same engine with FaissMIPSIndex's calling convention (emdr2_index.py:182-197)."""
+
+    def search_mips_index(self, query_embeds, top_k, reconstruct=True):
+        scores, ids = self.search(query_embeds, top_k)
+        distances = scores.cpu().numpy()
+        indices = ids.cpu().numpy()
+        if reconstruct:
+            rows = self.reconstruct_rows(ids).float().cpu().numpy()
+            return distances, indices, rows
+        return distances, indices
+
+
+__all__ = ["B200BruteForceIndex", "B200FaissMIPSIndex", "EvidenceStore", "chunk_range"]

@@ -97,9 +97,11 @@ EMDR2_API int emdr2_mips_merge(const float* dev_scores, const int64_t* dev_ids, 
                      float* dev_out_scores, int64_t* dev_out_ids, void* cuda_stream);
 
 /* Tuning / introspection. Options: "probe" (0/1, seed thresholds from a first probing tile),
- * "share" (0/1, cross-CTA threshold sharing), "max_ctas" (0 = all SMs).
+ * "share" (0/1, cross-CTA threshold sharing), "max_ctas" (0 = all SMs), "stats" (0/1, count
+ * appends/compactions), "timing" (0/1, bracket every scan launch with CUDA events on the stream).
  * Stats (of the last search, valid after the stream has been synchronised): "ctas", "tiles",
- * "stages", "smem_bytes", "appends", "compactions". */
+ * "stages", "smem_bytes", "sm_count", "appends", "compactions", "probe_wait_ns"; with "timing" on:
+ * "scan_launches" and "scan_ns" (sum of scan-kernel durations since switched on; reading resets). */
 EMDR2_API int emdr2_mips_set_option(void* handle, const char* name, int64_t value);
 EMDR2_API int emdr2_mips_get_stat(void* handle, const char* name, int64_t* out_value);
 

@@ -1,0 +1,165 @@
+"""Host-side logic on CPU: evidence store formats, the torch.chunk split rule, and the
+world_size-2 exchange (gloo) with the CUDA searcher replaced by an oracle-backed test double."""
+import os
+import pickle
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from emdr2_b200.index import B200BruteForceIndex, chunk_range
+from emdr2_b200.store import EvidenceStore, dict_to_arrays, load_flat, save_flat
+from oracle import mips as oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_chunk_range_is_torch_chunk():
+    for n in [0, 1, 7, 8, 9, 1000, 2625]:
+        for w in [1, 2, 3, 8]:
+            sizes = [c.shape[0] for c in torch.chunk(torch.empty(n, 1), w, dim=0)] if n else []
+            sizes += [0] * (w - len(sizes))
+            got = [chunk_range(n, w, r) for r in range(w)]
+            assert [hi - lo for lo, hi in got] == sizes
+            assert got[0][0] == 0 and all(got[r][1] == got[r + 1][0] for r in range(w - 1))
+            assert got == oracle.chunk_rows(n, w)
+
+
+def test_store_pickle_shards_merge_and_flat_roundtrip(tmp_path):
+    path = str(tmp_path / "evidence.pkl")
+    rng = np.random.RandomState(0)
+    rows = rng.randn(10, 8).astype(np.float32)
+    for rank, sl in enumerate([slice(0, 4), slice(4, 10)]):
+        st = EvidenceStore(path, load_from_path=False, rank=rank)
+        st.add_block_data(range(1 + sl.start, 1 + sl.stop), rows[sl])
+        with pytest.raises(ValueError):
+            st.add_block_data([1 + sl.start], rows[:1])
+        st.save_shard()
+    st0 = EvidenceStore(path, load_from_path=False, rank=0)
+    st0.add_block_data(range(1, 5), rows[:4])
+    st0.merge_shards_and_save()
+    assert not os.path.exists(st0.temp_dir_name)
+    with open(path, "rb") as f:
+        state = pickle.load(f)                       # the reference's on-disk format (:33-36)
+    assert list(state) == ["embed_data"] and len(state["embed_data"]) == 10
+    assert all(v.dtype == np.float16 for v in state["embed_data"].values())
+    loaded = EvidenceStore(path)
+    ids, arr = loaded.to_arrays()
+    assert sorted(ids.tolist()) == list(range(1, 11))
+    assert np.array_equal(arr[np.argsort(ids)], rows.astype(np.float16))
+    loaded.save_flat()
+    fids, frows = load_flat(path)
+    assert np.array_equal(fids, ids) and np.array_equal(np.asarray(frows), arr)
+    sids, srows = load_flat(path, row_range=(3, 7))
+    assert np.array_equal(sids, ids[3:7]) and np.array_equal(np.asarray(srows), arr[3:7])
+    loaded.clear()
+    assert loaded.embed_data == {}
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/megatron"), reason="reference not mounted")
+def test_store_is_interchangeable_with_the_reference_class(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_mips_golden
+    make_mips_golden.install_shims()
+    from megatron.data.emdr2_index import OpenRetreivalDataStore
+    path = str(tmp_path / "e.pkl")
+    ours = EvidenceStore(path, load_from_path=False, rank=0)
+    ours.add_block_data([5, 3, 9], np.arange(12, dtype=np.float32).reshape(3, 4))
+    ours.save_shard()
+    ours.merge_shards_and_save()
+    theirs = OpenRetreivalDataStore(path, load_from_path=True, rank=0)
+    assert list(theirs.embed_data) == [5, 3, 9]
+    for k in ours.embed_data:
+        assert np.array_equal(theirs.embed_data[k], ours.embed_data[k])
+    theirs.add_block_data([11], np.ones((1, 4), np.float32))
+    theirs.save_shard()
+    theirs.merge_shards_and_save()
+    again = EvidenceStore(path)
+    assert list(again.embed_data) == [5, 3, 9, 11]
+
+
+# ---------------------------------------------------------------- world_size-2 exchange on gloo
+class OracleSearcher(object):
+    """CPU test double with ShardSearcher's surface, backed by the oracle (tests only)."""
+
+    def __init__(self, d, dtype, device):
+        self.d = d
+
+    def set_shard(self, rows, ids, id_base=0):
+        self.rows = rows.cpu().numpy()
+        self.ids = None if ids is None else ids.cpu().numpy()
+        self.id_base = id_base
+
+    def search(self, q, k):
+        s, i = oracle.mips_topk(self.rows, q.cpu().numpy(), k, ids=self.ids, id_base=self.id_base)
+        return torch.from_numpy(s), torch.from_numpy(i)
+
+    def close(self):
+        pass
+
+
+def oracle_merge(scores, ids):
+    s, i = oracle.merge_topk(scores.numpy(), ids.numpy())
+    return torch.from_numpy(s), torch.from_numpy(i)
+
+
+class CpuDoubleIndex(B200BruteForceIndex):
+    searcher_factory = OracleSearcher
+    merge_fn = staticmethod(oracle_merge)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n, out_dir):
+    import torch.distributed as dist
+    from emdr2_b200.retriever import B200EvidenceRetriever
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank,
+                            world_size=world)
+    rng = np.random.RandomState(11)
+    rows = (rng.randint(-127, 128, size=(n, 32)) / 64).astype(np.float16)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    local_q = torch.from_numpy((np.random.RandomState(100 + rank).randint(-127, 128, size=(3, 32)) / 64)
+                               .astype(np.float16))
+    store = type("S", (), {})()
+    store.embed_data = {int(i): r for i, r in zip(ids, rows)}
+    store.embedding_path = "unused"
+    store.clear = lambda: None
+
+    class R(B200EvidenceRetriever):
+        index_cls = CpuDoubleIndex
+
+    ret = R(topk=6, embedding_size=32, store=store, allow_trivial_doc=False)
+    assert ret.topk == 7
+    lo, hi = chunk_range(n, world, rank)
+    assert (ret.mips_index.row_lo, ret.mips_index.row_hi) == (lo, hi)
+    scores, idx = ret.search_all(local_q)
+    topk_data, distance = ret.get_topk(local_q)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), scores=scores.numpy(), ids=idx.numpy(),
+             mine=np.array([t[0] for t in topk_data]), dist=distance.numpy(), q=local_q.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [101, 1])
+def test_sharded_search_world2_gloo_equals_unsharded_oracle(tmp_path, n):
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(str(tmp_path / ("r%d.npz" % i))) for i in range(world)]
+    assert np.array_equal(r[0]["scores"], r[1]["scores"]) and np.array_equal(r[0]["ids"], r[1]["ids"])
+    rng = np.random.RandomState(11)
+    rows = (rng.randint(-127, 128, size=(n, 32)) / 64).astype(np.float16)
+    allq = np.concatenate([r[0]["q"], r[1]["q"]])
+    s, i = oracle.mips_topk(rows, allq, 7, id_base=1)
+    assert np.array_equal(r[0]["scores"], s) and np.array_equal(r[0]["ids"], i)
+    for rank in range(world):
+        assert np.array_equal(r[rank]["mine"], i[3 * rank:3 * rank + 3].astype(np.int32))
+        assert r[rank]["dist"].dtype == np.float16
