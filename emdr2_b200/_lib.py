@@ -36,6 +36,25 @@ _SIGNATURES = {
     "emdr2_mips_get_stat": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p,
                                            ctypes.POINTER(ctypes.c_int64)]),
     "emdr2_mips_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "emdr2_gemm": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "emdr2_attention_fwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                           ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "emdr2_layernorm_fwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p]),
+    "emdr2_embedding_fwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }
 
 

@@ -1,0 +1,57 @@
+// Fused attention forward for the BERT towers and the T5 reader, sm_100a only, head dim 64.
+//
+//   O[b, i, h, :] = softmax_j( mask( scale * Q[b,i,h,:]·K[b,j,h,:] ) ) · V[b, j, h, :]
+//
+// Replaces ParallelAttention.forward's core (reference megatron/model/transformer.py:301-383:
+// baddbmm :309 -> FusedScaleMaskSoftmax :340 (megatron/model/fused_softmax.py:116-125, unfused
+// branch: masked_fill(mask, -10000) then softmax) -> dropout (p = 0 here) -> bmm :371 -> the
+// [b,np,sq,hn] -> [sq,b,hp] permute :377-383).  The [b,np,sq,sk] score / probability tensors of the
+// reference never exist: scores live in TMEM, probabilities in shared memory.
+//
+// Mask semantics are the reference's, not -inf: masked(i,j) = q_pad[b,i] | k_pad[b,j] |
+// (causal & j > i) and a masked score is REPLACED by -10000.0 (bert_model.py:31-33,
+// t5_model.py:28-30), so a fully masked query row attends uniformly to all sk keys.  The masks the
+// reference materialises as [b, sq, sk] bool tensors (make_attention_mask_3d(x, y) < 0.5,
+// megatron/data/mask_creation_utils.py:17-26; history mask :37-42) are exactly this outer-product /
+// triangular form, so two byte vectors and a flag carry them.
+//
+// One CTA per (128-query block, head, batch).  Per 128-key block: S = Q·Kᵀ (tcgen05, fp32 in TMEM,
+// double-buffered) -> 4 softmax warps, one thread per query row (online softmax in the log2
+// domain) -> P (16-bit) into shared memory in the K-major SW128 operand layout -> O_j = P·V_j
+// (V consumed MN-major straight from its TMA tile) -> accumulated in registers with the usual
+// running-max rescale.  K/V stream through a 3-stage TMA ring.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace emdr2 {
+
+constexpr int kAttnHeadDim = 64;
+constexpr int kAttnBQ = 128;      // query rows per CTA
+constexpr int kAttnBK = 128;      // keys per block
+constexpr int kAttnStages = 3;
+constexpr int kAttnThreads = 256; // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 softmax
+constexpr int kAttnTileBytes = kAttnBQ * kAttnHeadDim * 2;              // 16 KiB
+constexpr int kAttnSmemBytes = kAttnTileBytes                            // Q (reused for O)
+                               + kAttnStages * 2 * kAttnTileBytes        // K/V ring
+                               + 2 * kAttnTileBytes                      // P (two 64-key K blocks)
+                               + 1024 + 1024;                            // barriers + alignment
+
+struct AttnArgs {
+  uint32_t batch, heads, sq, sk;
+  uint32_t causal;
+  uint32_t idesc_s;        // M=128, N=128, A/B K-major
+  uint32_t idesc_o;        // M=128, N=64,  B MN-major
+  float scale_log2;        // scale * log2(e)
+  const uint8_t* q_pad;    // [batch, sq] or nullptr (1 = padding token)
+  const uint8_t* k_pad;    // [batch, sk] or nullptr
+  float* lse;              // [batch, heads, sq] natural-log sum-exp of the masked scores, or nullptr
+};
+
+cudaError_t attention_prepare();
+void launch_attention_fwd(const CUtensorMap& tmap_q, const CUtensorMap& tmap_k,
+                          const CUtensorMap& tmap_v, const CUtensorMap& tmap_o,
+                          const AttnArgs& args, bool bf16, cudaStream_t stream);
+
+}  // namespace emdr2

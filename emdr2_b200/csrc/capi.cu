@@ -14,79 +14,13 @@
 #include "mips_merge.cuh"
 #include "mips_scan.cuh"
 #include "ptx.cuh"
+#include "capi_common.cuh"
 
 namespace {
 
-thread_local std::string g_last_error;
-
-int fail(int code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  g_last_error = buf;
-  return code;
-}
-
-#define CUDA_TRY(expr)                                                                    \
-  do {                                                                                    \
-    cudaError_t e_ = (expr);                                                              \
-    if (e_ != cudaSuccess)                                                                \
-      return fail(EMDR2_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),    \
-                  __FILE__, __LINE__);                                                    \
-  } while (0)
-
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
-            cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-
-// 2-D row-major [rows, cols] 16-bit tensor, box = [box_rows, 64 cols], 128-B swizzle, OOB -> 0.
-int make_tmap_2d(CUtensorMap* out, int dtype, const void* base, uint64_t rows, uint64_t cols,
-                 uint32_t box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return fail(EMDR2_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  const cuuint64_t gdim[2] = {cols, rows};
-  const cuuint64_t gstride[1] = {cols * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(emdr2::kBlockK), box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapDataType dt =
-      dtype == EMDR2_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(EMDR2_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)",
-                static_cast<int>(r), static_cast<unsigned long long>(rows),
-                static_cast<unsigned long long>(cols));
-  return EMDR2_OK;
-}
-
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
-    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
+using emdr2::capi::fail;
+using emdr2::capi::make_tmap_2d;
+using emdr2::capi::DeviceGuard;
 
 struct MipsHandle {
   uint32_t magic = 0x4d495053u;  // "MIPS"
@@ -149,7 +83,7 @@ void free_workspace(MipsHandle* h) {
 
 extern "C" {
 
-const char* emdr2_last_error(void) { return g_last_error.c_str(); }
+const char* emdr2_last_error(void) { return emdr2::capi::last_error(); }
 
 const char* emdr2_version(void) {
   static char buf[96];
@@ -248,7 +182,7 @@ int emdr2_mips_set_shard(void* handle, const void* dev_rows, const int64_t* dev_
     if (reinterpret_cast<uintptr_t>(dev_rows) % 16 != 0)
       return fail(EMDR2_EINVAL, "dev_rows must be 16-byte aligned");
     int rc = make_tmap_2d(&h->tmap_e, h->dtype, dev_rows, static_cast<uint64_t>(n),
-                          static_cast<uint64_t>(h->d), emdr2::kTileN);
+                          static_cast<uint64_t>(h->d), static_cast<uint64_t>(h->d), emdr2::kTileN);
     if (rc != EMDR2_OK) return rc;
   }
   h->rows = dev_rows;
@@ -294,7 +228,7 @@ int emdr2_mips_search(void* handle, const void* dev_q, int nq, int k, float* dev
     const uint8_t* qptr = static_cast<const uint8_t*>(dev_q) + static_cast<size_t>(q0) * h->d * elt;
     CUtensorMap tmap_q;
     int rc = make_tmap_2d(&tmap_q, h->dtype, qptr, static_cast<uint64_t>(nq_pass),
-                          static_cast<uint64_t>(h->d), emdr2::kQ);
+                          static_cast<uint64_t>(h->d), static_cast<uint64_t>(h->d), emdr2::kQ);
     if (rc != EMDR2_OK) return rc;
 
     emdr2::ScanArgs a;

@@ -1,0 +1,265 @@
+// See gemm.cuh for the design. sm_100a only.
+#include "gemm.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+namespace emdr2 {
+using namespace ptx;
+
+namespace {
+
+struct GemmBars {
+  uint64_t full[kGemmStages];
+  uint64_t empty[kGemmStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(GemmBars) <= kGemmBarBytes, "barrier block too large");
+
+template <bool kBf16>
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+  if constexpr (kBf16) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+  } else {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (kBf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_d, const GemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  constexpr uint32_t off_out = kGemmStages * kGemmStageBytes;
+  constexpr uint32_t off_bar = off_out + kGemmOutBytes;
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + off_bar);
+  const uint32_t smem_base = smem_u32(smem);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t num_tiles = a.tiles_m * a.tiles_n;
+  const uint32_t num_kb = (a.K + kGemmBK - 1) / kGemmBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGemmStages; ++s) {
+      mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars->tmem_full[b]), 1);
+      mbar_init(smem_u32(&bars->tmem_empty[b]), 8);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_d);
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int32_t m0 = static_cast<int32_t>((t / a.tiles_n) * kGemmBM);
+        const int32_t n0 = static_cast<int32_t>((t % a.tiles_n) * kGemmBN);
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
+          const uint32_t fbar = smem_u32(&bars->full[stage]);
+          mbar_arrive_expect_tx(fbar, kGemmStageBytes);
+          const uint32_t sa = smem_base + stage * kGemmStageBytes;
+          tma_load_2d(sa, &tmap_a, fbar, static_cast<int32_t>(kb * kGemmBK), m0, kEvictNormal);
+          tma_load_2d(sa + kGemmStageA, &tmap_b, fbar, static_cast<int32_t>(kb * kGemmBK), n0,
+                      kEvictLast);
+          if (++stage == kGemmStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(smem_u32(&bars->tmem_empty[buf]), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kGemmBN;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&bars->full[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kGemmStageBytes;
+          const uint64_t adesc = smem_desc_sw128(sa);
+          const uint64_t bdesc = smem_desc_sw128(sa + kGemmStageA);
+#pragma unroll
+          for (int kk = 0; kk < kGemmBK / 16; ++kk)
+            mma_f16_ss(d_tmem, adesc + static_cast<uint64_t>(kk * 2),
+                       bdesc + static_cast<uint64_t>(kk * 2), a.idesc, (kb | kk) != 0 ? 1u : 0u);
+          mma_commit(smem_u32(&bars->empty[stage]));
+          if (++stage == kGemmStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        mma_commit(smem_u32(&bars->tmem_full[buf]));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue
+    const uint32_t quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const uint32_t hh = (warp - 4) >> 2;     // column half of the tile
+    const uint32_t row = quad * 32 + lane;   // tile row == TMEM lane
+    const uint32_t stage_off = off_out + hh * (kGemmBM * 64 * 2);
+    uint8_t* stage_ptr = smem + stage_off;
+    const bool issuer = (warp - 4) % 4 == 0 && lane == 0;
+    const uint32_t bar_id = 1 + hh;
+    const bool has_bias = (a.flags & kGemmBias) != 0;
+    const bool has_gelu = (a.flags & kGemmGelu) != 0;
+    const bool has_res = (a.flags & kGemmResidual) != 0;
+    const uint16_t* bias = static_cast<const uint16_t*>(a.bias);
+    const uint16_t* resid = static_cast<const uint16_t*>(a.residual);
+
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      const uint32_t m0 = (t / a.tiles_n) * kGemmBM;
+      const uint32_t n0 = (t % a.tiles_n) * kGemmBN;
+      mbar_wait(smem_u32(&bars->tmem_full[buf]), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (uint32_t ch = 0; ch < 2; ++ch) {
+        const uint32_t col0 = hh * 128 + ch * 64;
+        const bool live = n0 + col0 < a.N;
+        uint32_t v[64];
+        if (live) {
+          const uint32_t t_addr = tmem_base + ((quad * 32) << 16) + buf * kGemmBN + col0;
+          tmem_ld_32x32b_x32(t_addr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32b_x32(t_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+        }
+        if (ch == 1) {  // this warp has read everything it needs from the accumulator buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
+        }
+        if (!live) continue;
+
+        const uint32_t gcol = n0 + col0;
+        const bool row_ok = m0 + row < a.M;
+        uint32_t packed[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {  // 8 columns per group == one 16-byte chunk
+          const bool col_ok = gcol + g * 8 < a.N;
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
+          if (has_bias && col_ok) {
+            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + gcol + g * 8));
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack2<kBf16>(bw[j]);
+              x[2 * j] += f.x;
+              x[2 * j + 1] += f.y;
+            }
+          }
+          if (has_gelu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+          }
+          if (has_res && col_ok && row_ok) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
+                resid + static_cast<size_t>(m0 + row) * a.ldr + gcol + g * 8));
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack2<kBf16>(rw[j]);
+              x[2 * j] += f.x;
+              x[2 * j + 1] += f.y;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) packed[g * 4 + j] = pack2<kBf16>(x[2 * j], x[2 * j + 1]);
+        }
+
+        // staging buffer must be free: the previous TMA store has finished reading it
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(bar_id, 128);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+          *reinterpret_cast<uint4*>(stage_ptr + row * 128u + phys) =
+              make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (issuer) {
+          tma_store_2d(&tmap_d, smem_base + stage_off, static_cast<int32_t>(gcol),
+                       static_cast<int32_t>(m0));
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+cudaError_t gemm_prepare() {
+  cudaError_t e = cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              kGemmSmemBytes);
+}
+
+void launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
+                 const GemmArgs& args, bool bf16, int grid, cudaStream_t stream) {
+  if (bf16)
+    gemm_kernel<true><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(tmap_a, tmap_b, tmap_d, args);
+  else
+    gemm_kernel<false><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(tmap_a, tmap_b, tmap_d, args);
+}
+
+}  // namespace emdr2

@@ -1,0 +1,59 @@
+// Dense GEMM with fused epilogue for the BERT/T5 blocks, sm_100a only.
+//
+//   D[M,N] = epilogue( A[M,K] · B[N,K]ᵀ )      A, B, D 16-bit (fp16 or bf16), fp32 accumulate
+//
+// i.e. torch.nn.functional.linear(x, W): every projection of the reference's transformer layer
+// (megatron/mpu/layers.py:255,353 called from megatron/model/transformer.py:97,107,223,243,262,389)
+// and the tied LM head (megatron/model/language_model.py:28-42).  The epilogue fuses what the
+// reference runs as separate ATen kernels:
+//   +bias[N]                          (ColumnParallelLinear / RowParallelLinear bias add)
+//   GeLU(erf)                         (transformer.py:80,99-104, F.gelu default)
+//   +residual[M,N]                    (bias_dropout_add with dropout off, transformer.py:397-401)
+//
+// Structure (one persistent CTA per SM, 128x256 output tiles, N fastest so concurrently running
+// CTAs share A rows through L2):
+//   warp 0      TMA producer: A box 128x64, B box 256x64 elements per stage, 4-stage mbarrier ring
+//   warp 1      tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, accumulators double-buffered
+//               in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: tcgen05.ld -> bias/GeLU/residual in fp32 -> 16-bit -> swizzled smem
+//               staging -> TMA store (64-column boxes), two column halves in parallel
+// Roofline: tensor pipe (2·M·N·K flop); DRAM traffic is A once + D once (B stays in L2).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace emdr2 {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBN = 256;
+constexpr int kGemmBK = 64;
+constexpr int kGemmStages = 4;
+constexpr int kGemmThreads = 384;
+constexpr int kGemmStageA = kGemmBM * kGemmBK * 2;            // 16 KiB
+constexpr int kGemmStageB = kGemmBN * kGemmBK * 2;            // 32 KiB
+constexpr int kGemmStageBytes = kGemmStageA + kGemmStageB;    // 48 KiB
+constexpr int kGemmOutBytes = 2 * kGemmBM * 64 * 2;           // two 128x64 staging boxes
+constexpr int kGemmBarBytes = 1024;
+constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + kGemmOutBytes + kGemmBarBytes + 1024;
+
+constexpr uint32_t kGemmBias = 1u;
+constexpr uint32_t kGemmGelu = 2u;
+constexpr uint32_t kGemmResidual = 4u;
+
+struct GemmArgs {
+  uint32_t M, N, K;
+  uint32_t tiles_m, tiles_n;
+  uint32_t idesc;
+  uint32_t flags;
+  uint32_t ldr;            // residual leading dimension (elements)
+  const void* bias;        // [N] 16-bit
+  const void* residual;    // [M, ldr] 16-bit
+};
+
+cudaError_t gemm_prepare();
+void launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
+                 const GemmArgs& args, bool bf16, int grid, cudaStream_t stream);
+
+}  // namespace emdr2

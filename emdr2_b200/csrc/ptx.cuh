@@ -79,6 +79,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
       : "memory");
 }
 
+// 3-D tiled load (used with box depth 1: a 2-D tile of one batch entry; rows past the end of the
+// batch entry read as zero instead of running into the next one).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, uint32_t bar,
+                                            int32_t c0, int32_t c1, int32_t c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+      "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src_smem, int32_t c0,
+                                             int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // 2-D tiled store shared -> global (bulk group completion).
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem, int32_t c0,
                                              int32_t c1) {
@@ -131,11 +150,27 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major.
-// fmt: 0 = fp16, 1 = bf16.
-__host__ __device__ constexpr uint32_t instr_desc_f16(int fmt, int M, int N) {
+// kind::f16 instruction descriptor: fp32 accumulate; fmt: 0 = fp16, 1 = bf16.
+// a_mn / b_mn: 1 = that operand is MN-major in shared memory (bit 15 / bit 16), 0 = K-major.
+__host__ __device__ constexpr uint32_t instr_desc_f16(int fmt, int M, int N, int a_mn = 0,
+                                                      int b_mn = 0) {
   return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
+         (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// MN-major operand, 128-byte swizzle: the tile is stored [k rows][64 contiguous MN elements]
+// (128-B rows, exactly what a TMA box of 64 columns produces).  8-row k groups are `sbo` bytes
+// apart (1024 for densely packed rows); 64-element MN atoms are `lbo` bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                       uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; single issuing thread.

@@ -1,0 +1,179 @@
+// See rowops.cuh. One warp per row, 16-byte vectorised loads/stores, fp32 math.
+#include "rowops.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace emdr2 {
+namespace {
+
+constexpr int kMaxChunks = 4;  // 8 elements per lane per chunk -> h <= 1024
+
+template <bool kBf16>
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 p;
+    if constexpr (kBf16) p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    else p = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = p.x;
+    f[2 * i + 1] = p.y;
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if constexpr (kBf16) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const uint16_t* __restrict__ x, int64_t ldx, const uint16_t* __restrict__ gamma,
+                     const uint16_t* __restrict__ beta, uint16_t* __restrict__ y, int64_t ldy,
+                     int rows, int h, float eps, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint16_t* xr = x + static_cast<size_t>(row) * ldx;
+  float v[kMaxChunks][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < h) {
+      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(xr + col)), v[c]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += v[c][i];
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(h);
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < h) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[c][i] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(h) + eps);
+  uint16_t* yr = y + static_cast<size_t>(row) * ldy;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < h) {
+      float g[8], bt[8], o[8];
+      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(gamma + col)), g);
+      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(beta + col)), bt);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf((v[c][i] - mean) * rstd, g[i], bt[i]);
+      *reinterpret_cast<uint4*>(yr + col) = pack8<kBf16>(o);
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+embedding_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ types,
+                     const uint16_t* __restrict__ word, const uint16_t* __restrict__ pos,
+                     const uint16_t* __restrict__ type_emb, uint16_t* __restrict__ out, int tokens,
+                     int seq, int h, int vocab, int num_types) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= tokens) return;
+  int64_t id = ids[t];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);   // clamp: never read outside the table
+  const uint16_t* wr = word + static_cast<size_t>(id) * h;
+  const uint16_t* pr = pos + static_cast<size_t>(t % seq) * h;
+  const uint16_t* tr = nullptr;
+  if (types && type_emb) {
+    int64_t ty = types[t];
+    ty = ty < 0 ? 0 : (ty >= num_types ? num_types - 1 : ty);
+    tr = type_emb + static_cast<size_t>(ty) * h;
+  }
+  uint16_t* o = out + static_cast<size_t>(t) * h;
+  for (int col = lane * 8; col < h; col += 256) {
+    float a[8], b[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(wr + col)), a);
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(pr + col)), b);
+    // the reference adds in the 16-bit dtype: (word + pos) rounded, then + type rounded
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = a[i] + b[i];
+    if (tr) {
+      uint4 r = pack8<kBf16>(s);
+      unpack8<kBf16>(r, s);
+      float c[8];
+      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(tr + col)), c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += c[i];
+    }
+    *reinterpret_cast<uint4*>(o + col) = pack8<kBf16>(s);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_layernorm_fwd(bool bf16, const void* x, int64_t ldx, const void* gamma,
+                                 const void* beta, void* y, int64_t ldy, int rows, int h, float eps,
+                                 float* mean, float* rstd, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (h % 8 || h > kMaxChunks * 256) return cudaErrorInvalidValue;
+  const int warps = 8;
+  const int grid = (rows + warps - 1) / warps;
+  auto xs = static_cast<const uint16_t*>(x);
+  auto gs = static_cast<const uint16_t*>(gamma);
+  auto bs = static_cast<const uint16_t*>(beta);
+  auto ys = static_cast<uint16_t*>(y);
+  if (bf16)
+    layernorm_fwd_kernel<true><<<grid, warps * 32, 0, stream>>>(xs, ldx, gs, bs, ys, ldy, rows, h, eps, mean, rstd);
+  else
+    layernorm_fwd_kernel<false><<<grid, warps * 32, 0, stream>>>(xs, ldx, gs, bs, ys, ldy, rows, h, eps, mean, rstd);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_embedding_fwd(bool bf16, const int64_t* ids, const int64_t* types,
+                                 const void* word, const void* pos, const void* type_emb, void* out,
+                                 int tokens, int seq, int h, int vocab, int num_types,
+                                 cudaStream_t stream) {
+  if (tokens <= 0) return cudaSuccess;
+  if (h % 8) return cudaErrorInvalidValue;
+  const int warps = 8;
+  const int grid = (tokens + warps - 1) / warps;
+  auto ws = static_cast<const uint16_t*>(word);
+  auto ps = static_cast<const uint16_t*>(pos);
+  auto ts = static_cast<const uint16_t*>(type_emb);
+  auto os = static_cast<uint16_t*>(out);
+  if (bf16)
+    embedding_fwd_kernel<true><<<grid, warps * 32, 0, stream>>>(ids, types, ws, ps, ts, os, tokens, seq, h, vocab, num_types);
+  else
+    embedding_fwd_kernel<false><<<grid, warps * 32, 0, stream>>>(ids, types, ws, ps, ts, os, tokens, seq, h, vocab, num_types);
+  return cudaGetLastError();
+}
+
+}  // namespace emdr2

@@ -1,0 +1,24 @@
+// Row-wise HBM-bound operators of the transformer blocks: LayerNorm and the embedding sum.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace emdr2 {
+
+// y[r,:] = (x[r,:] - mean) * rsqrt(var + eps) * gamma + beta, statistics in fp32 (biased variance),
+// like torch.nn.LayerNorm / apex FusedLayerNorm (reference megatron/mpu/layers.py:28-36,
+// eps = args.layernorm_epsilon = 1e-5, megatron/arguments.py:199).  h % 8 == 0, h <= 1024.
+// mean / rstd ([rows] fp32) are optional outputs for the backward pass.
+cudaError_t launch_layernorm_fwd(bool bf16, const void* x, int64_t ldx, const void* gamma,
+                                 const void* beta, void* y, int64_t ldy, int rows, int h, float eps,
+                                 float* mean, float* rstd, cudaStream_t stream);
+
+// out[t,:] = word[ids[t],:] + pos[t % seq,:] (+ type[types[t],:]): Embedding.forward with dropout
+// off (reference megatron/model/language_model.py:169-181; position ids = arange(seq),
+// bert_model.py:51-58, t5_model.py:42-49).  ids / types int64 [tokens].
+cudaError_t launch_embedding_fwd(bool bf16, const int64_t* ids, const int64_t* types,
+                                 const void* word, const void* pos, const void* type_emb, void* out,
+                                 int tokens, int seq, int h, int vocab, int num_types,
+                                 cudaStream_t stream);
+
+}  // namespace emdr2

@@ -1,0 +1,149 @@
+"""Torch-tensor front end of the C-ABI transformer-block operators (csrc/gemm.cu, ...).
+
+PyTorch owns the memory and the stream; all arithmetic runs in libemdr2_b200.so.  No CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float16: _lib.EMDR2_DTYPE_FP16, torch.bfloat16: _lib.EMDR2_DTYPE_BF16}
+GEMM_BIAS, GEMM_GELU, GEMM_RESIDUAL = 1, 2, 4
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_2d(name, t, dtype, device):
+    if t.dim() != 2 or t.dtype != dtype or t.device != device or t.stride(1) != 1:
+        raise ValueError("%s must be a 2-D %s tensor on %s with unit inner stride" % (name, dtype, device))
+
+
+def linear(x, weight, bias=None, gelu=False, residual=None, out=None):
+    """out[m, n] = (GeLU)(x[m, k] @ weight[n, k].T + bias) + residual, fp32 accumulate.
+
+    x / residual / out may be row-strided views (e.g. a column block of a wider buffer)."""
+    if x.dtype not in _DTYPES:
+        raise TypeError("linear takes float16/bfloat16 tensors, got %s" % x.dtype)
+    if not x.is_cuda:
+        raise RuntimeError("emdr2_b200 has no CPU path")
+    dtype, device = x.dtype, x.device
+    _check_2d("x", x, dtype, device)
+    _check_2d("weight", weight, dtype, device)
+    m, k = x.shape
+    n = weight.shape[0]
+    if weight.shape[1] != k:
+        raise ValueError("weight is [%d, %d], expected [n, %d]" % (weight.shape[0], weight.shape[1], k))
+    if out is None:
+        out = torch.empty((m, n), dtype=dtype, device=device)
+    _check_2d("out", out, dtype, device)
+    flags = 0
+    if bias is not None:
+        if bias.dtype != dtype or bias.device != device or bias.numel() != n or not bias.is_contiguous():
+            raise ValueError("bias must be a contiguous [n] tensor of the same dtype/device")
+        flags |= GEMM_BIAS
+    if gelu:
+        flags |= GEMM_GELU
+    ldr = 0
+    if residual is not None:
+        _check_2d("residual", residual, dtype, device)
+        if tuple(residual.shape) != (m, n):
+            raise ValueError("residual must be [m, n]")
+        flags |= GEMM_RESIDUAL
+        ldr = residual.stride(0)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.emdr2_gemm(_DTYPES[dtype], _ptr(x), x.stride(0) if m > 1 else max(k, x.stride(0)),
+                                  _ptr(weight), weight.stride(0) if n > 1 else max(k, weight.stride(0)),
+                                  _ptr(out), out.stride(0) if m > 1 else max(n, out.stride(0)),
+                                  _ptr(bias), _ptr(residual), ldr, m, n, k, flags, _stream(device)),
+                   "emdr2_gemm")
+    return out
+
+
+def attention(q, k, v, batch, heads, sq, sk, q_pad=None, k_pad=None, causal=False, scale=None,
+              out=None, return_lse=False):
+    """Fused attention forward (head dim 64).  q/out: [batch*sq, >= heads*64] views, k/v:
+    [batch*sk, >= heads*64] views (unit inner stride; e.g. column blocks of a fused QKV buffer).
+    q_pad [batch, sq] / k_pad [batch, sk]: uint8/bool, 1 = padding.  Masked scores are replaced by
+    -10000 (the reference's attention_mask_func), not -inf."""
+    dtype, device = q.dtype, q.device
+    if dtype not in _DTYPES or not q.is_cuda:
+        raise TypeError("attention takes CUDA float16/bfloat16 tensors")
+    width = heads * 64
+    for name, t, rows in (("q", q, batch * sq), ("k", k, batch * sk), ("v", v, batch * sk)):
+        _check_2d(name, t, dtype, device)
+        if t.shape[0] != rows or t.shape[1] != width:
+            raise ValueError("%s must be [%d, %d], got %s" % (name, rows, width, tuple(t.shape)))
+    if out is None:
+        out = torch.empty((batch * sq, width), dtype=dtype, device=device)
+    _check_2d("out", out, dtype, device)
+    masks = []
+    for name, m, n in (("q_pad", q_pad, sq), ("k_pad", k_pad, sk)):
+        if m is not None:
+            m = m.to(device=device, dtype=torch.uint8).contiguous()
+            if tuple(m.shape) != (batch, n):
+                raise ValueError("%s must be [batch, %d]" % (name, n))
+        masks.append(m)
+    lse = torch.empty((batch, heads, sq), dtype=torch.float32, device=device) if return_lse else None
+    if scale is None:
+        scale = 1.0 / 8.0
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.emdr2_attention_fwd(
+            _DTYPES[dtype], _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
+            _ptr(out), out.stride(0), batch, heads, sq, sk, _ptr(masks[0]), _ptr(masks[1]),
+            1 if causal else 0, float(scale), _ptr(lse), _stream(device)), "emdr2_attention_fwd")
+    return (out, lse) if return_lse else out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None, return_stats=False):
+    """Row-wise LayerNorm of a 2-D [rows, h] view (h % 8 == 0, h <= 1024), fp32 statistics."""
+    dtype, device = x.dtype, x.device
+    if dtype not in _DTYPES or not x.is_cuda:
+        raise TypeError("layernorm takes CUDA float16/bfloat16 tensors")
+    _check_2d("x", x, dtype, device)
+    rows, h = x.shape
+    if out is None:
+        out = torch.empty((rows, h), dtype=dtype, device=device)
+    _check_2d("out", out, dtype, device)
+    mean = torch.empty(rows, dtype=torch.float32, device=device) if return_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=device) if return_stats else None
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.emdr2_layernorm_fwd(
+            _DTYPES[dtype], _ptr(x), max(h, x.stride(0)), _ptr(gamma.contiguous()), _ptr(beta.contiguous()),
+            _ptr(out), max(h, out.stride(0)), rows, h, float(eps), _ptr(mean), _ptr(rstd), _stream(device)),
+            "emdr2_layernorm_fwd")
+    return (out, mean, rstd) if return_stats else out
+
+
+def embedding(ids, word, pos, types=None, type_emb=None, seq=None):
+    """out[b*s + i] = word[ids[b,i]] + pos[i] (+ type_emb[types[b,i]]); ids int64 [b, s]."""
+    dtype, device = word.dtype, word.device
+    if dtype not in _DTYPES or not word.is_cuda:
+        raise TypeError("embedding takes CUDA float16/bfloat16 tables")
+    ids = ids.to(device=device, dtype=torch.int64).contiguous()
+    if seq is None:
+        seq = ids.shape[-1]
+    tokens = ids.numel()
+    h = word.shape[1]
+    if pos.shape[0] < seq:
+        raise ValueError("sequence length %d exceeds the position table (%d rows)" % (seq, pos.shape[0]))
+    if types is not None:
+        types = types.to(device=device, dtype=torch.int64).contiguous()
+    out = torch.empty((tokens, h), dtype=dtype, device=device)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.emdr2_embedding_fwd(
+            _DTYPES[dtype], _ptr(ids), _ptr(types), _ptr(word.contiguous()), _ptr(pos.contiguous()),
+            _ptr(type_emb.contiguous()) if type_emb is not None else None, _ptr(out), tokens, int(seq), h,
+            word.shape[0], type_emb.shape[0] if type_emb is not None else 0, _stream(device)),
+            "emdr2_embedding_fwd")
+    return out

@@ -107,6 +107,55 @@ EMDR2_API int emdr2_mips_get_stat(void* handle, const char* name, int64_t* out_v
 
 EMDR2_API int emdr2_mips_destroy(void* handle);
 
+/* ------------------------------------------------------------------------------------------------
+ * Transformer-block operators (BERT towers and the T5 reader).  All tensors are 16-bit (dtype =
+ * EMDR2_DTYPE_*), row-major, device memory, 16-byte aligned; all calls are asynchronous on
+ * `cuda_stream` and run on the calling thread's current CUDA device.
+ * ---------------------------------------------------------------------------------------------- */
+
+#define EMDR2_GEMM_BIAS 1      /* + bias[n]                                                        */
+#define EMDR2_GEMM_GELU 2      /* exact (erf) GeLU after the bias                                   */
+#define EMDR2_GEMM_RESIDUAL 4  /* + residual[m, n] after the activation                             */
+
+/* d[m,n] = epilogue(a[m,k] . b[n,k]^T): torch.nn.functional.linear with fp32 accumulation and the
+ * bias / GeLU / residual-add fused into the store.  Replaces mpu.ColumnParallelLinear /
+ * RowParallelLinear at model-parallel size 1 (megatron/mpu/layers.py:170-363) with the bias-GeLU
+ * (megatron/model/transformer.py:99-104) and bias-dropout-add at p=0 (:397-419) of the reference's
+ * layer, and parallel_lm_logits (megatron/model/language_model.py:28-42).  lda/ldb/ldd/ldr are row
+ * pitches in elements (multiples of 8); n and k multiples of 8. */
+EMDR2_API int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, int64_t ldb, void* d,
+                         int64_t ldd, const void* bias, const void* residual, int64_t ldr, int m,
+                         int n, int k, int flags, void* cuda_stream);
+
+/* Fused attention forward, head dimension 64:
+ *   o[b,i,h,:] = softmax_j(mask(scale * q[b,i,h,:].k[b,j,h,:])) . v[b,j,h,:]
+ * q/o are [batch*sq, >= heads*64] and k/v [batch*sk, >= heads*64] row-major views (row pitches
+ * ldq/ldk/ldv/ldo in elements, head h in columns h*64 .. h*64+63) - e.g. column blocks of a fused
+ * QKV projection.  Mask = q_pad[b,i] | k_pad[b,j] | (causal && j > i) (byte vectors, 1 = masked,
+ * NULL = none); a masked score is replaced by -10000 exactly as the reference's
+ * attention_mask_func does (megatron/model/bert_model.py:31-33, t5_model.py:28-30), then softmax.
+ * Replaces the baddbmm -> scale-mask-softmax -> bmm core of ParallelAttention.forward
+ * (megatron/model/transformer.py:301-383) with attention dropout off.  lse (optional) receives
+ * log(sum_j exp(masked score)) as [batch, heads, sq] fp32. */
+EMDR2_API int emdr2_attention_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                  const void* v, int64_t ldv, void* o, int64_t ldo, int batch,
+                                  int heads, int sq, int sk, const uint8_t* q_pad,
+                                  const uint8_t* k_pad, int causal, float scale, float* lse,
+                                  void* cuda_stream);
+
+/* y[r,:] = LayerNorm(x[r,:]) * gamma + beta with fp32 statistics (biased variance), h % 8 == 0,
+ * h <= 1024: mpu.LayerNorm (megatron/mpu/layers.py:28-36).  mean/rstd: optional [rows] fp32. */
+EMDR2_API int emdr2_layernorm_fwd(int dtype, const void* x, int64_t ldx, const void* gamma,
+                                  const void* beta, void* y, int64_t ldy, int rows, int h, float eps,
+                                  float* mean, float* rstd, void* cuda_stream);
+
+/* out[t,:] = word[ids[t]] + pos[t % seq] (+ type_emb[types[t]]): Embedding.forward with dropout off
+ * (megatron/model/language_model.py:169-181).  ids/types: int64 [tokens] device arrays. */
+EMDR2_API int emdr2_embedding_fwd(int dtype, const int64_t* ids, const int64_t* types,
+                                  const void* word, const void* pos, const void* type_emb, void* out,
+                                  int tokens, int seq, int h, int vocab, int num_types,
+                                  void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

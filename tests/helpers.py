@@ -66,3 +66,42 @@ def to_oracle_input(t):
     if t.dtype == torch.float16:
         return t.numpy()
     return t.view(torch.int16).numpy().view(np.uint16)
+
+
+# ------------------------------------------------------------------ tiny BERT/T5 config (blocks)
+TINY = dict(hidden=128, heads=2, layers=2, ffn=256, vocab=128, max_pos=64)
+
+
+def seeded_weights(name, shape):
+    """Deterministic parameter values keyed by the parameter's name (shared by the script that ran
+    the reference and by the tests, so fixtures hold no weights).  CPU generator: identical bits in
+    the build container and on the GPU box (same image)."""
+    import zlib
+    import torch
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    w = torch.randn(shape, generator=g)
+    if "layernorm" in name and name.endswith("weight"):
+        return 1.0 + 0.1 * w
+    if len(shape) >= 2:
+        return 0.08 * w
+    return 0.05 * w
+
+
+def tiny_inputs():
+    """Seeded token ids with ragged padding (pad id 0) for the tiny BERT tower and T5 reader."""
+    rng = np.random.RandomState(4321)
+    v = TINY["vocab"]
+
+    def ragged(b, s, lo):
+        ids = rng.randint(1, v, size=(b, s)).astype(np.int64)
+        lens = rng.randint(lo, s + 1, size=b)
+        lens[0] = s
+        for i, n in enumerate(lens):
+            ids[i, n:] = 0
+        return ids
+
+    bert_ids = ragged(6, 48, 5)
+    bert_types = (rng.rand(6, 48) < 0.5).astype(np.int64) * (bert_ids > 0)
+    b, k, s = 2, 3, 40
+    return dict(bert_ids=bert_ids, bert_types=bert_types, t5_enc_ids=ragged(b * k, s, 7),
+                t5_dec_ids=ragged(b * k, 12, 2), fid_shape=(b, k, s))
