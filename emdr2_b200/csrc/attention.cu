@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace emdr2 {
@@ -19,8 +21,8 @@ struct AttnBars {
   uint64_t q_full;
   uint64_t kv_full[kAttnStages];
   uint64_t kv_empty[kAttnStages];
-  uint64_t s_full[2];
-  uint64_t s_empty[2];
+  uint64_t s_full;
+  uint64_t s_empty;
   uint64_t p_full;
   uint64_t o_full;
   uint32_t tmem_base;
@@ -43,15 +45,24 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
+static_assert(sizeof(AttnBars) <= kAttnBarBytes, "barrier block too large");
+
+template <int kRegs>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
 template <bool kBf16>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
                      const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v,
                      const __grid_constant__ CUtensorMap tmap_o, const AttnArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // SW128 tiles need 1024-B alignment
   constexpr uint32_t off_q = 0;
   constexpr uint32_t off_kv = kAttnTileBytes;
   constexpr uint32_t off_p = off_kv + kAttnStages * 2 * kAttnTileBytes;
@@ -73,10 +84,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(smem_u32(&bars->kv_full[s]), 1);
       mbar_init(smem_u32(&bars->kv_empty[s]), 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars->s_full[i]), 1);
-      mbar_init(smem_u32(&bars->s_empty[i]), 4);
-    }
+    mbar_init(smem_u32(&bars->s_full), 1);
+    mbar_init(smem_u32(&bars->s_empty), 4);
     mbar_init(smem_u32(&bars->p_full), 4);
     mbar_init(smem_u32(&bars->o_full), 1);
     fence_mbar_init();
@@ -89,15 +98,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
     prefetch_tmap(&tmap_o);
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_alloc(smem_u32(&bars->tmem_base), kAttnTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const uint32_t tmem_o = tmem_base + 2 * kAttnBK;
+  const uint32_t tmem_o = tmem_base + kAttnBK;
 
+  if (warp < 4) {
+  reg_dealloc<40>();   // warpgroup 0 (TMA, MMA, allocator, spare) hands its registers to the softmax warps
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
@@ -129,16 +140,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const uint64_t qdesc = smem_desc_sw128(smem_base + off_q);
       uint32_t ld_stage = 0, ld_phase = 0;  // stage/phase of the next S block to issue
       auto issue_s = [&](uint32_t j) {
-        const uint32_t sb = j & 1;
         mbar_wait(smem_u32(&bars->kv_full[ld_stage]), ld_phase);
-        mbar_wait(smem_u32(&bars->s_empty[sb]), ((j >> 1) & 1) ^ 1);
+        mbar_wait(smem_u32(&bars->s_empty), (j & 1) ^ 1);
         tc_fence_after();
         const uint64_t kdesc = smem_desc_sw128(smem_base + off_kv + ld_stage * 2 * kAttnTileBytes);
 #pragma unroll
         for (int kk = 0; kk < kAttnHeadDim / 16; ++kk)
-          mma_f16_ss(tmem_base + sb * kAttnBK, qdesc + static_cast<uint64_t>(kk * 2),
+          mma_f16_ss(tmem_base, qdesc + static_cast<uint64_t>(kk * 2),
                      kdesc + static_cast<uint64_t>(kk * 2), a.idesc_s, kk != 0 ? 1u : 0u);
-        mma_commit(smem_u32(&bars->s_full[sb]));
+        mma_commit(smem_u32(&bars->s_full));
         if (++ld_stage == kAttnStages) {
           ld_stage = 0;
           ld_phase ^= 1;
@@ -165,8 +175,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (++stage == kAttnStages) stage = 0;
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ===================================================== softmax + output (one thread per row)
+    reg_alloc<216>();
     const uint32_t quad = warp & 3;
     const uint32_t row = quad * 32 + lane;
     const uint32_t qi = q0 + row;
@@ -196,89 +208,108 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
     };
 
     for (uint32_t j = 0; j < nblk; ++j) {
-      const uint32_t sb = j & 1;
       const uint32_t kb0 = j * kAttnBK;
-      mbar_wait(smem_u32(&bars->s_full[sb]), (j >> 1) & 1);
+      mbar_wait(smem_u32(&bars->s_full), j & 1);
       tc_fence_after();
-      uint32_t v[kAttnBK];
       float alpha = 1.f;
+      float m_new = m_run;
+      uint32_t t[64];   // scores as raw fp32 bits (tcgen05.ld output registers)
+      // ---- key-side mask bits of this block (same in every warp), 32 keys per word
+      uint32_t km[4] = {0u, 0u, 0u, 0u};
+      uint32_t valid = kAttnBK;
+      bool plain = true;
       if (warp_active) {
-        const uint32_t s_addr = tmem_base + lane_tmem + sb * kAttnBK;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          tmem_ld_32x32b_x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[sb]));
-
-      if (warp_active) {
-        // ---- key-side mask bits of this block (same in every warp), 32 keys per word
-        uint32_t km[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t idx = kb0 + c * 32 + lane;
           const bool f = a.k_pad && idx < a.sk && a.k_pad[static_cast<size_t>(b) * a.sk + idx] != 0;
           km[c] = __ballot_sync(kFull, f);
         }
-        const uint32_t valid = min(static_cast<uint32_t>(kAttnBK), a.sk - kb0);
+        valid = min(static_cast<uint32_t>(kAttnBK), a.sk - kb0);
         const bool causal_hit = a.causal && (kb0 + kAttnBK - 1 > qi);
-        const bool plain = !q_is_pad && !causal_hit && valid == kAttnBK &&
-                           (km[0] | km[1] | km[2] | km[3]) == 0u;
+        plain = !q_is_pad && !causal_hit && valid == kAttnBK && (km[0] | km[1] | km[2] | km[3]) == 0u;
+      }
+      // Loads the scores of keys [half*64, half*64+64) of the block into t as masked log2-domain
+      // values and returns their maximum.  Half 0 is read twice (max pass, then exp pass) so that
+      // only 64 scores are ever live next to the 64 output accumulators.
+      auto load_scores = [&](auto half_c) -> float {
+        constexpr int half = decltype(half_c)::value;
+        const uint32_t s_addr = tmem_base + lane_tmem + half * 64;
+        tmem_ld_32x32b_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&t[0]));
+        tmem_ld_32x32b_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&t[32]));
+        tmem_ld_wait();
         float mx = __uint_as_float(0xff800000u);
         if (plain) {
 #pragma unroll
-          for (int c = 0; c < kAttnBK; ++c) {
-            const float t = __uint_as_float(v[c]) * a.scale_log2;
-            v[c] = __float_as_uint(t);
-            mx = fmaxf(mx, t);
+          for (int c = 0; c < 64; ++c) {
+            const float x = __uint_as_float(t[c]) * a.scale_log2;
+            t[c] = __float_as_uint(x);
+            mx = fmaxf(mx, x);
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < kAttnBK; ++c) {
-            float t = __uint_as_float(v[c]) * a.scale_log2;
-            const bool masked = q_is_pad || ((km[c >> 5] >> (c & 31)) & 1u) ||
-                                (a.causal && kb0 + c > qi);
-            t = masked ? kMaskedLog2 : t;
-            t = (static_cast<uint32_t>(c) < valid) ? t : __uint_as_float(0xff800000u);
-            v[c] = __float_as_uint(t);
-            mx = fmaxf(mx, t);
+          for (int c = 0; c < 64; ++c) {
+            const uint32_t cc = half * 64 + c;
+            float x = __uint_as_float(t[c]) * a.scale_log2;
+            const bool masked = q_is_pad || ((km[cc >> 5] >> (cc & 31)) & 1u) ||
+                                (a.causal && kb0 + cc > qi);
+            x = masked ? kMaskedLog2 : x;
+            x = (cc < valid) ? x : __uint_as_float(0xff800000u);
+            t[c] = __float_as_uint(x);
+            mx = fmaxf(mx, x);
           }
         }
-        const float m_new = fmaxf(m_run, mx);
-        alpha = ex2(m_run - m_new);
+        return mx;
+      };
+      // exp2(t - m_new) of the 64 live scores -> 16-bit -> P rows in shared memory; returns the sum
+      auto write_probs = [&](auto half_c) -> float {
+        constexpr int half = decltype(half_c)::value;
         float sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < kAttnBK; c += 2) {
-          const float p0 = ex2(__uint_as_float(v[c]) - m_new);
-          const float p1 = ex2(__uint_as_float(v[c + 1]) - m_new);
-          sum += p0 + p1;
-          v[c >> 1] = pack2<kBf16>(p0, p1);
+        for (int g = 0; g < 8; ++g) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float p0 = ex2(__uint_as_float(t[g * 8 + 2 * i]) - m_new);
+            const float p1 = ex2(__uint_as_float(t[g * 8 + 2 * i + 1]) - m_new);
+            sum += p0 + p1;
+            w[i] = pack2<kBf16>(p0, p1);
+          }
+          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+          *reinterpret_cast<uint4*>(p_row + half * kAttnTileBytes + phys) =
+              make_uint4(w[0], w[1], w[2], w[3]);
         }
-        l_run = fmaf(l_run, alpha, sum);
-        m_run = m_new;
-      }
+        return sum;
+      };
 
-      // O_{j-1} must have landed (and P's buffer be free) before P_j is written
+      // O_{j-1} must have landed (and P's buffer be free) before P_j is written; folding it in
+      // first keeps the score registers and the tcgen05.ld staging registers from overlapping
       if (j > 0) {
         mbar_wait(smem_u32(&bars->o_full), (j - 1) & 1);
         tc_fence_after();
         if (warp_active) accumulate_o(alpha_prev);
       }
+      if (warp_active) {
+        const float mx0 = load_scores(std::integral_constant<int, 0>{});
+        const float mx1 = load_scores(std::integral_constant<int, 1>{});   // t holds the second half
+        m_new = fmaxf(m_run, fmaxf(mx0, mx1));
+        alpha = ex2(m_run - m_new);
+      }
       alpha_prev = alpha;
       if (warp_active) {
-#pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          const uint32_t phys = (static_cast<uint32_t>(g & 7) ^ (row & 7u)) * 16u;
-          *reinterpret_cast<uint4*>(p_row + (g >> 3) * kAttnTileBytes + phys) =
-              make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        }
+        float sum = write_probs(std::integral_constant<int, 1>{});
+        load_scores(std::integral_constant<int, 0>{});
+        sum += write_probs(std::integral_constant<int, 0>{});
+        l_run = fmaf(l_run, alpha, sum);
+        m_run = m_new;
         fence_proxy_async_smem();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->p_full));
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bars->s_empty));
+        mbar_arrive(smem_u32(&bars->p_full));
+      }
     }
 
     mbar_wait(smem_u32(&bars->o_full), (nblk - 1) & 1);
@@ -311,7 +342,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, kAttnTmemCols);
 }
 
 }  // namespace

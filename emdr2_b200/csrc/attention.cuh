@@ -19,7 +19,8 @@
 // double-buffered) -> 4 softmax warps, one thread per query row (online softmax in the log2
 // domain) -> P (16-bit) into shared memory in the K-major SW128 operand layout -> O_j = P·V_j
 // (V consumed MN-major straight from its TMA tile) -> accumulated in registers with the usual
-// running-max rescale.  K/V stream through a 3-stage TMA ring.
+// running-max rescale.  K/V stream through a 2-stage TMA ring.  Two CTAs are resident per SM
+// (setmaxnreg moves registers from the TMA/MMA warps to the softmax warps to make that fit).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -30,13 +31,17 @@ namespace emdr2 {
 constexpr int kAttnHeadDim = 64;
 constexpr int kAttnBQ = 128;      // query rows per CTA
 constexpr int kAttnBK = 128;      // keys per block
-constexpr int kAttnStages = 3;
+constexpr int kAttnStages = 2;
 constexpr int kAttnThreads = 256; // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 softmax
 constexpr int kAttnTileBytes = kAttnBQ * kAttnHeadDim * 2;              // 16 KiB
+// 112 KiB of tiles + 256 B of barriers: two CTAs fit one SM (2 x 113 KiB), so one CTA's TMA / MMA /
+// softmax latencies are hidden behind the other's; TMEM is split 256 + 256 columns.
+constexpr int kAttnBarBytes = 256;
 constexpr int kAttnSmemBytes = kAttnTileBytes                            // Q (reused for O)
                                + kAttnStages * 2 * kAttnTileBytes        // K/V ring
                                + 2 * kAttnTileBytes                      // P (two 64-key K blocks)
-                               + 1024 + 1024;                            // barriers + alignment
+                               + kAttnBarBytes;
+constexpr int kAttnTmemCols = 256;                                       // S [0,128) + O [128,192)
 
 struct AttnArgs {
   uint32_t batch, heads, sq, sk;

@@ -58,10 +58,14 @@ int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, int64_t ldb
     CUDA_TRY(emdr2::gemm_prepare());
     prepared[info.device] = true;
   }
-  CUtensorMap ta, tb, td;
+  CUtensorMap ta, tb, td, tr;
   if ((rc = make_tmap_2d(&ta, dtype, a, m, k, lda, emdr2::kGemmBM)) != EMDR2_OK) return rc;
   if ((rc = make_tmap_2d(&tb, dtype, b, n, k, ldb, emdr2::kGemmBN)) != EMDR2_OK) return rc;
   if ((rc = make_tmap_2d(&td, dtype, d, m, n, ldd, emdr2::kGemmBM)) != EMDR2_OK) return rc;
+  tr = td;
+  if ((flags & EMDR2_GEMM_RESIDUAL) &&
+      (rc = make_tmap_2d(&tr, dtype, residual, m, n, ldr, emdr2::kGemmBM)) != EMDR2_OK)
+    return rc;
   emdr2::GemmArgs ga;
   ga.M = m;
   ga.N = n;
@@ -70,12 +74,10 @@ int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, int64_t ldb
   ga.tiles_n = (n + emdr2::kGemmBN - 1) / emdr2::kGemmBN;
   ga.idesc = emdr2::ptx::instr_desc_f16(dtype == EMDR2_DTYPE_BF16 ? 1 : 0, emdr2::kGemmBM, emdr2::kGemmBN);
   ga.flags = static_cast<uint32_t>(flags);
-  ga.ldr = static_cast<uint32_t>(ldr);
   ga.bias = bias;
-  ga.residual = residual;
   const uint32_t tiles = ga.tiles_m * ga.tiles_n;
   const int grid = static_cast<int>(tiles < static_cast<uint32_t>(info.sm_count) ? tiles : info.sm_count);
-  emdr2::launch_gemm(ta, tb, td, ga, dtype == EMDR2_DTYPE_BF16, grid, static_cast<cudaStream_t>(cuda_stream));
+  emdr2::launch_gemm(ta, tb, td, tr, ga, dtype == EMDR2_DTYPE_BF16, grid, static_cast<cudaStream_t>(cuda_stream));
   CUDA_TRY(cudaGetLastError());
   return EMDR2_OK;
 }
@@ -169,6 +171,24 @@ int emdr2_embedding_fwd(int dtype, const int64_t* ids, const int64_t* types, con
   CUDA_TRY(emdr2::launch_embedding_fwd(dtype == EMDR2_DTYPE_BF16, ids, types, word, pos, type_emb, out,
                                        tokens, seq, h, vocab, num_types,
                                        static_cast<cudaStream_t>(cuda_stream)));
+  return EMDR2_OK;
+}
+
+int emdr2_token_logprob(int dtype, const void* logits, int64_t ld, const int64_t* labels,
+                        float* logprob, float* lse, int rows, int vocab, void* cuda_stream) {
+  if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
+    return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
+  if (rows < 0 || vocab < 1 || ld < vocab)
+    return fail(EMDR2_EINVAL, "token_logprob needs rows >= 0, vocab >= 1, ld >= vocab");
+  if (rows == 0) return EMDR2_OK;
+  if (!logits || !labels || !logprob) return fail(EMDR2_EINVAL, "NULL pointer passed to emdr2_token_logprob");
+  if ((vocab % 8 == 0) && (ld % 8 == 0) && !aligned16(logits))
+    return fail(EMDR2_EINVAL, "logits must be 16-byte aligned");
+  DeviceInfo info;
+  int rc = require_b200(&info);
+  if (rc != EMDR2_OK) return rc;
+  CUDA_TRY(emdr2::launch_token_logprob(dtype == EMDR2_DTYPE_BF16, logits, ld, labels, logprob, lse, rows,
+                                       vocab, static_cast<cudaStream_t>(cuda_stream)));
   return EMDR2_OK;
 }
 

@@ -16,6 +16,7 @@ struct GemmBars {
   uint64_t empty[kGemmStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full[2];    // residual box landed in the staging buffer of column half 0 / 1
   uint32_t tmem_base;
 };
 static_assert(sizeof(GemmBars) <= kGemmBarBytes, "barrier block too large");
@@ -39,8 +40,22 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
+// GeLU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7,
+// far below the 16-bit output rounding): 2 MUFU + ~12 FP32 ops instead of erff's two-branch
+// polynomial, which made the h -> 4h GEMM epilogue-bound.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float q = 0.5f * poly * e;          // 0.5 * (1 - erf(|x| / sqrt 2))
+  return x >= 0.f ? fmaf(-x, q, x) : x * q;
 }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
@@ -50,7 +65,8 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 template <bool kBf16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const __grid_constant__ CUtensorMap tmap_d, const GemmArgs a) {
+            const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
+            const GemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -72,6 +88,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bars->tmem_full[b]), 1);
       mbar_init(smem_u32(&bars->tmem_empty[b]), 8);
+      mbar_init(smem_u32(&bars->res_full[b]), 1);
     }
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -80,6 +97,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_d);
+    if (a.flags & kGemmResidual) prefetch_tmap(&tmap_r);
   }
   if (warp == 2) {
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
@@ -153,7 +171,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const bool has_gelu = (a.flags & kGemmGelu) != 0;
     const bool has_res = (a.flags & kGemmResidual) != 0;
     const uint16_t* bias = static_cast<const uint16_t*>(a.bias);
-    const uint16_t* resid = static_cast<const uint16_t*>(a.residual);
+    const uint32_t res_bar = smem_u32(&bars->res_full[hh]);
+    uint32_t res_phase = 0;
+
+    // The residual tile of a chunk is fetched by TMA into the chunk's own staging buffer (coalesced,
+    // asynchronous) and the result overwrites it in place.  `load_residual(t, ch)` is called by the
+    // issuer thread as soon as the buffer is free, i.e. one chunk ahead of its use.
+    auto chunk_live = [&](uint32_t t, uint32_t ch) {
+      return t < num_tiles && (t % a.tiles_n) * kGemmBN + hh * 128 + ch * 64 < a.N;
+    };
+    auto load_residual = [&](uint32_t t, uint32_t ch) {
+      mbar_arrive_expect_tx(res_bar, kGemmBM * 64 * 2);
+      tma_load_2d(smem_base + stage_off, &tmap_r, res_bar,
+                  static_cast<int32_t>((t % a.tiles_n) * kGemmBN + hh * 128 + ch * 64),
+                  static_cast<int32_t>((t / a.tiles_n) * kGemmBM), kEvictNormal);
+    };
+    if (has_res && issuer && chunk_live(blockIdx.x, 0)) load_residual(blockIdx.x, 0);
 
     uint32_t it = 0;
     for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -181,11 +214,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (!live) continue;
 
         const uint32_t gcol = n0 + col0;
-        const bool row_ok = m0 + row < a.M;
-        uint32_t packed[32];
+        if (has_res) {
+          mbar_wait(res_bar, res_phase);   // residual box is in the staging buffer
+          res_phase ^= 1;
+        } else {
+          // staging buffer must be free: the previous TMA store has finished reading it
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, 128);
+        }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {  // 8 columns per group == one 16-byte chunk
           const bool col_ok = gcol + g * 8 < a.N;
+          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+          uint4* slot = reinterpret_cast<uint4*>(stage_ptr + row * 128u + phys);
           float x[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
@@ -203,9 +244,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
           }
-          if (has_res && col_ok && row_ok) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
-                resid + static_cast<size_t>(m0 + row) * a.ldr + gcol + g * 8));
+          if (has_res) {   // out-of-range rows / columns were zero-filled by the TMA load
+            const uint4 rv = *slot;
             const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -214,18 +254,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               x[2 * j + 1] += f.y;
             }
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) packed[g * 4 + j] = pack2<kBf16>(x[2 * j], x[2 * j + 1]);
-        }
-
-        // staging buffer must be free: the previous TMA store has finished reading it
-        if (issuer) tma_store_wait_read<0>();
-        named_bar_sync(bar_id, 128);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
-          *reinterpret_cast<uint4*>(stage_ptr + row * 128u + phys) =
-              make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+          *slot = make_uint4(pack2<kBf16>(x[0], x[1]), pack2<kBf16>(x[2], x[3]),
+                             pack2<kBf16>(x[4], x[5]), pack2<kBf16>(x[6], x[7]));
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
@@ -233,6 +263,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tma_store_2d(&tmap_d, smem_base + stage_off, static_cast<int32_t>(gcol),
                        static_cast<int32_t>(m0));
           tma_store_commit();
+          if (has_res) {   // prefetch the residual of this group's next live chunk
+            uint32_t nt = t, nch = ch + 1;
+            if (nch == 2 || !chunk_live(nt, nch)) {
+              nt = t + gridDim.x;
+              nch = 0;
+            }
+            if (chunk_live(nt, nch)) {
+              tma_store_wait_read<0>();
+              load_residual(nt, nch);
+            }
+          }
         }
       }
     }
@@ -255,11 +296,12 @@ cudaError_t gemm_prepare() {
 }
 
 void launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
-                 const GemmArgs& args, bool bf16, int grid, cudaStream_t stream) {
+                 const CUtensorMap& tmap_r, const GemmArgs& args, bool bf16, int grid,
+                 cudaStream_t stream) {
   if (bf16)
-    gemm_kernel<true><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(tmap_a, tmap_b, tmap_d, args);
+    gemm_kernel<true><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(tmap_a, tmap_b, tmap_d, tmap_r, args);
   else
-    gemm_kernel<false><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(tmap_a, tmap_b, tmap_d, args);
+    gemm_kernel<false><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(tmap_a, tmap_b, tmap_d, tmap_r, args);
 }
 
 }  // namespace emdr2

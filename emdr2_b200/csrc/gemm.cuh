@@ -17,7 +17,8 @@
 //               in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warp 2      TMEM allocator
 //   warps 4-11  epilogue: tcgen05.ld -> bias/GeLU/residual in fp32 -> 16-bit -> swizzled smem
-//               staging -> TMA store (64-column boxes), two column halves in parallel
+//               staging -> TMA store (64-column boxes), two column halves in parallel; the residual
+//               tile is prefetched by TMA into the same staging buffer one chunk ahead
 // Roofline: tensor pipe (2·M·N·K flop); DRAM traffic is A once + D once (B stays in L2).
 #pragma once
 #include <cuda.h>
@@ -47,13 +48,14 @@ struct GemmArgs {
   uint32_t tiles_m, tiles_n;
   uint32_t idesc;
   uint32_t flags;
-  uint32_t ldr;            // residual leading dimension (elements)
   const void* bias;        // [N] 16-bit
-  const void* residual;    // [M, ldr] 16-bit
 };
 
 cudaError_t gemm_prepare();
+// tmap_r describes the residual [M, N] (box 128 x 64) and is only read with kGemmResidual; pass
+// tmap_d otherwise.
 void launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
-                 const GemmArgs& args, bool bf16, int grid, cudaStream_t stream);
+                 const CUtensorMap& tmap_r, const GemmArgs& args, bool bf16, int grid,
+                 cudaStream_t stream);
 
 }  // namespace emdr2

@@ -137,7 +137,88 @@ embedding_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict_
   }
 }
 
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+token_logprob_kernel(const uint16_t* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
+                     float* __restrict__ logprob, float* __restrict__ lse_out, int vocab) {
+  __shared__ float s_max[8], s_sum[8];
+  const int row = blockIdx.x;
+  const uint16_t* lr = logits + static_cast<size_t>(row) * ld;
+  // online (max, sum exp) per thread over 16-byte chunks
+  float m = -INFINITY, s = 0.f;
+  const bool vec = (vocab % 8 == 0) && (ld % 8 == 0);
+  if (!vec) {  // odd vocabulary sizes (toy configurations): element-wise loads
+    for (int col = threadIdx.x; col < vocab; col += 256) {
+      const uint16_t raw = lr[col];
+      float x;
+      if constexpr (kBf16) x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&raw));
+      else x = __half2float(*reinterpret_cast<const __half*>(&raw));
+      const float nm = fmaxf(m, x);
+      s = s * __expf(m - nm) + __expf(x - nm);
+      m = nm;
+    }
+  }
+  for (int col = threadIdx.x * 8; vec && col < vocab; col += 256 * 8) {
+    float f[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(lr + col)), f);
+    float cm = f[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) cm = fmaxf(cm, f[i]);
+    const float nm = fmaxf(m, cm);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += __expf(f[i] - nm);
+    s = s * __expf(m - nm) + acc;
+    m = nm;
+  }
+  // warp, then block combine of (m, s)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const float os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float nm = fmaxf(m, om);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - nm)) + (om == -INFINITY ? 0.f : os * __expf(om - nm));
+    m = nm;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_max[threadIdx.x >> 5] = m;
+    s_sum[threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bm = s_max[0], bs = s_sum[0];
+    for (int w = 1; w < 8; ++w) {
+      const float om = s_max[w], os = s_sum[w];
+      const float nm = fmaxf(bm, om);
+      bs = (bm == -INFINITY ? 0.f : bs * __expf(bm - nm)) + (om == -INFINITY ? 0.f : os * __expf(om - nm));
+      bm = nm;
+    }
+    const float lse = bm + logf(bs);
+    if (lse_out) lse_out[row] = lse;
+    const int64_t lab = labels[row];
+    float lp = 0.f;
+    if (lab >= 0 && lab < vocab) {
+      const uint16_t raw = lr[lab];
+      float x;
+      if constexpr (kBf16) x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&raw));
+      else x = __half2float(*reinterpret_cast<const __half*>(&raw));
+      lp = x - lse;
+    }
+    logprob[row] = lp;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_token_logprob(bool bf16, const void* logits, int64_t ld, const int64_t* labels,
+                                 float* logprob, float* lse, int rows, int vocab,
+                                 cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  auto ls = static_cast<const uint16_t*>(logits);
+  if (bf16) token_logprob_kernel<true><<<rows, 256, 0, stream>>>(ls, ld, labels, logprob, lse, vocab);
+  else token_logprob_kernel<false><<<rows, 256, 0, stream>>>(ls, ld, labels, logprob, lse, vocab);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_layernorm_fwd(bool bf16, const void* x, int64_t ldx, const void* gamma,
                                  const void* beta, void* y, int64_t ldy, int rows, int h, float eps,

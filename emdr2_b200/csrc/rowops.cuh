@@ -21,4 +21,13 @@ cudaError_t launch_embedding_fwd(bool bf16, const int64_t* ids, const int64_t* t
                                  int tokens, int seq, int h, int vocab, int num_types,
                                  cudaStream_t stream);
 
+// logprob[r] = logits[r, labels[r]] - log(sum_v exp(logits[r, v])) and lse[r] = that log-sum-exp:
+// the log_softmax + gather of the reader / retriever losses (reference
+// tasks/openqa/e2eqa/train_e2eqa.py:82-98 and the CrossEntropyLoss at :156-160) in one pass over
+// the logits, fp32 math.  labels outside [0, vocab) give logprob 0.  16-byte loads when vocab and
+// ld are multiples of 8, element-wise otherwise.
+cudaError_t launch_token_logprob(bool bf16, const void* logits, int64_t ld, const int64_t* labels,
+                                 float* logprob, float* lse, int rows, int vocab,
+                                 cudaStream_t stream);
+
 }  // namespace emdr2

@@ -1,0 +1,126 @@
+"""Passage -> model-input formatting of the retrieve-and-read step (host side, integer work).
+
+Mirrors reference megatron/model/emdr2_model.py:250-376 (`postprocess`,
+`query_extended_context_t5_format`, `query_single_context_t5_format`) and
+megatron/data/orqa_wiki_dataset.py:86-120 (`build_tokens_types_paddings_from_ids`, imported there
+as `context_bert_format`): same names, argument order and outputs — element for element — but
+written over preallocated numpy rows instead of growing Python lists, and returning one pinned
+host block per tensor so the four uploads are single async copies.
+
+Layouts produced (all int64):
+  context ids / types   [B, K, S_ret]   [CLS] title [SEP] passage [SEP] pad...        (types all 0)
+  extended              [B*K, S]        query title [SEP] passage(+neighbour fill) [SEP] pad...
+  single                [B*K, S]        query title [SEP] passage [SEP] pad...
+"""
+import numpy as np
+import torch
+
+
+def build_tokens_types_paddings_from_ids(text_ids, max_seq_length, cls_id, sep_id, pad_id):
+    """[CLS] text (cut to max_seq_length-2 tokens) [SEP] pad...; returns (ids, types, pad_mask)."""
+    body = list(text_ids)[:max(0, max_seq_length - 2)]
+    n = len(body) + 2
+    ids = [cls_id] + body + [sep_id] + [pad_id] * (max_seq_length - n)
+    types = [0] * n + [pad_id] * (max_seq_length - n)
+    pad_mask = np.zeros(max(max_seq_length, n), dtype=np.int64)
+    pad_mask[:n] = 1
+    return ids, types, pad_mask
+
+
+context_bert_format = build_tokens_types_paddings_from_ids
+
+
+def _fill_context(context_doc_list, main_doc_idx, room):
+    """The passage plus as much of its neighbours as fits in `room` tokens (emdr2_model.py:309-350)."""
+    main = list(context_doc_list[main_doc_idx])
+    if len(main) > room or len(context_doc_list) == 1:
+        return main[:room]
+    spare = room - len(main)
+    if main_doc_idx == 0:                       # neighbours follow the passage
+        tail = [t for doc in context_doc_list[1:] for t in doc]
+        return main + tail[:spare]
+    if main_doc_idx == -1:                      # neighbours precede the passage
+        head = [t for doc in context_doc_list[:-1] for t in doc]
+        if len(head) > spare:
+            head = head[len(head) - spare + 1:]          # the reference keeps spare-1 tokens here
+        return head + main
+    left = list(context_doc_list[0])            # passage in the middle
+    if len(left) > spare:
+        return left[len(left) - spare + 1:] + main
+    out = left + main
+    if len(context_doc_list) == 3:
+        out = out + list(context_doc_list[2])[:spare - len(left)]
+    return out
+
+
+def query_extended_context_t5_format(query_ids, title_ids, context_doc_list, main_doc_idx,
+                                     max_seq_length, sep_id, pad_id):
+    head = list(query_ids) + list(title_ids) + [sep_id]
+    room = max(0, max_seq_length - len(head) - 1)
+    enc = head + _fill_context(context_doc_list, main_doc_idx, room) + [sep_id]
+    return enc + [pad_id] * (max_seq_length - len(enc))
+
+
+def query_single_context_t5_format(query_ids, title_ids, context_ids, max_seq_length, sep_id, pad_id):
+    enc = (list(query_ids) + list(title_ids) + [sep_id] + list(context_ids))[:max_seq_length - 1]
+    enc.append(sep_id)
+    return enc + [pad_id] * (max_seq_length - len(enc))
+
+
+def postprocess_arrays(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data, topk_retrievals,
+                       seq_length_ret, seq_length, cls_id, sep_id, pad_id):
+    """numpy version of `postprocess`: returns (context_ids [B,K,S_ret], context_types [B,K,S_ret],
+    extended [B*K,S], single [B*K,S]) as int64 arrays."""
+    uids = [int(u) for u in query_uid]
+    bsz = len(uids)
+    k_keep = int(topk_retrievals)
+    ctx_ids = np.full((bsz, k_keep, seq_length_ret), pad_id, dtype=np.int64)
+    ctx_types = np.zeros((bsz, k_keep, seq_length_ret), dtype=np.int64)
+    extended = np.full((bsz * k_keep, seq_length), pad_id, dtype=np.int64)
+    single = np.full((bsz * k_keep, seq_length), pad_id, dtype=np.int64)
+    row = 0
+    for bi, (qid, (topkids, text_list)) in enumerate(zip(uids, topk_evidence_data)):
+        query = [int(t) for t in query_ids_t5[bi][:int(query_ids_t5_len[bi])]]
+        kept = 0
+        for eid, (doc_list, main_idx, title_ids) in zip(topkids, text_list):
+            if qid == eid or kept >= k_keep:        # drop the passage the question came from
+                continue
+            passage = doc_list[main_idx]
+            ids, types, _ = build_tokens_types_paddings_from_ids(
+                list(title_ids) + [sep_id] + list(passage), seq_length_ret, cls_id, sep_id, pad_id)
+            ctx_ids[bi, kept] = ids
+            ctx_types[bi, kept] = types
+            extended[row] = query_extended_context_t5_format(query, title_ids, doc_list, main_idx,
+                                                             seq_length, sep_id, pad_id)
+            single[row] = query_single_context_t5_format(query, title_ids, passage, seq_length,
+                                                         sep_id, pad_id)
+            kept += 1
+            row += 1
+        if kept != k_keep:
+            raise ValueError("query %d kept %d of %d passages (the reference would build a ragged "
+                             "tensor here)" % (bi, kept, k_keep))
+    return ctx_ids, ctx_types, extended, single
+
+
+def postprocess(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data, topk_retrievals,
+                seq_length_ret, seq_length, cls_id, sep_id, pad_id, device=None):
+    """Drop-in for emdr2_model.py:250-303 with the tokenizer ids / lengths passed explicitly
+    (the reference reads them from get_args()/get_t5_tokenizer()).  Returns four int64 tensors on
+    `device` (default: current CUDA device)."""
+    if torch.is_tensor(query_uid):
+        query_uid = query_uid.tolist()
+    if torch.is_tensor(query_ids_t5):
+        query_ids_t5 = query_ids_t5.tolist()
+    if torch.is_tensor(query_ids_t5_len):
+        query_ids_t5_len = query_ids_t5_len.tolist()
+    arrays = postprocess_arrays(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data,
+                                topk_retrievals, seq_length_ret, seq_length, cls_id, sep_id, pad_id)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    out = []
+    for a in arrays:
+        t = torch.from_numpy(a)
+        if torch.device(device).type == "cuda":
+            t = t.pin_memory().to(device, non_blocking=True)
+        out.append(t)
+    return tuple(out)

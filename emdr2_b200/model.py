@@ -1,0 +1,137 @@
+"""EMDR2 retrieve-and-read model (forward orchestration) on the B200 kernels.
+
+Mirrors reference megatron/model/emdr2_model.py:31-214 (`EMDR2Model`) and
+megatron/model/dualencoder_model.py:27-82 (`DualEncoderModel`): same attribute names
+(`language_model`, `retriever_model.query_model/context_model`, checkpoint keys
+'encoder/t5_model' and 'retriever/biencoder_model'), same forward signature and return tuples.
+The steps are the reference's:
+
+  1 query tower            -> [B, h]                              emdr2_model.py:98-104
+  2 retrieve               -> top-k doc ids + passage tokens      :107-108   (emdr2_b200/retriever.py)
+  3 format                 -> BERT / T5 input ids                 :110-115   (emdr2_b200/formatter.py)
+  4 context tower          -> [B, K, h]                           :118-131
+  5 fresh scores           -> log_softmax(q·c / sqrt(h)) [B, K]   :134-145
+  6 T5 encoder, K passages -> [B, K*S, h] (FiD concatenation)     :148-164
+  7 T5 decoder + LM head   -> logits [B, L, V]                    :166-183
+  8 one-context pass       -> logits [B, K, L, V] (training, --update-retriever)   :185-210
+
+Differences behind that surface: masks are never materialised (the kernels derive them from the
+ids, which is how the reference builds them: make_attention_mask_3d(ids, ids) < 0.5), the run is
+forward-only (no autograd graph is recorded yet), and configuration is passed explicitly instead of
+through the global get_args().
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import formatter
+from .blocks import BertTower, T5Reader
+
+
+class DualEncoder(nn.Module):
+    """DualEncoderModel: separate query and context BERT towers, CLS embedding without pooler."""
+
+    def __init__(self, cfg, bert_vocab_size=None, only_query_model=False, only_context_model=False):
+        super().__init__()
+        assert not (only_query_model and only_context_model)
+        self.use_query_model = not only_context_model
+        self.use_context_model = not only_query_model
+        if self.use_query_model:
+            self.query_model = BertTower(cfg, num_tokentypes=2, vocab_size=bert_vocab_size)
+        if self.use_context_model:
+            self.context_model = BertTower(cfg, num_tokentypes=2, vocab_size=bert_vocab_size)
+
+    @staticmethod
+    def embed_text(model, tokens, attention_mask, token_types):
+        """dualencoder_model.py:76-82."""
+        return model(tokens, attention_mask, token_types)
+
+    def forward(self, query_tokens, query_attention_mask, query_types, context_tokens,
+                context_attention_mask, context_types):
+        q = self.embed_text(self.query_model, query_tokens, query_attention_mask, query_types) \
+            if self.use_query_model else None
+        c = self.embed_text(self.context_model, context_tokens, context_attention_mask, context_types) \
+            if self.use_context_model else None
+        return q, c
+
+
+class EMDR2Model(nn.Module):
+    """cfg: dict(hidden, heads, layers, ffn, vocab, max_pos, dtype).  `settings` carries what the
+    reference reads from get_args()/tokenizers on every call (emdr2_model.py:92,250-303):
+    topk_retrievals, seq_length, seq_length_ret, retriever_score_scaling, update_retriever,
+    cls_id, sep_id, pad_id."""
+
+    def __init__(self, cfg, evidence_retriever, settings, t5_vocab_size=None, bert_vocab_size=None):
+        super().__init__()
+        self.cfg = cfg
+        self.settings = dict(settings)
+        self.topk = int(settings["topk_retrievals"])
+        self.language_model = T5Reader(cfg, num_tokentypes=2, vocab_size=t5_vocab_size)
+        self._language_model_key = 'encoder/t5_model'
+        self.retriever_model = DualEncoder(cfg, bert_vocab_size=bert_vocab_size)
+        self._retriever_model_key = 'retriever/biencoder_model'
+        self.evidence_retriever = evidence_retriever
+
+    def retriever_embedder(self, tokens, mask, types, embedder_type, disable_dropout=False):
+        m = self.retriever_model
+        if embedder_type == "query":
+            return m.embed_text(m.query_model, tokens, mask, types)
+        if embedder_type == "context":
+            return m.embed_text(m.context_model, tokens, mask, types)
+        raise ValueError("Invalid embedder type.")
+
+    @torch.no_grad()
+    def forward(self, query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5,
+                query_ids_t5_len, dec_ids, all_query_context_hidden_states=None,
+                all_query_context_ids_unflat=None, topk_log_probs=None):
+        st = self.settings
+        topk = self.topk
+        bsize = query_ids_bert.shape[0]
+        hidden = self.cfg["hidden"]
+        seq_length = int(st["seq_length"])
+        query_one_context_ids = None
+
+        if all_query_context_hidden_states is None:
+            query_logits = self.retriever_embedder(query_ids_bert, query_mask_bert, query_types, "query")
+            topk_evidence_data, _stale = self.evidence_retriever.get_topk(query_logits.clone().detach())
+            all_context_ids, all_context_types, all_query_extended_context_ids, query_one_context_ids = \
+                formatter.postprocess(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data,
+                                      topk, int(st["seq_length_ret"]), seq_length, st["cls_id"],
+                                      st["sep_id"], st["pad_id"], device=query_ids_bert.device)
+            s_ret = all_context_ids.shape[-1]
+            all_context_logits = self.retriever_embedder(all_context_ids.reshape(-1, s_ret), None,
+                                                         all_context_types.reshape(-1, s_ret), "context")
+            all_context_logits = all_context_logits.reshape(bsize, topk, -1).float()
+            topk_sim_scores = torch.bmm(query_logits.unsqueeze(1).float(), all_context_logits.transpose(1, 2))
+            if st.get("retriever_score_scaling", True):
+                topk_sim_scores = topk_sim_scores / math.sqrt(hidden)
+            topk_log_probs = torch.log_softmax(topk_sim_scores, dim=2).squeeze(1)
+
+            enc = self.language_model(all_query_extended_context_ids, dec_ids, output_enc_hidden=True)
+            all_query_context_hidden_states = enc.reshape(bsize, topk * seq_length, hidden)
+            all_query_context_ids_unflat = all_query_extended_context_ids.reshape(bsize, topk * seq_length)
+
+        lm_logits, _ = self.language_model(all_query_context_ids_unflat[:, :seq_length], dec_ids,
+                                           enc_hidden_states=all_query_context_hidden_states,
+                                           enc_ids_for_mask=all_query_context_ids_unflat)
+        if self.training:
+            lm_logits_one_context = None
+            if st.get("update_retriever", False) and query_one_context_ids is not None:
+                dec_ids_repeated = torch.repeat_interleave(dec_ids, topk, dim=0)
+                flat, _ = self.language_model(query_one_context_ids, dec_ids_repeated)
+                lm_logits_one_context = flat.reshape(bsize, topk, flat.shape[1], flat.shape[2])
+            return lm_logits, topk_log_probs, lm_logits_one_context
+        return lm_logits, topk_log_probs, all_query_context_hidden_states, all_query_context_ids_unflat
+
+    def state_dict_for_save_checkpoint(self, destination=None, prefix='', keep_vars=False):
+        return {self._language_model_key: self.language_model.state_dict(),
+                self._retriever_model_key: self.retriever_model.state_dict()}
+
+    def load_state_dict(self, state_dict, strict=True):
+        if self._language_model_key in state_dict:
+            from .blocks import load_reference_state_dict
+            load_reference_state_dict(self.language_model, state_dict[self._language_model_key], strict)
+            load_reference_state_dict(self.retriever_model, state_dict[self._retriever_model_key], strict)
+            return
+        return super().load_state_dict(state_dict, strict)

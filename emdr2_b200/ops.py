@@ -147,3 +147,27 @@ def embedding(ids, word, pos, types=None, type_emb=None, seq=None):
             word.shape[0], type_emb.shape[0] if type_emb is not None else 0, _stream(device)),
             "emdr2_embedding_fwd")
     return out
+
+
+def token_logprob(logits, labels):
+    """(logprob, lse) fp32, shaped like `labels`: logprob = logits[..., label] - logsumexp(logits).
+    logits [..., V] 16-bit CUDA (last dim contiguous), labels int64 [...]."""
+    dtype, device = logits.dtype, logits.device
+    if dtype not in _DTYPES or not logits.is_cuda:
+        raise TypeError("token_logprob takes CUDA float16/bfloat16 logits")
+    vocab = logits.shape[-1]
+    l2 = logits.reshape(-1, vocab)
+    if l2.stride(1) != 1:
+        l2 = l2.contiguous()
+    lab = labels.to(device=device, dtype=torch.int64).reshape(-1).contiguous()
+    rows = l2.shape[0]
+    if lab.numel() != rows:
+        raise ValueError("labels must have one entry per logits row")
+    lp = torch.empty(rows, dtype=torch.float32, device=device)
+    lse = torch.empty(rows, dtype=torch.float32, device=device)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.emdr2_token_logprob(_DTYPES[dtype], _ptr(l2), max(vocab, l2.stride(0)), _ptr(lab),
+                                           _ptr(lp), _ptr(lse), rows, vocab, _stream(device)),
+                   "emdr2_token_logprob")
+    return lp.view(labels.shape), lse.view(labels.shape)

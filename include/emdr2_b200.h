@@ -156,6 +156,13 @@ EMDR2_API int emdr2_embedding_fwd(int dtype, const int64_t* ids, const int64_t* 
                                   int tokens, int seq, int h, int vocab, int num_types,
                                   void* cuda_stream);
 
+/* logprob[r] = logits[r, labels[r]] - logsumexp(logits[r, :]) (and lse[r], optional) in one pass:
+ * the log_softmax + gather of get_loss_and_retriever_utility / get_kl_div_retriever
+ * (tasks/openqa/e2eqa/train_e2eqa.py:82-98,196-208) and of the reader's CrossEntropyLoss (:156-160).
+ * logits [rows, vocab] 16-bit with row pitch ld; labels int64 [rows] (out of range -> logprob 0). */
+EMDR2_API int emdr2_token_logprob(int dtype, const void* logits, int64_t ld, const int64_t* labels,
+                                  float* logprob, float* lse, int rows, int vocab, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
