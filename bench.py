@@ -1,27 +1,32 @@
 #!/usr/bin/env python
-"""Benchmark of the retrieve hot path: brute-force MIPS top-k of a query batch over the evidence matrix.
+"""Benchmark of the retrieve-and-read hot path (BASELINE.json metric: "queries/sec retrieve+read @21M
+docs, 1/2/4/8 GPU; MIPS HBM GB/s vs peak").
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU (FAISS-flat) path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
     torchrun --nproc-per-node N ... bench.py --gpus N ...    # N > 1: one rank per GPU, NCCL
 
-Workload (BASELINE.json `metric`: "queries/sec ... @21M docs, 1/2/4/8 GPU"): 21 000 000 x 768 fp16
-synthetic evidence, batch of 64 queries, top-50 — configs[2].  The corpus is FIXED and row-sharded
-over the N ranks with the reference's torch.chunk rule (strong scaling); it fits a single B200
-(32.3 GB of 180 GB), so N=1 runs the same corpus.  One "step" = one search of the 64-query batch:
-fused GEMM+top-k scan of the local shard, pool merge, and for N>1 one all-gather of [64,50]
-(score,id) pairs + k-way merge on every rank.
+One step = EMDR2Model.forward (reference megatron/model/emdr2_model.py:87-214, eval path) for a
+batch of `--batch` questions per GPU (8, the reference recipe): query tower (BERT-base, S=256) ->
+all-gather of the queries -> brute-force top-50 MIPS over the 21 000 000 x 768 fp16 evidence matrix
+row-sharded over the N ranks (one all-gather of [nq,k] pairs + merge) -> passage lookup + formatting
+on the host -> context tower over 50 passages per question (S=256) -> fresh scores -> T5-base encoder
+over the 50 (question, passage) pairs (S=512) -> FiD decoder (L=32, cross-attention over 25 600
+keys) + LM head.  Forward only: the backward pass is not in the timed region (not built yet).
+Synthetic NQ-shaped data: random-init weights N(0, 0.02), question length
+U[8,24], passages U[100,180] tokens, titles U[2,8], answers U[2,6].
 
-The one JSON line printed by rank 0 carries:
-  value        queries/s, evidence AND queries resident in HBM, CUDA-event timed, max over ranks
-  e2e          same, through B200BruteForceIndex.search_mips_index with pinned HOST query buffers
-               copied in and fp16 scores / int32 ids copied back out inside the timed region
-  roofline     the scan kernel: algorithmic bytes per launch / its mean launch duration (CUDA events
-               recorded around every scan launch on the launching stream by the library), against the
-               measured HBM copy bandwidth in MEASURED_PEAKS.json
-  cpu_baseline the reference's CPU path (FAISS IndexFlatIP algorithm, oracle/flat_ip.py: blocked
-               SGEMM + running top-k) timed on this box's host cores over a bounded row sample and
-               scaled linearly to the full corpus (rank 0, N=1 only)
+Scaling is "weak": every rank reads 8 questions (global batch 8N) over a FIXED 21 M-row corpus, so
+per-GPU reader work is constant and the per-GPU MIPS shard shrinks as 1/N.
+
+JSON line (rank 0): value = questions/s, CUDA-event timed, max over ranks, inputs resident on the
+device; e2e = same through pinned HOST input buffers with the predicted token ids and passage
+log-probabilities copied back; roofline = the dominant kernel (emdr2::gemm_kernel, tensor-bound:
+sum of 2mnk over its launches / sum of their CUDA-event durations vs the measured sustained cuBLAS
+bf16 rate); roofline_mips = emdr2::mips_scan_kernel (HBM-bound: algorithmic bytes / launch duration
+vs the measured copy bandwidth) — the "MIPS HBM GB/s vs peak" half of the metric; cpu_baseline = the
+reference's CPU path (FAISS-flat port + fp32 PyTorch reader restatement) on a bounded sample.
+`--retrieve-only` benches the search alone with a 64-question batch (BASELINE configs[1]/[2]).
 """
 import argparse
 import json
@@ -42,31 +47,45 @@ L2_BYTES = 126 * 1024 * 1024
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=200)
-    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--steps", type=int, default=None, help="default 20 (retrieve+read) / 200 (--retrieve-only)")
+    p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--rows", type=int, default=21_000_000, help="total evidence rows (all ranks)")
     p.add_argument("--dim", type=int, default=768)
-    p.add_argument("--nq", type=int, default=64)
+    p.add_argument("--nq", type=int, default=64, help="questions per search with --retrieve-only")
     p.add_argument("--k", type=int, default=50)
+    p.add_argument("--batch", type=int, default=8, help="questions per GPU per step (retrieve+read)")
+    p.add_argument("--seq-ret", type=int, default=256)
+    p.add_argument("--seq", type=int, default=512)
+    p.add_argument("--dec", type=int, default=32)
+    p.add_argument("--layers", type=int, default=12)
+    p.add_argument("--retrieve-only", action="store_true")
+    p.add_argument("--model-dtype", default="bf16", choices=["fp16", "bf16"])
     p.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     p.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-gpu-reference", action="store_true")
-    return p.parse_args()
+    a = p.parse_args()
+    if a.steps is None:
+        a.steps = 200 if a.retrieve_only else 20
+    return a
 
 
 def workload_name(a):
-    return "%d x %d %s evidence, %d queries, top-%d" % (a.rows, a.dim, a.dtype, a.nq, a.k)
+    if a.retrieve_only:
+        return "%d x %d %s evidence, %d queries, top-%d" % (a.rows, a.dim, a.dtype, a.nq, a.k)
+    return ("%d x %d %s evidence; %d questions/GPU; top-%d; BERT-base towers S=%d; T5-base-shaped reader "
+            "S=%d L=%d, %d layers" % (a.rows, a.dim, a.dtype, a.batch, a.k, a.seq_ret, a.seq, a.dec, a.layers))
 
 
-def measured_peak():
+def measured_peak(key="hbm_gbs"):
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return float(json.load(f)[key]), "measured (MEASURED_PEAKS.json %s)" % key
     except Exception:
-        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+        fallback = {"hbm_gbs": FALLBACK_HBM_GBS, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}[key]
+        return fallback, "fallback (B200_PROFILING.md)"
 
 
 def recorded_traffic(rows_per_gpu, dim):
@@ -134,10 +153,63 @@ class ClockSampler(object):
                 "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------------------- synthetic corpus
+class SyntheticTokens(object):
+    """passages_map / title_map stand-in: x[doc_id - 1] -> np.int64 token array.  A pool of
+    pre-generated passages indexed modulo its size (21 M real passages would be 25 GB of tokens)."""
+
+    def __init__(self, lo, hi, seed, pool=65536):
+        import numpy as np
+        rng = np.random.RandomState(seed)
+        lens = rng.randint(lo, hi + 1, size=pool)
+        self.items = [rng.randint(1000, 30000, size=int(n)).astype(np.int64) for n in lens]
+
+    def __getitem__(self, i):
+        return self.items[i % len(self.items)]
+
+
+class SyntheticTitleMap(object):
+    """Articles of 4 consecutive passages (tools/inverted_title_index.py:22-37 semantics)."""
+
+    def __init__(self, num_docs, per_article=4):
+        self.n, self.per = num_docs, per_article
+
+    def get_neighbour_paragraphs(self, doc_id):
+        first = ((doc_id - 1) // self.per) * self.per + 1
+        docs = list(range(first, min(self.n, first + self.per - 1) + 1))
+        i = docs.index(doc_id)
+        if i == 0:
+            return docs[0:3], 0
+        if i == len(docs) - 1:
+            return docs[i - 2:i + 1], -1
+        return docs[i - 1:i + 2], 1
+
+
+def synthetic_questions(a, rank):
+    """NQ-shaped batch as CPU int64 tensors."""
+    import numpy as np
+    import torch
+    rng = np.random.RandomState(1234 + rank)
+    b = a.batch
+    q_bert = torch.zeros(b, a.seq_ret, dtype=torch.int64)
+    q_t5 = torch.zeros(b, 64, dtype=torch.int64)
+    q_len = torch.zeros(b, dtype=torch.int64)
+    dec = torch.zeros(b, a.dec, dtype=torch.int64)
+    for i in range(b):
+        n = int(rng.randint(8, 25))
+        toks = torch.from_numpy(rng.randint(1000, 30000, size=n))
+        q_bert[i, 0], q_bert[i, 1:1 + n], q_bert[i, 1 + n] = 101, toks, 102
+        q_t5[i, :n], q_len[i] = toks, n
+        m = int(rng.randint(2, 7))
+        dec[i, 0], dec[i, 1:1 + m] = 30522, torch.from_numpy(rng.randint(1000, 30000, size=m))
+    return dict(uid=-torch.arange(1, b + 1), q_bert=q_bert, q_types=torch.zeros_like(q_bert), q_t5=q_t5,
+                q_len=q_len, dec=dec)
+
+
 # ------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_step_fn(a):
-    """Returns (step, sample_description, cores): step() runs one search of the nq-query batch over
-    the bounded row sample with the FAISS-flat port and returns its wall seconds."""
+def cpu_mips_step_fn(a, nq):
+    """step() runs one search of an nq-question batch over the bounded row sample with the
+    FAISS-flat port (oracle/flat_ip.py) and returns wall seconds; scale = rows / sample rows."""
     import torch
     from oracle.flat_ip import flat_ip_search, host_threads
     cores = host_threads()
@@ -148,45 +220,139 @@ def cpu_reference_step_fn(a):
     for r0 in range(0, s_rows, 1 << 17):               # generated in slices: bounded temporaries
         r1 = min(s_rows, r0 + (1 << 17))
         rows[r0:r1] = (torch.randn(r1 - r0, a.dim, generator=g) / a.dim ** 0.5).half().float()
-    queries = torch.randn(a.nq, a.dim, generator=g).half().float()
+    queries = torch.randn(nq, a.dim, generator=g).half().float()
 
     def step():
         t0 = time.perf_counter()
         flat_ip_search(rows, None, queries, a.k)
         return time.perf_counter() - t0
 
-    sample = ("%d of %d rows (fp32 copies of fp16 values), %d queries, top-%d; time scaled x%.3f "
-              "to the full corpus" % (s_rows, a.rows, a.nq, a.k, a.rows / s_rows))
+    sample = "search: %d of %d rows (fp32 copies of fp16 values), %d questions, top-%d, time x%.3f" % (
+        s_rows, a.rows, nq, a.k, a.rows / s_rows)
     return step, sample, cores, a.rows / s_rows
+
+
+def cpu_reader_step_fn(a, passages=2):
+    """step() runs the fp32 PyTorch restatement of the reader path (oracle/blocks.py) for ONE question
+    and `passages` of its top-k passages: query tower, context tower, T5 encoder, FiD decoder + LM
+    head; scale = batch * k / passages (the encoders dominate and are linear in passages)."""
+    import torch
+    from oracle import blocks as ob
+    h, heads, ffn, layers, vocab = 768, 12, 3072, a.layers, 30720
+    g = torch.Generator().manual_seed(7)
+
+    def weights(decoder):
+        w = {}
+
+        def lin(name, o, i):
+            w[name + ".weight"] = torch.randn(o, i, generator=g) * 0.02
+            w[name + ".bias"] = torch.zeros(o)
+
+        def ln(name):
+            w[name + ".weight"], w[name + ".bias"] = torch.ones(h), torch.zeros(h)
+
+        w["language_model.embedding.word_embeddings.weight"] = torch.randn(vocab, h, generator=g) * 0.02
+        w["language_model.embedding.position_embeddings.weight"] = torch.randn(512, h, generator=g) * 0.02
+        w["language_model.embedding.tokentype_embeddings.weight"] = torch.randn(2, h, generator=g) * 0.02
+        for stack in (["encoder", "decoder"] if decoder else ["encoder"]):
+            for i in range(layers):
+                p = "language_model.%s.layers.%d" % (stack, i)
+                ln(p + ".input_layernorm")
+                lin(p + ".self_attention.query_key_value", 3 * h, h)
+                lin(p + ".self_attention.dense", h, h)
+                ln(p + ".post_attention_layernorm")
+                if stack == "decoder":
+                    lin(p + ".inter_attention.query", h, h)
+                    lin(p + ".inter_attention.key_value", 2 * h, h)
+                    lin(p + ".inter_attention.dense", h, h)
+                    ln(p + ".post_inter_attention_layernorm")
+                lin(p + ".mlp.dense_h_to_4h", ffn, h)
+                lin(p + ".mlp.dense_4h_to_h", h, ffn)
+            ln("language_model.%s.final_layernorm" % stack)
+        w["lm_head.bias"] = torch.zeros(vocab)
+        return w
+
+    wb, wt = weights(False), weights(True)
+    q = synthetic_questions(argparse.Namespace(batch=1, seq_ret=a.seq_ret, dec=a.dec), 0)
+    ctx = torch.randint(1000, 30000, (passages, a.seq_ret), generator=g)
+    ctx[:, 180:] = 0
+    ext = torch.randint(1000, 30000, (passages, a.seq), generator=g)
+    ext[:, 200:] = 0
+
+    def step():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ob.bert_pooled(q["q_bert"], q["q_types"], wb, heads, layers)
+            ob.bert_pooled(ctx, torch.zeros_like(ctx), wb, heads, layers)
+            enc = ob.t5_encode(ext, wt, heads, layers)
+            ob.t5_decode(q["dec"], enc.reshape(1, passages * a.seq, h), ext.reshape(1, passages * a.seq), wt,
+                         heads, layers)
+        return time.perf_counter() - t0
+
+    scale = a.batch * a.k / passages
+    sample = "read: 1 question x %d of %d passages in fp32 on the host (oracle/blocks.py), time x%.1f" % (
+        passages, a.k, scale)
+    return step, sample, scale
+
+
+def cpu_baseline(a, budget_s=25.0):
+    """Reference CPU path on a bounded sample -> dict for the JSON line (rank 0, N=1 only)."""
+    nq = a.nq if a.retrieve_only else a.batch * a.gpus
+    mips_step, sample, cores, mips_scale = cpu_mips_step_fn(a, nq)
+    mips_step()
+    t_mips = min(mips_step() for _ in range(3)) * mips_scale
+    if a.retrieve_only:
+        return dict(value=nq / t_mips, unit="queries/s", cores=cores, kind="port", sample=sample + "; best of 3")
+    read_step, read_sample, read_scale = cpu_reader_step_fn(a)
+    read_step()
+    t_read = read_step() * read_scale
+    return dict(value=a.batch / (t_mips + t_read), unit="queries/s", cores=cores, kind="port",
+                sample=sample + "; " + read_sample, search_s_per_step=t_mips, read_s_per_step=t_read)
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    step, sample, cores, scale = cpu_reference_step_fn(a)
+    nq = a.nq if a.retrieve_only else a.batch * a.gpus
+    mips_step, sample, cores, mips_scale = cpu_mips_step_fn(a, nq)
+    read = None if a.retrieve_only else cpu_reader_step_fn(a)
     for _ in range(max(1, min(a.warmup, 2))):
-        step()
-    steps = max(1, a.steps)
-    budget_s, times = 150.0, []
-    for _ in range(steps):                       # bounded: stop early rather than run for hours
-        times.append(step())
-        if sum(times) > budget_s:
+        mips_step()
+        if read:
+            read[0]()
+    budget_s, times, wall0 = 150.0, [], time.perf_counter()
+    for _ in range(max(1, a.steps)):             # bounded: stop early rather than run for hours
+        t = mips_step() * mips_scale
+        if read:
+            t += read[0]() * read[2]
+        times.append(t)
+        if time.perf_counter() - wall0 > budget_s:
             break
-    sec = statistics.mean(times) * scale
-    value = a.nq / sec
+    sec = statistics.mean(times)
+    queries_per_step = nq if a.retrieve_only else a.batch * a.gpus
+    value = queries_per_step / sec
+    full_sample = sample + ("" if not read else "; " + read[1])
     line = {
-        "impl": "reference", "metric": "queries/sec retrieve (brute-force MIPS top-%d) @%.0fM docs" % (a.k, a.rows / 1e6),
-        "value": value, "unit": "queries/s", "n_gpus": a.gpus, "steps": len(times), "warmup": a.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "path": "FaissMIPSIndex CPU (IndexFlatIP) restated by oracle/flat_ip.py; faiss itself is absent from the image"},
-        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric_name(a), "value": value, "unit": "queries/s", "n_gpus": a.gpus,
+        "steps": len(times), "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong" if a.retrieve_only else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a),
+                   "path": "FaissMIPSIndex CPU (IndexFlatIP) restated by oracle/flat_ip.py + fp32 PyTorch "
+                           "restatement of the reader (oracle/blocks.py); faiss is absent from the image and the "
+                           "reference's own modules are CUDA-only"},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": full_sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def metric_name(a):
+    if a.retrieve_only:
+        return "queries/sec retrieve (brute-force MIPS top-%d) @%.0fM docs" % (a.k, a.rows / 1e6)
+    return "queries/sec retrieve+read (forward) @%.0fM docs" % (a.rows / 1e6)
 
 
 # ------------------------------------------------------------------------------------- B200 arm
@@ -200,62 +366,41 @@ def make_shard(torch, n_local, dim, dtype, seed, device):
     return rows
 
 
-def run_b200_arm(a):
-    import torch
-    import torch.distributed as dist
-    from emdr2_b200.index import B200BruteForceIndex, chunk_range
+class Dist(object):
+    """Rank bookkeeping + the barrier / max-over-ranks timing helpers of the bench contract."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != a.gpus:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch N>1 with torch.distributed.run" % (a.gpus, world))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: emdr2_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    tdtype = {"fp16": torch.float16, "bf16": torch.bfloat16}[a.dtype]
+    def __init__(self, a):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != a.gpus:
+            raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch N>1 with torch.distributed.run" % (a.gpus, self.world))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: emdr2_b200 has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
+        self.group = dist.group.WORLD if self.world > 1 else None
 
-    lo, hi = chunk_range(a.rows, world, rank)
-    rows = make_shard(torch, hi - lo, a.dim, tdtype, 1234 + rank, device)
-    index = B200BruteForceIndex(a.dim, dtype=tdtype, device=device,
-                                group=dist.group.WORLD if world > 1 else None)
-    index.add_local_shard(None, rows, num_rows=a.rows, row_lo=lo)       # ids = 1-based row numbers
-    searcher = index._searcher
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    gq = torch.Generator(device=device).manual_seed(99)                 # same queries on all ranks
-    n_batches = 8
-    q_dev = [torch.randn(a.nq, a.dim, generator=gq, device=device).to(tdtype) for _ in range(n_batches)]
-    q_host = [q.cpu().pin_memory() for q in q_dev]
-    out_d = torch.empty((a.nq, a.k), dtype=torch.float16).pin_memory()
-    out_i = torch.empty((a.nq, a.k), dtype=torch.int32).pin_memory()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
+    def max_over_ranks(self, x):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def resident_step(i):
-        return index.search(q_dev[i % n_batches], a.k)
-
-    def e2e_step(i):
-        q = q_host[i % n_batches].to(device, non_blocking=True)
-        d, ix = index.search_mips_index(q, a.k, reconstruct=False)
-        out_d.copy_(d, non_blocking=True)
-        out_i.copy_(ix, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the caller consumes the ids on the host
-
-    def timed(step_fn, steps):
-        barrier()
+    def timed(self, step_fn, steps):
+        torch = self.torch
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
@@ -263,74 +408,91 @@ def run_b200_arm(a):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        barrier()
-        return max_over_ranks(ms)
+        self.barrier()
+        return self.max_over_ranks(ms)
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def mips_roofline(a, d, searcher, n_local, nq):
+    scan_launches = searcher.stat("scan_launches")
+    scan_ns = searcher.stat("scan_ns")
+    algo_bytes = n_local * a.dim * 2 + nq * a.dim * 2 + nq * a.k * 12
+    scan_ms = d.max_over_ranks(scan_ns / max(1, scan_launches) * 1e-6)
+    peak, peak_src = measured_peak("hbm_gbs")
+    achieved = algo_bytes / (scan_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": recorded_traffic(n_local, a.dim), "kernel": "emdr2::mips_scan_kernel",
+            "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": scan_ms, "launches_timed": scan_launches,
+            "peak_source": peak_src}
+
+
+def run_retrieve_only(a):
+    import torch
+    from emdr2_b200.index import B200BruteForceIndex, chunk_range
+    d = Dist(a)
+    device, world, rank = d.device, d.world, d.rank
+    tdtype = {"fp16": torch.float16, "bf16": torch.bfloat16}[a.dtype]
+    lo, hi = chunk_range(a.rows, world, rank)
+    rows = make_shard(torch, hi - lo, a.dim, tdtype, 1234 + rank, device)
+    index = B200BruteForceIndex(a.dim, dtype=tdtype, device=device, group=d.group)
+    index.add_local_shard(None, rows, num_rows=a.rows, row_lo=lo)       # ids = 1-based row numbers
+    searcher = index._searcher
+    gq = torch.Generator(device=device).manual_seed(99)                 # same queries on all ranks
+    n_batches = 8
+    q_dev = [torch.randn(a.nq, a.dim, generator=gq, device=device).to(tdtype) for _ in range(n_batches)]
+    q_host = [q.cpu().pin_memory() for q in q_dev]
+    out_d = torch.empty((a.nq, a.k), dtype=torch.float16).pin_memory()
+    out_i = torch.empty((a.nq, a.k), dtype=torch.int32).pin_memory()
+
+    def resident_step(i):
+        return index.search(q_dev[i % n_batches], a.k)
+
+    def e2e_step(i):
+        q = q_host[i % n_batches].to(device, non_blocking=True)
+        dd, ix = index.search_mips_index(q, a.k, reconstruct=False)
+        out_d.copy_(dd, non_blocking=True)
+        out_i.copy_(ix, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller consumes the ids on the host
 
     warm = max(3, a.warmup)
     for i in range(warm):
         resident_step(i)
         e2e_step(i)
     torch.cuda.synchronize()
-
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(d.local_rank) as clocks:
         searcher.set_option("timing", 1)
-        ms_total = timed(resident_step, a.steps)
-        scan_launches = searcher.stat("scan_launches")
-        scan_ns = searcher.stat("scan_ns")
+        ms_total = d.timed(resident_step, a.steps)
+        roof = mips_roofline(a, d, searcher, hi - lo, a.nq)
         searcher.set_option("timing", 0)
-        ms_e2e = timed(e2e_step, a.steps)
+        ms_e2e = d.timed(e2e_step, a.steps)
     ms_step = ms_total / a.steps
-    value = a.nq / (ms_step * 1e-3)
-    e2e_value = a.nq / (ms_e2e / a.steps * 1e-3)
-
     n_local = hi - lo
-    algo_bytes = n_local * a.dim * 2 + a.nq * a.dim * 2 + a.nq * a.k * 12
-    scan_ms = max_over_ranks(scan_ns / max(1, scan_launches) * 1e-6)
-    peak, peak_src = measured_peak()
-    achieved = algo_bytes / (scan_ms * 1e-3) / 1e9
-    launches_per_step = (2 if world == 1 else 3) * (-(-a.nq // 64))
-
     line = {
-        "metric": "queries/sec retrieve (brute-force MIPS top-%d) @%.0fM docs" % (a.k, a.rows / 1e6),
-        "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": warm,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": a.dtype + " inputs, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
+        "metric": metric_name(a), "value": a.nq / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+        "steps": a.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": a.dtype + " inputs, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
         "config": {
-            "workload": workload_name(a),
-            "rows_per_gpu": n_local, "sharding": "torch.chunk row ranges, one rank per GPU",
+            "workload": workload_name(a), "rows_per_gpu": n_local,
+            "sharding": "torch.chunk row ranges, one rank per GPU",
             "exchange": "none" if world == 1 else "one all-gather of [nq,k] (fp32 score,int64 id) + k-way merge per rank",
             "l2": "inputs larger than L2 (%.2f GB evidence per GPU streamed per step vs 126 MB L2, evict-first)" % (n_local * a.dim * 2 / 1e9),
-            "stage": "retrieve only (BERT encoders and the T5 reader are not in this timed region)",
-        },
-        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": a.nq * a.dim * 2,
+            "stage": "retrieve only (--retrieve-only)"},
+        "e2e": {"value": a.nq / (ms_e2e / a.steps * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": a.nq * a.dim * 2,
                 "d2h_bytes_per_step": a.nq * a.k * (2 + 4),
                 "api": "B200BruteForceIndex.search_mips_index (pinned host queries in, fp16 scores + int32 ids out)"},
-        "gpu_launches": launches_per_step * a.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": recorded_traffic(n_local, a.dim),
-                     "kernel": "emdr2::mips_scan_kernel", "algorithmic_bytes_per_launch": algo_bytes,
-                     "kernel_ms": scan_ms, "launches_timed": scan_launches, "peak_source": peak_src},
-        "clocks": clocks.summary(),
+        "gpu_launches": (2 if world == 1 else 3) * (-(-a.nq // 64)) * a.steps,
+        "roofline": roof, "clocks": clocks.summary(),
     }
-
     if world == 1 and not a.no_gpu_reference:
         line["gpu_reference"] = gpu_reference_leg(torch, rows, q_dev, a)
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        step, sample, cores, scale = cpu_reference_step_fn(a)
-        step()
-        times = []
-        while len(times) < 5 and sum(times) < 20.0:
-            times.append(step())
-        sec = min(times) * scale
-        line["cpu_baseline"] = {"value": a.nq / sec, "unit": "queries/s", "cores": cores,
-                                "kind": "port", "sample": sample + "; best of %d" % len(times)}
-    else:
-        line["cpu_baseline"] = None
+    line["cpu_baseline"] = cpu_baseline(a) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    d.finish()
     return 0
 
 
@@ -353,17 +515,129 @@ def gpu_reference_leg(torch, rows, q_dev, a):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        return {"value": a.nq / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
+        return {"value": q_dev[0].shape[0] / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
                 "what": "torch.matmul (cuBLAS) -> C[nq,N] in HBM -> torch.topk, same GPU, same shard"}
     except Exception as exc:        # e.g. out of memory for the C matrix on a small GPU
         return {"unavailable": str(exc).splitlines()[0][:200]}
+
+
+def run_retrieve_read(a):
+    import torch
+    from emdr2_b200 import ops
+    from emdr2_b200.index import chunk_range
+    from emdr2_b200.model import EMDR2Model
+    from emdr2_b200.retriever import B200EvidenceRetriever
+    d = Dist(a)
+    device, world, rank = d.device, d.world, d.rank
+    mdtype = {"fp16": torch.float16, "bf16": torch.bfloat16}[a.model_dtype]
+    edtype = {"fp16": torch.float16, "bf16": torch.bfloat16}[a.dtype]
+
+    # ---- evidence shard + retriever (ids = 1-based row numbers, the TSV numbering)
+    lo, hi = chunk_range(a.rows, world, rank)
+    rows = make_shard(torch, hi - lo, a.dim, edtype, 1234 + rank, device)
+    retriever = B200EvidenceRetriever(a.k, a.dim, allow_trivial_doc=True, group=d.group, dtype=edtype,
+                                      passages_map=SyntheticTokens(100, 180, 1), title_map=SyntheticTokens(2, 8, 2),
+                                      wikititledocmap=SyntheticTitleMap(a.rows))
+    retriever.mips_index.add_local_shard(None, rows, num_rows=a.rows, row_lo=lo)
+    searcher = retriever.mips_index._searcher
+
+    # ---- model: 2 x BERT-base towers + T5-base-shaped reader, random init N(0, 0.02)
+    cfg = dict(hidden=a.dim, heads=a.dim // 64, layers=a.layers, ffn=4 * a.dim, vocab=30720, max_pos=512, dtype=mdtype)
+    settings = dict(topk_retrievals=a.k, seq_length=a.seq, seq_length_ret=a.seq_ret, retriever_score_scaling=True,
+                    update_retriever=False, cls_id=101, sep_id=102, pad_id=0)
+    torch.manual_seed(1234)
+    model = EMDR2Model(cfg, retriever, settings, t5_vocab_size=30720, bert_vocab_size=30592).to(device).eval()
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "layernorm" in name:
+                p.fill_(1.0 if name.endswith("weight") else 0.0)
+            elif name.endswith("bias"):
+                p.zero_()
+            else:
+                p.normal_(0.0, 0.02)
+
+    host = synthetic_questions(a, rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    dev = {k: v.to(device) for k, v in host.items()}
+    out_ids = torch.empty((a.batch, a.dec), dtype=torch.int64).pin_memory()
+    out_lp = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
+
+    def forward(x):
+        return model(x["uid"], x["q_bert"], x["q_types"], None, x["q_t5"], x["q_len"], x["dec"])
+
+    def resident_step(i):
+        return forward(dev)
+
+    def e2e_step(i):
+        x = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
+        lm_logits, topk_log_probs, _, _ = forward(x)
+        out_ids.copy_(lm_logits.argmax(dim=-1), non_blocking=True)
+        out_lp.copy_(topk_log_probs, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    warm = max(3, a.warmup)
+    for i in range(warm):
+        resident_step(i)
+    e2e_step(0)
+    torch.cuda.synchronize()
+    nq_search = a.batch * world
+    with ClockSampler(d.local_rank) as clocks:
+        searcher.set_option("timing", 1)
+        ops.timing(True)
+        ms_total = d.timed(resident_step, a.steps)
+        roof_mips = mips_roofline(a, d, searcher, hi - lo, nq_search)
+        gemm_s, gemm_n, gemm_fl = ops.timing_read(ops.KIND_GEMM)
+        attn_s, attn_n, attn_fl = ops.timing_read(ops.KIND_ATTENTION)
+        row_s, row_n, _ = ops.timing_read(ops.KIND_ROWOP)
+        ops.timing(False)
+        searcher.set_option("timing", 0)
+        ms_e2e = d.timed(e2e_step, a.steps)
+    ms_step = ms_total / a.steps
+    peak_t, peak_t_src = measured_peak("bf16_tflops_sustained")
+    gemm_tf = gemm_fl / d.max_over_ranks(gemm_s) / 1e12
+    attn_tf = attn_fl / max(attn_s, 1e-12) / 1e12
+    launches_step = (gemm_n + attn_n + row_n) // a.steps + (2 if world == 1 else 3)
+    tokens = a.batch * (a.seq_ret + a.k * a.seq_ret + a.k * a.seq)
+    fmt_h2d = a.batch * a.k * (2 * a.seq_ret + 2 * a.seq) * 8
+    in_bytes = sum(v.numel() * 8 for v in host.values())
+    line = {
+        "metric": metric_name(a), "value": a.batch * world / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+        "steps": a.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": a.model_dtype + " reader/retriever, " + a.dtype + " evidence, fp32 accumulate",
+        "data": "synthetic",
+        "config": {
+            "workload": workload_name(a),
+            "rows_per_gpu": hi - lo, "global_batch": a.batch * world, "encoder_tokens_per_gpu_per_step": tokens,
+            "sharding": "evidence rows by torch.chunk over ranks; questions data-parallel",
+            "exchange": "none" if world == 1 else "all-gather of queries [B,768] + all-gather of [nq,k] (score,id) pairs + merge",
+            "l2": "inputs larger than L2 (%.2f GB evidence + %.1f GB of activations streamed per step vs 126 MB L2)" % (
+                (hi - lo) * a.dim * 2 / 1e9, tokens * a.dim * 2 * 40 / 1e9),
+            "stage": "retrieve + read FORWARD (EMDR2Model.forward eval path); no backward/optimizer in the timed region"},
+        "e2e": {"value": a.batch * world / (ms_e2e / a.steps * 1e-3), "unit": "queries/s",
+                "h2d_bytes_per_step": in_bytes + fmt_h2d, "d2h_bytes_per_step": out_ids.numel() * 8 + out_lp.numel() * 4 + a.batch * a.k * 4,
+                "api": "EMDR2Model.forward (pinned host question tensors in; greedy token ids + passage log-probs out); includes the host-side passage lookup/formatting"},
+        "gpu_launches": int(launches_step * a.steps),
+        "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_t, "unit": "TFLOP/s", "frac": gemm_tf / peak_t,
+                     "traffic": None, "kernel": "emdr2::gemm_kernel", "algorithmic_flops_per_step": gemm_fl / a.steps,
+                     "kernel_ms_per_step": gemm_s / a.steps * 1e3, "launches_timed": gemm_n, "peak_source": peak_t_src},
+        "roofline_mips": roof_mips,
+        "kernel_time_ms_per_step": {"gemm": gemm_s / a.steps * 1e3, "attention": attn_s / a.steps * 1e3,
+                                    "rowops": row_s / a.steps * 1e3, "mips_scan": roof_mips["kernel_ms"],
+                                    "attention_tflops": attn_tf},
+        "clocks": clocks.summary(),
+    }
+    line["cpu_baseline"] = cpu_baseline(a) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    d.finish()
+    return 0
 
 
 def main():
     a = parse_args()
     if a.impl == "reference":
         return run_reference_arm(a)
-    return run_b200_arm(a)
+    return run_retrieve_only(a) if a.retrieve_only else run_retrieve_read(a)
 
 
 if __name__ == "__main__":

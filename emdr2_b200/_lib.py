@@ -44,8 +44,14 @@ _SIGNATURES = {
                                            ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                            ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "emdr2_gemm_ex": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "emdr2_layernorm_fwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_int64, ctypes.c_int, ctypes.c_int,
@@ -58,6 +64,28 @@ _SIGNATURES = {
     "emdr2_token_logprob": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "emdr2_attention_bwd": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p, ctypes.c_int64] * 8 +
+                            [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_float,
+                                                                          ctypes.c_void_p, ctypes.c_void_p,
+                                                                          ctypes.c_void_p]),
+    "emdr2_layernorm_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                           ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_void_p]),
+    "emdr2_colsum": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "emdr2_token_logprob_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "emdr2_embedding_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_void_p]),
+    "emdr2_ops_timing": (ctypes.c_int, [ctypes.c_int]),
+    "emdr2_ops_timing_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                             ctypes.POINTER(ctypes.c_int64),
+                                             ctypes.POINTER(ctypes.c_double)]),
 }
 
 

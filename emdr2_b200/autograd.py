@@ -1,0 +1,301 @@
+"""Differentiable front end of the block operators: torch.autograd.Function wrappers whose forward
+AND backward run in libemdr2_b200.so (csrc/gemm.cu, attention.cu, attention_bwd.cu, rowops*.cu).
+
+This is the autograd of the reference's transformer layer (megatron/model/transformer.py:58-563,
+mpu/layers.py:170-363, language_model.py:98-181) with dropout off.  PyTorch only records the graph
+and adds gradients where branches meet (the residual stream); every product, softmax, LayerNorm and
+embedding gradient is a kernel of this library:
+
+  linear        dX = dY.W (W read in place as an MN-major operand), dW = dY^T.X (both operands
+                MN-major, split-K over the tokens into an fp32 buffer), db = column sums
+  mlp           h->4h->h with the GeLU forward/backward fused into the GEMM epilogues; the saved
+                pre-activation comes out of the first GEMM's epilogue for free
+  attention     csrc/attention_bwd.cu (dQ kernel + dK/dV kernel), gradients written straight into
+                the fused [tokens, 3h] / [tokens, 2h] projection-gradient buffers
+  layernorm, embedding, token_logprob   csrc/rowops_bwd.cu
+
+Each public function below dispatches on torch.is_grad_enabled(): without grad it is the plain
+forward op (emdr2_b200/ops.py), so inference pays nothing for the training path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+
+_DT = ops._DTYPES
+_SPLIT_TOKENS = 4096        # tokens per split-K slice of a weight-gradient product
+
+
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _splits(tokens, tiles):
+    """Split-K factor for dW: enough work items for the 148 SMs, slices of >= 4096 tokens."""
+    want = max(1, (148 * 2 + tiles - 1) // tiles)
+    return max(1, min(want, (tokens + _SPLIT_TOKENS - 1) // _SPLIT_TOKENS))
+
+
+def _weight_grad(dy, x):
+    """dW[n, k] = dy[m, n]^T . x[m, k] in fp32 (split-K), returned in the parameter dtype."""
+    m, n = dy.shape
+    k = x.shape[1]
+    acc = torch.zeros((n, k), dtype=torch.float32, device=dy.device)
+    tiles = ((n + 127) // 128) * ((k + 255) // 256)
+    ops.gemm_ex(dy, x, a_mn=True, b_mn=True, accumulate_into=acc, splits=_splits(m, tiles))
+    return acc.to(dy.dtype)
+
+
+def _bias_grad(dy):
+    out = torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
+    lib = _lib.load()
+    with torch.cuda.device(dy.device):
+        _lib.check(lib.emdr2_colsum(_DT[dy.dtype], ops._ptr(dy), dy.stride(0), ops._ptr(out), dy.shape[0],
+                                    dy.shape[1], ops._stream(dy.device)), "emdr2_colsum")
+    return out.to(dy.dtype)
+
+
+def _c(t):
+    return t if t.stride(-1) == 1 and (t.dim() < 2 or t.stride(0) % 8 == 0) else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------- linear
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        return ops.linear(x, weight, bias, residual=residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        dx = ops.gemm_ex(dy, weight, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw = _weight_grad(dy, x) if ctx.needs_input_grad[1] else None
+        db = _bias_grad(dy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dres
+
+
+def linear(x, weight, bias=None, residual=None):
+    if _needs_grad(x, weight, bias, residual):
+        return _LinearFn.apply(x, weight, bias, residual)
+    return ops.linear(x, weight, bias, residual=residual)
+
+
+# ------------------------------------------------------------------------------------------ mlp
+class _MlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual):
+        pre = torch.empty((x.shape[0], w1.shape[0]), dtype=x.dtype, device=x.device)
+        act = ops.gemm_ex(x, w1, bias=b1, gelu=True, preact_out=pre)
+        ctx.save_for_backward(x, w1, w2, pre, act)
+        ctx.has_res = residual is not None
+        return ops.linear(act, w2, b2, residual=residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, pre, act = ctx.saved_tensors
+        dy = _c(dy)
+        du = ops.gemm_ex(dy, w2, b_mn=True, gelu_bwd_aux=pre)        # (dy . W2) * GeLU'(pre)
+        dw2 = _weight_grad(dy, act) if ctx.needs_input_grad[3] else None
+        db2 = _bias_grad(dy) if ctx.needs_input_grad[4] else None
+        dx = ops.gemm_ex(du, w1, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw1 = _weight_grad(du, x) if ctx.needs_input_grad[1] else None
+        db1 = _bias_grad(du) if ctx.needs_input_grad[2] else None
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[5]) else None
+        return dx, dw1, db1, dw2, db2, dres
+
+
+def mlp(x, w1, b1, w2, b2, residual=None):
+    """residual + (GeLU(x w1^T + b1) w2^T + b2): ParallelMLP + bias-dropout-add at p = 0."""
+    if _needs_grad(x, w1, b1, w2, b2, residual):
+        return _MlpFn.apply(x, w1, b1, w2, b2, residual)
+    return ops.linear(ops.linear(x, w1, b1, gelu=True), w2, b2, residual=residual)
+
+
+# ------------------------------------------------------------------------------------ layernorm
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        y, mean, rstd = ops.layernorm(x, gamma, beta, eps, return_stats=True)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dy = _c(dy)
+        rows, h = x.shape
+        dx = torch.empty_like(x)
+        dgamma = torch.zeros(h, dtype=torch.float32, device=x.device)
+        dbeta = torch.zeros(h, dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.emdr2_layernorm_bwd(
+                _DT[x.dtype], ops._ptr(dy), dy.stride(0), ops._ptr(x), x.stride(0), ops._ptr(gamma),
+                ops._ptr(mean), ops._ptr(rstd), None, 0, ops._ptr(dx), dx.stride(0), ops._ptr(dgamma),
+                ops._ptr(dbeta), rows, h, ops._stream(x.device)), "emdr2_layernorm_bwd")
+        return dx, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    if _needs_grad(x, gamma, beta):
+        return _LayerNormFn.apply(x, gamma, beta, eps)
+    return ops.layernorm(x, gamma, beta, eps)
+
+
+# ------------------------------------------------------------------------------------ attention
+def _attention_bwd(q, k, v, o, dout, dq, dk, dv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, causal,
+                   scale, lse):
+    dvec = torch.empty((batch, heads, sq), dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    p = ops._ptr
+    with torch.cuda.device(q.device):
+        _lib.check(lib.emdr2_attention_bwd(
+            _DT[q.dtype], p(q), q.stride(0), p(k), k.stride(0), p(v), v.stride(0), p(o), o.stride(0),
+            p(dout), dout.stride(0), p(dq), dq.stride(0), p(dk), dk.stride(0), p(dv), dv.stride(0),
+            batch, heads, sq, sk, p(q_pad), p(k_pad), p(q_live), p(k_live), 1 if causal else 0, float(scale),
+            p(lse), p(dvec), ops._stream(q.device)), "emdr2_attention_bwd")
+
+
+def _u8(m, device):
+    return None if m is None else m.to(device=device, dtype=torch.uint8).contiguous()
+
+
+class _SelfAttentionFn(torch.autograd.Function):
+    """ctx = attention(q, k, v) with q | k | v the three column blocks of one [tokens, 3h] tensor."""
+
+    @staticmethod
+    def forward(ctx, qkv, batch, heads, seq, pad, live, causal, scale):
+        h = heads * 64
+        pad, live = _u8(pad, qkv.device), _u8(live, qkv.device)
+        out, lse = ops.attention(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], batch, heads, seq, seq, q_pad=pad,
+                                 k_pad=pad, causal=causal, scale=scale, return_lse=True, q_live=live, k_live=live)
+        ctx.save_for_backward(qkv, out, lse, pad, live)
+        ctx.cfg = (batch, heads, seq, causal, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse, pad, live = ctx.saved_tensors
+        batch, heads, seq, causal, scale = ctx.cfg
+        h = heads * 64
+        dout = _c(dout)
+        dqkv = torch.empty_like(qkv)
+        _attention_bwd(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], out, dout, dqkv[:, :h], dqkv[:, h:2 * h],
+                       dqkv[:, 2 * h:], batch, heads, seq, seq, pad, pad, live, live, causal, scale, lse)
+        return dqkv, None, None, None, None, None, None, None
+
+
+class _CrossAttentionFn(torch.autograd.Function):
+    """ctx = attention(q, k, v) with k | v the two column blocks of one [batch*sk, 2h] tensor."""
+
+    @staticmethod
+    def forward(ctx, q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale):
+        h = heads * 64
+        q_pad, k_pad = _u8(q_pad, q.device), _u8(k_pad, q.device)
+        q_live, k_live = _u8(q_live, q.device), _u8(k_live, q.device)
+        out, lse = ops.attention(q, kv[:, :h], kv[:, h:], batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad,
+                                 scale=scale, return_lse=True, q_live=q_live, k_live=k_live)
+        ctx.save_for_backward(q, kv, out, lse, q_pad, k_pad, q_live, k_live)
+        ctx.cfg = (batch, heads, sq, sk, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv, out, lse, q_pad, k_pad, q_live, k_live = ctx.saved_tensors
+        batch, heads, sq, sk, scale = ctx.cfg
+        h = heads * 64
+        dout = _c(dout)
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        _attention_bwd(q, kv[:, :h], kv[:, h:], out, dout, dq, dkv[:, :h], dkv[:, h:], batch, heads, sq, sk,
+                       q_pad, k_pad, q_live, k_live, False, scale, lse)
+        return (dq, dkv) + (None,) * 9
+
+
+def self_attention(qkv, batch, heads, seq, pad=None, live=None, causal=False, scale=0.125):
+    if _needs_grad(qkv):
+        return _SelfAttentionFn.apply(qkv, batch, heads, seq, pad, live, causal, scale)
+    h = heads * 64
+    return ops.attention(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], batch, heads, seq, seq, q_pad=pad, k_pad=pad,
+                         causal=causal, scale=scale, q_live=live, k_live=live)
+
+
+def cross_attention(q, kv, batch, heads, sq, sk, q_pad=None, k_pad=None, q_live=None, k_live=None, scale=0.125):
+    if _needs_grad(q, kv):
+        return _CrossAttentionFn.apply(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale)
+    h = heads * 64
+    return ops.attention(q, kv[:, :h], kv[:, h:], batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad, scale=scale,
+                         q_live=q_live, k_live=k_live)
+
+
+# ------------------------------------------------------------------------------------ embedding
+class _EmbeddingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, word, pos, types, type_emb):
+        ctx.save_for_backward(ids, types)
+        ctx.shapes = (word.shape, pos.shape, None if type_emb is None else type_emb.shape, word.dtype)
+        return ops.embedding(ids, word, pos, types, type_emb)
+
+    @staticmethod
+    def backward(ctx, dx):
+        ids, types = ctx.saved_tensors
+        wshape, pshape, tshape, dtype = ctx.shapes
+        dx = dx.contiguous()
+        dev = dx.device
+        dword = torch.zeros(wshape, dtype=torch.float32, device=dev)
+        dpos = torch.zeros(pshape, dtype=torch.float32, device=dev)
+        dtyp = torch.zeros(tshape, dtype=torch.float32, device=dev) if (tshape is not None and types is not None) else None
+        ids2 = ids.to(torch.int64).contiguous()
+        ty2 = None if types is None else types.to(torch.int64).contiguous()
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            _lib.check(lib.emdr2_embedding_bwd(
+                _DT[dtype], ops._ptr(dx), ops._ptr(ids2), ops._ptr(ty2), ops._ptr(dword), ops._ptr(dpos),
+                ops._ptr(dtyp), ids2.numel(), ids2.shape[-1], wshape[1], wshape[0],
+                0 if tshape is None else tshape[0], ops._stream(dev)), "emdr2_embedding_bwd")
+        return (None, dword.to(dtype), dpos.to(dtype), None,
+                None if tshape is None else (dtyp.to(dtype) if dtyp is not None else torch.zeros(tshape, dtype=dtype, device=dev)))
+
+
+def embedding(ids, word, pos, types=None, type_emb=None):
+    if _needs_grad(word, pos, type_emb):
+        return _EmbeddingFn.apply(ids, word, pos, types, type_emb if types is not None else None)
+    return ops.embedding(ids, word, pos, types, type_emb)
+
+
+# -------------------------------------------------------------------------------- token_logprob
+class _TokenLogprobFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        lp, lse = ops.token_logprob(logits, labels)
+        ctx.save_for_backward(logits, labels, lse)
+        return lp
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, lse = ctx.saved_tensors
+        vocab = logits.shape[-1]
+        l2 = logits.reshape(-1, vocab)
+        if l2.stride(1) != 1:
+            l2 = l2.contiguous()
+        lab = labels.to(torch.int64).reshape(-1).contiguous()
+        gg = g.to(torch.float32).reshape(-1).contiguous()
+        dl = torch.empty((l2.shape[0], vocab), dtype=logits.dtype, device=logits.device)
+        lib = _lib.load()
+        with torch.cuda.device(logits.device):
+            _lib.check(lib.emdr2_token_logprob_bwd(
+                _DT[logits.dtype], ops._ptr(l2), max(vocab, l2.stride(0)), ops._ptr(lab), ops._ptr(lse.reshape(-1).contiguous()),
+                ops._ptr(gg), ops._ptr(dl), vocab, l2.shape[0], vocab, ops._stream(logits.device)),
+                "emdr2_token_logprob_bwd")
+        return dl.view(logits.shape), None
+
+
+def token_logprob(logits, labels):
+    """log p(label) per row, differentiable w.r.t. the logits."""
+    if _needs_grad(logits):
+        return _TokenLogprobFn.apply(logits, labels)
+    return ops.token_logprob(logits, labels)[0]

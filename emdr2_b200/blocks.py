@@ -1,4 +1,4 @@
-"""BERT tower and T5 reader modules on the sm_100a block kernels (forward path).
+"""BERT tower and T5 reader modules on the sm_100a block kernels (forward and backward).
 
 Host-side mirror of the reference's model surface (DevSinghSachan/emdr2 @ edb8cf67):
 
@@ -24,13 +24,16 @@ QKV layout: the reference packs the fused projection as [np, hn, 3] along the ou
 keyed on the parameter version.
 
 Dropout is off (p = 0 / eval): hidden_dropout and attention_dropout are identity here.
-No CPU path: forward on a CPU tensor raises.
+Training: every op dispatches through emdr2_b200/autograd.py, whose backward passes are kernels of
+the same library (csrc/gemm.cu MN-major/split-K products, attention_bwd.cu, rowops_bwd.cu); under
+torch.no_grad() the plain forward ops run.  No CPU path: forward on a CPU tensor raises.
 """
 import math
 
 import torch
 import torch.nn as nn
 
+from . import autograd as ag
 from . import ops
 
 PAD_ID = 0   # tokenizer.pad; masks are `ids >= 1` (megatron/data/mask_creation_utils.py:17-26)
@@ -42,8 +45,8 @@ class Linear(nn.Module):
         self.weight = nn.Parameter(torch.empty(out_features, in_features, dtype=dtype))
         self.bias = nn.Parameter(torch.zeros(out_features, dtype=dtype))
 
-    def forward(self, x, gelu=False, residual=None):
-        return ops.linear(x, self.weight, self.bias, gelu=gelu, residual=residual)
+    def forward(self, x, residual=None):
+        return ag.linear(x, self.weight, self.bias, residual=residual)
 
 
 class LayerNorm(nn.Module):
@@ -54,7 +57,7 @@ class LayerNorm(nn.Module):
         self.eps = eps
 
     def forward(self, x):
-        return ops.layernorm(x, self.weight, self.bias, self.eps)
+        return ag.layernorm(x, self.weight, self.bias, self.eps)
 
 
 def _unpack_rows(t, heads, hn, splits):
@@ -83,8 +86,14 @@ class _PackedProjection(nn.Module):
         return self._cache[1], self._cache[2]
 
     def forward(self, x):
-        w, b = self._packed()
-        return ops.linear(x, w, b)
+        if torch.is_grad_enabled() and (self.weight.requires_grad or x.requires_grad):
+            # training: the permutation is part of the graph so gradients land in the parameter's
+            # (reference) row order
+            w = _unpack_rows(self.weight, self.heads, self.hn, self.splits)
+            b = _unpack_rows(self.bias, self.heads, self.hn, self.splits)
+        else:
+            w, b = self._packed()
+        return ag.linear(x, w, b)
 
 
 class ParallelAttention(nn.Module):
@@ -103,18 +112,16 @@ class ParallelAttention(nn.Module):
         self.scale = 1.0 / math.sqrt(hidden // heads)
 
     def forward(self, x, batch, sq, q_pad, residual, causal=False, encoder_output=None, sk=None,
-                k_pad=None):
-        h = self.hidden
+                k_pad=None, q_live=None, k_live=None):
         if self.attention_type == "self":
             qkv = self.query_key_value(x)
-            q, k, v = qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:]
-            sk, k_pad = sq, q_pad
+            ctx = ag.self_attention(qkv, batch, self.heads, sq, pad=q_pad, live=q_live, causal=causal,
+                                    scale=self.scale)
         else:
             q = self.query(x)
             kv = self.key_value(encoder_output)
-            k, v = kv[:, :h], kv[:, h:]
-        ctx = ops.attention(q, k, v, batch, self.heads, sq, sk, q_pad=q_pad, k_pad=k_pad,
-                            causal=causal, scale=self.scale)
+            ctx = ag.cross_attention(q, kv, batch, self.heads, sq, sk, q_pad=q_pad, k_pad=k_pad,
+                                     q_live=q_live, k_live=k_live, scale=self.scale)
         return self.dense(ctx, residual=residual)          # bias + residual fused (dropout p=0)
 
 
@@ -125,7 +132,8 @@ class ParallelMLP(nn.Module):
         self.dense_4h_to_h = Linear(ffn, hidden, dtype)
 
     def forward(self, x, residual):
-        return self.dense_4h_to_h(self.dense_h_to_4h(x, gelu=True), residual=residual)
+        return ag.mlp(x, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, self.dense_4h_to_h.weight,
+                      self.dense_4h_to_h.bias, residual=residual)
 
 
 class ParallelTransformerLayer(nn.Module):
@@ -140,12 +148,14 @@ class ParallelTransformerLayer(nn.Module):
             self.post_inter_attention_layernorm = LayerNorm(hidden, eps, dtype)
         self.mlp = ParallelMLP(hidden, ffn, dtype)
 
-    def forward(self, x, batch, seq, pad, causal=False, encoder_output=None, enc_seq=None, enc_pad=None):
-        x = self.self_attention(self.input_layernorm(x), batch, seq, pad, residual=x, causal=causal)
+    def forward(self, x, batch, seq, pad, causal=False, encoder_output=None, enc_seq=None, enc_pad=None,
+                q_live=None, enc_live=None):
+        x = self.self_attention(self.input_layernorm(x), batch, seq, pad, residual=x, causal=causal,
+                                q_live=q_live)
         ln = self.post_attention_layernorm(x)
         if self.layer_type == "decoder":
             x = self.inter_attention(ln, batch, seq, pad, residual=x, encoder_output=encoder_output,
-                                     sk=enc_seq, k_pad=enc_pad)
+                                     sk=enc_seq, k_pad=enc_pad, q_live=q_live, k_live=enc_live)
             ln = self.post_inter_attention_layernorm(x)
         return self.mlp(ln, residual=x)
 
@@ -178,8 +188,8 @@ class Embedding(nn.Module):
 
     def forward(self, input_ids, tokentype_ids=None):
         typ = self.tokentype_embeddings.weight if tokentype_ids is not None else None
-        return ops.embedding(input_ids, self.word_embeddings.weight, self.position_embeddings.weight,
-                             tokentype_ids, typ)
+        return ag.embedding(input_ids, self.word_embeddings.weight, self.position_embeddings.weight,
+                            tokentype_ids, typ)
 
 
 class TransformerLanguageModel(nn.Module):
@@ -196,11 +206,16 @@ class TransformerLanguageModel(nn.Module):
             self.decoder = ParallelTransformer(cfg["hidden"], cfg["heads"], cfg["ffn"], cfg["layers"],
                                                cfg.get("eps", 1e-5), d, layer_type="decoder")
 
+    #: True: attention skips padding (zeros at padding positions, identical results at every
+    #: non-padding position); False: the reference's values at padding positions too.
+    skip_padding = True
+
     def encode(self, ids, tokentype_ids=None):
         b, s = ids.shape
         pad = ids < 1
         x = self.embedding(ids, tokentype_ids)
-        return self.encoder(x, b, s, pad).view(b, s, self.hidden)
+        q_live = ops.live_blocks(pad) if self.skip_padding else None
+        return self.encoder(x, b, s, pad, q_live=q_live).view(b, s, self.hidden)
 
     def decode(self, dec_ids, enc_states, enc_pad):
         """enc_states [b, sk, h] (sk may be K*S: FiD concatenation, emdr2_model.py:159-164)."""
@@ -208,8 +223,11 @@ class TransformerLanguageModel(nn.Module):
         sk = enc_states.shape[1]
         x = self.embedding(dec_ids)
         enc2d = enc_states.reshape(b * sk, self.hidden)
-        y = self.decoder(x, b, sq, dec_ids < 1, causal=True, encoder_output=enc2d, enc_seq=sk,
-                         enc_pad=enc_pad)
+        dec_pad = dec_ids < 1
+        q_live = ops.live_blocks(dec_pad) if self.skip_padding else None
+        enc_live = ops.live_blocks(enc_pad) if self.skip_padding else None
+        y = self.decoder(x, b, sq, dec_pad, causal=True, encoder_output=enc2d, enc_seq=sk,
+                         enc_pad=enc_pad, q_live=q_live, enc_live=enc_live)
         return y.view(b, sq, self.hidden)
 
 
@@ -227,12 +245,10 @@ class BertTower(nn.Module):
         super().__init__()
         self.language_model = TransformerLanguageModel(cfg, num_tokentypes, False, vocab_size)
 
-    @torch.no_grad()
     def forward(self, input_ids, attention_mask=None, tokentype_ids=None):
         _require_cuda(input_ids)
         return self.language_model.encode(input_ids, tokentype_ids)[:, 0, :]
 
-    @torch.no_grad()
     def hidden_states(self, input_ids, tokentype_ids=None):
         return self.language_model.encode(input_ids, tokentype_ids)
 
@@ -256,7 +272,6 @@ class T5Reader(nn.Module):
         self.language_model = TransformerLanguageModel(cfg, num_tokentypes, True, vocab_size)
         self.lm_head = _LMHead(vocab_size or cfg["vocab"], cfg["dtype"])
 
-    @torch.no_grad()
     def forward(self, encoder_input_ids, decoder_input_ids, encoder_attn_mask=None,
                 decoder_attn_mask=None, encoder_decoder_attn_mask=None, tokentype_ids=None,
                 lm_labels=None, enc_hidden_states=None, output_enc_hidden=False,
@@ -274,11 +289,10 @@ class T5Reader(nn.Module):
         dec = lm.decode(decoder_input_ids, enc, mask_ids < 1)
         b, sq, h = dec.shape
         word = lm.embedding.word_embeddings.weight
-        logits = ops.linear(dec.view(b * sq, h), word, self.lm_head.bias).view(b, sq, word.shape[0])
+        logits = ag.linear(dec.reshape(b * sq, h), word, self.lm_head.bias).view(b, sq, word.shape[0])
         if lm_labels is None:
             return logits, enc
-        loss = torch.nn.functional.cross_entropy(logits.float().view(b * sq, -1), lm_labels.view(-1),
-                                                 reduction="none").view(b, sq)
+        loss = -ag.token_logprob(logits, lm_labels)          # vocab_parallel_cross_entropy (t5_model.py:139-146)
         return loss, enc
 
 

@@ -76,6 +76,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t head = blockIdx.y;
   const uint32_t b = blockIdx.z;
   const uint32_t nblk = (a.sk + kAttnBK - 1) / kAttnBK;
+  // Optional padding skip (results at padding query positions are then zero / partial instead of
+  // the reference's uniform average; no non-padding position can observe the difference):
+  //   k_live[b, j] == 0: key block j of batch b is all padding -> not loaded, not multiplied (its
+  //                      probabilities are exactly 0 for every non-padding query);
+  //   q_live[b, i] == 0: query block i is all padding -> the CTA just stores zeros.
+  const uint8_t* k_live = a.k_live ? a.k_live + static_cast<size_t>(b) * nblk : nullptr;
+  auto next_live = [&](uint32_t j) {   // first live key block >= j (nblk if none)
+    while (j < nblk && k_live && k_live[j] == 0) ++j;
+    return j;
+  };
+  const bool cta_dead = a.q_live && a.q_live[static_cast<size_t>(b) * gridDim.x + blockIdx.x] == 0;
   const int32_t col_h = static_cast<int32_t>(head * kAttnHeadDim);
 
   if (threadIdx.x == 0) {
@@ -111,13 +122,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
   reg_dealloc<40>();   // warpgroup 0 (TMA, MMA, allocator, spare) hands its registers to the softmax warps
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    if (lane == 0 && !cta_dead) {
       const uint32_t qbar = smem_u32(&bars->q_full);
       mbar_arrive_expect_tx(qbar, kAttnTileBytes);
       tma_load_3d(smem_base + off_q, &tmap_q, qbar, col_h, static_cast<int32_t>(q0),
                   static_cast<int32_t>(b), kEvictNormal);
       uint32_t stage = 0, phase = 0;
-      for (uint32_t j = 0; j < nblk; ++j) {
+      for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1)) {
         mbar_wait(smem_u32(&bars->kv_empty[stage]), phase ^ 1);
         const uint32_t fbar = smem_u32(&bars->kv_full[stage]);
         mbar_arrive_expect_tx(fbar, 2 * kAttnTileBytes);
@@ -134,14 +145,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && !cta_dead) {
       mbar_wait(smem_u32(&bars->q_full), 0);
       tc_fence_after();
       const uint64_t qdesc = smem_desc_sw128(smem_base + off_q);
       uint32_t ld_stage = 0, ld_phase = 0;  // stage/phase of the next S block to issue
-      auto issue_s = [&](uint32_t j) {
+      auto issue_s = [&](uint32_t n) {   // n = running index of the live block
         mbar_wait(smem_u32(&bars->kv_full[ld_stage]), ld_phase);
-        mbar_wait(smem_u32(&bars->s_empty), (j & 1) ^ 1);
+        mbar_wait(smem_u32(&bars->s_empty), (n & 1) ^ 1);
         tc_fence_after();
         const uint64_t kdesc = smem_desc_sw128(smem_base + off_kv + ld_stage * 2 * kAttnTileBytes);
 #pragma unroll
@@ -155,10 +166,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       };
       issue_s(0);
-      uint32_t stage = 0;
-      for (uint32_t j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) issue_s(j + 1);
-        mbar_wait(smem_u32(&bars->p_full), j & 1);
+      uint32_t stage = 0, n = 0;
+      for (uint32_t j = next_live(0); j < nblk; ++n) {
+        j = next_live(j + 1);
+        if (j < nblk) issue_s(n + 1);
+        mbar_wait(smem_u32(&bars->p_full), n & 1);
         tc_fence_after();
         const uint32_t vbase = smem_base + off_kv + stage * 2 * kAttnTileBytes + kAttnTileBytes;
 #pragma unroll
@@ -207,9 +219,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
     };
 
-    for (uint32_t j = 0; j < nblk; ++j) {
+    if (cta_dead) {   // all-padding query block: zero rows, no attention work
+      uint8_t* o_row = smem + off_q + row * 128u;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(o_row + g * 16) = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 4 && lane == 0) {
+        tma_store_3d(&tmap_o, smem_base + off_q, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b));
+        tma_store_commit();
+        tma_store_wait<0>();
+      }
+    } else {
+    uint32_t n = 0;   // running index of the live key block
+    for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1), ++n) {
       const uint32_t kb0 = j * kAttnBK;
-      mbar_wait(smem_u32(&bars->s_full), j & 1);
+      mbar_wait(smem_u32(&bars->s_full), n & 1);
       tc_fence_after();
       float alpha = 1.f;
       float m_new = m_run;
@@ -217,7 +242,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // ---- key-side mask bits of this block (same in every warp), 32 keys per word
       uint32_t km[4] = {0u, 0u, 0u, 0u};
       uint32_t valid = kAttnBK;
-      bool plain = true;
+      bool plain = true;        // no masking at all in this block for this row
+      bool constant = false;    // every score of this row in this block is the masked value
+      bool causal_row = false;  // the causal diagonal crosses this block for this row
       if (warp_active) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -226,14 +253,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
           km[c] = __ballot_sync(kFull, f);
         }
         valid = min(static_cast<uint32_t>(kAttnBK), a.sk - kb0);
-        const bool causal_hit = a.causal && (kb0 + kAttnBK - 1 > qi);
-        plain = !q_is_pad && !causal_hit && valid == kAttnBK && (km[0] | km[1] | km[2] | km[3]) == 0u;
+        causal_row = a.causal && (kb0 + kAttnBK - 1 > qi);
+        plain = !q_is_pad && !causal_row && valid == kAttnBK && (km[0] | km[1] | km[2] | km[3]) == 0u;
+        constant = valid == kAttnBK && (q_is_pad || (km[0] & km[1] & km[2] & km[3]) == 0xffffffffu ||
+                                        (a.causal && kb0 > qi));
       }
       // Loads the scores of keys [half*64, half*64+64) of the block into t as masked log2-domain
       // values and returns their maximum.  Half 0 is read twice (max pass, then exp pass) so that
       // only 64 scores are ever live next to the 64 output accumulators.
       auto load_scores = [&](auto half_c) -> float {
         constexpr int half = decltype(half_c)::value;
+        if (constant) {   // warp-divergent but cheap: nothing to read, nothing to compare
+#pragma unroll
+          for (int c = 0; c < 64; ++c) t[c] = __float_as_uint(kMaskedLog2);
+          return kMaskedLog2;
+        }
         const uint32_t s_addr = tmem_base + lane_tmem + half * 64;
         tmem_ld_32x32b_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&t[0]));
         tmem_ld_32x32b_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&t[32]));
@@ -246,13 +280,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
             t[c] = __float_as_uint(x);
             mx = fmaxf(mx, x);
           }
+        } else if (!causal_row && valid == kAttnBK) {   // key-padding bits only
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const uint32_t cc = half * 64 + c;
+            float x = __uint_as_float(t[c]) * a.scale_log2;
+            x = (km[cc >> 5] & (1u << (cc & 31))) ? kMaskedLog2 : x;
+            t[c] = __float_as_uint(x);
+            mx = fmaxf(mx, x);
+          }
         } else {
 #pragma unroll
           for (int c = 0; c < 64; ++c) {
             const uint32_t cc = half * 64 + c;
             float x = __uint_as_float(t[c]) * a.scale_log2;
-            const bool masked = q_is_pad || ((km[cc >> 5] >> (cc & 31)) & 1u) ||
-                                (a.causal && kb0 + cc > qi);
+            const bool masked = ((km[cc >> 5] >> (cc & 31)) & 1u) || (a.causal && kb0 + cc > qi);
             x = masked ? kMaskedLog2 : x;
             x = (cc < valid) ? x : __uint_as_float(0xff800000u);
             t[c] = __float_as_uint(x);
@@ -264,6 +306,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // exp2(t - m_new) of the 64 live scores -> 16-bit -> P rows in shared memory; returns the sum
       auto write_probs = [&](auto half_c) -> float {
         constexpr int half = decltype(half_c)::value;
+        if (constant) {   // one probability value for the whole row of this block
+          const float p = ex2(kMaskedLog2 - m_new);
+          const uint32_t w = pack2<kBf16>(p, p);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(p_row + half * kAttnTileBytes + g * 16) = make_uint4(w, w, w, w);
+          return 64.f * p;
+        }
         float sum = 0.f;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -284,8 +334,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
       // O_{j-1} must have landed (and P's buffer be free) before P_j is written; folding it in
       // first keeps the score registers and the tcgen05.ld staging registers from overlapping
-      if (j > 0) {
-        mbar_wait(smem_u32(&bars->o_full), (j - 1) & 1);
+      if (n > 0) {
+        mbar_wait(smem_u32(&bars->o_full), (n - 1) & 1);
         tc_fence_after();
         if (warp_active) accumulate_o(alpha_prev);
       }
@@ -312,7 +362,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
     }
 
-    mbar_wait(smem_u32(&bars->o_full), (nblk - 1) & 1);
+    mbar_wait(smem_u32(&bars->o_full), (n - 1) & 1);   // n >= 1: the host marks at least one block live
     tc_fence_after();
     if (warp_active) {
       accumulate_o(alpha_prev);
@@ -338,6 +388,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tma_store_commit();
       tma_store_wait<0>();
     }
+    }   // !cta_dead
   }
 
   tc_fence_before();

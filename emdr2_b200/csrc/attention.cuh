@@ -51,8 +51,32 @@ struct AttnArgs {
   float scale_log2;        // scale * log2(e)
   const uint8_t* q_pad;    // [batch, sq] or nullptr (1 = padding token)
   const uint8_t* k_pad;    // [batch, sk] or nullptr
+  const uint8_t* q_live;   // [batch, ceil(sq/128)] or nullptr: 0 = query block is all padding (store zeros)
+  const uint8_t* k_live;   // [batch, ceil(sk/128)] or nullptr: 0 = key block is all padding (skipped);
+                           // every batch entry must have at least one live key block
   float* lse;              // [batch, heads, sq] natural-log sum-exp of the masked scores, or nullptr
 };
+
+struct AttnBwdArgs {
+  uint32_t batch, heads, sq, sk;
+  uint32_t causal;
+  uint32_t idesc_s;        // M=128, N=128, A/B K-major
+  uint32_t idesc_o;        // M=128, N=64,  B MN-major
+  float scale, scale_log2;
+  const uint8_t* q_pad;
+  const uint8_t* k_pad;
+  const uint8_t* q_live;
+  const uint8_t* k_live;
+  const float* lse;        // [batch, heads, sq] from the forward
+  const float* dvec;       // [batch, heads, sq] rowsum(dO * O), from launch_attention_bwd_prep
+};
+
+cudaError_t attention_bwd_prepare();
+cudaError_t launch_attention_bwd_prep(bool bf16, const void* dout, int64_t lddo, const void* out, int64_t ldo,
+                                      float* dvec, int batch, int heads, int sq, cudaStream_t stream);
+cudaError_t launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                                 const CUtensorMap& tdo, const CUtensorMap& tdq, const CUtensorMap& tdk,
+                                 const CUtensorMap& tdv, const AttnBwdArgs& a, bool bf16, cudaStream_t stream);
 
 cudaError_t attention_prepare();
 void launch_attention_fwd(const CUtensorMap& tmap_q, const CUtensorMap& tmap_k,

@@ -1,0 +1,583 @@
+// Backward of the fused attention (attention.cu), sm_100a only, head dim 64.
+//
+// Given dO, the saved Q, K, V, O and the per-row log-sum-exp L of the forward:
+//   D_i   = sum_d dO_i,d * O_i,d
+//   P_ij  = exp(s_ij - L_i),  s_ij = scale * q_i.k_j with masked entries replaced by -10000
+//   dV_j  = sum_i P_ij dO_i
+//   dP_ij = dO_i . v_j
+//   dS_ij = P_ij (dP_ij - D_i) * scale, and 0 where the score was masked (masked_fill replaces the
+//           score, so no gradient reaches q.k there — reference megatron/model/bert_model.py:31-33,
+//           t5_model.py:28-30 under autograd)
+//   dQ_i  = sum_j dS_ij k_j,   dK_j = sum_i dS_ij q_i
+// This is the autograd of transformer.py:301-383 (baddbmm, mask+softmax, bmm) without ever
+// materialising the [b, np, sq, sk] tensors.  Two kernels, both shaped like the forward (TMA ring,
+// tcgen05 S-type products into TMEM, one thread per row for the elementwise part, P/dS handed back
+// to the tensor core through shared memory), so neither needs atomics:
+//   attention_bwd_dq_kernel    one CTA per 128-query block, loops over key blocks,   dQ in TMEM
+//   attention_bwd_dkv_kernel   one CTA per 128-key block,   loops over query blocks, dK and dV in TMEM
+#include "attention.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
+#include "ptx.cuh"
+
+namespace emdr2 {
+using namespace ptx;
+
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr float kMaskedLog2 = -10000.0f * 1.4426950408889634f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kTile = kAttnTileBytes;   // 128 x 64 x 2 B
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (kBf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+  if constexpr (kBf16) return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+  else return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+
+// D[b, h, i] = sum_d dO[b, i, h, d] * O[b, i, h, d]
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+attention_bwd_prep_kernel(const uint16_t* __restrict__ dout, int64_t lddo, const uint16_t* __restrict__ out,
+                          int64_t ldo, float* __restrict__ dvec, int batch, int heads, int sq) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;   // (token, head)
+  const int64_t total = static_cast<int64_t>(batch) * sq * heads;
+  if (idx >= total) return;
+  const int64_t tok = idx / heads;
+  const int h = static_cast<int>(idx % heads);
+  const uint16_t* a = dout + tok * lddo + h * 64;
+  const uint16_t* b = out + tok * ldo + h * 64;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(a + c * 8));
+    const uint4 y = __ldg(reinterpret_cast<const uint4*>(b + c * 8));
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 p = unpack2<kBf16>(xw[i]), q = unpack2<kBf16>(yw[i]);
+      acc = fmaf(p.x, q.x, acc);
+      acc = fmaf(p.y, q.y, acc);
+    }
+  }
+  const int64_t bi = tok / sq, i = tok % sq;
+  dvec[(bi * heads + h) * sq + i] = acc;
+}
+
+struct BwdBars {
+  uint64_t fixed_full;     // the CTA's own tiles (Q,dO resp. K,V)
+  uint64_t ring_full[2];   // streamed tiles (K,V resp. Q,dO)
+  uint64_t ring_empty[2];
+  uint64_t sdp_full;       // S and dP products landed in TMEM
+  uint64_t sdp_empty;      // row threads have read them (4 warps)
+  uint64_t pds_full;       // P / dS written to shared memory (4 warps)
+  uint64_t acc_done;       // accumulating products of this block issued and complete
+  uint32_t tmem_base;
+};
+
+// ============================================================================ dQ
+// smem: Q 16K | dO 16K | ring 2 x (K 16K + V 16K) | dS 32K | bars
+constexpr int kDqSmem = 2 * kTile + 2 * 2 * kTile + 2 * kTile + 256;
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                        const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr uint32_t off_q = 0, off_do = kTile, off_ring = 2 * kTile, off_ds = off_ring + 4 * kTile,
+                     off_bar = off_ds + 2 * kTile;
+  BwdBars* bars = reinterpret_cast<BwdBars*>(smem + off_bar);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q0 = blockIdx.x * kAttnBQ, head = blockIdx.y, b = blockIdx.z;
+  const uint32_t nblk = (a.sk + kAttnBK - 1) / kAttnBK;
+  const int32_t col_h = static_cast<int32_t>(head * kAttnHeadDim);
+  const uint8_t* k_live = a.k_live ? a.k_live + static_cast<size_t>(b) * nblk : nullptr;
+  auto next_live = [&](uint32_t j) {
+    while (j < nblk && k_live && k_live[j] == 0) ++j;
+    return j;
+  };
+  const bool cta_dead = a.q_live && a.q_live[static_cast<size_t>(b) * gridDim.x + blockIdx.x] == 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars->fixed_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bars->ring_full[s]), 1);
+      mbar_init(smem_u32(&bars->ring_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bars->sdp_full), 1);
+    mbar_init(smem_u32(&bars->sdp_empty), 4);
+    mbar_init(smem_u32(&bars->pds_full), 4);
+    mbar_init(smem_u32(&bars->acc_done), 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0 && !cta_dead) {
+      const uint32_t fb = smem_u32(&bars->fixed_full);
+      mbar_arrive_expect_tx(fb, 2 * kTile);
+      tma_load_3d(smem_base + off_q, &tmap_q, fb, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b), kEvictNormal);
+      tma_load_3d(smem_base + off_do, &tmap_do, fb, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b), kEvictNormal);
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1)) {
+        mbar_wait(smem_u32(&bars->ring_empty[stage]), phase ^ 1);
+        const uint32_t fbar = smem_u32(&bars->ring_full[stage]);
+        mbar_arrive_expect_tx(fbar, 2 * kTile);
+        const uint32_t dst = smem_base + off_ring + stage * 2 * kTile;
+        tma_load_3d(dst, &tmap_k, fbar, col_h, static_cast<int32_t>(j * kAttnBK), static_cast<int32_t>(b), kEvictLast);
+        tma_load_3d(dst + kTile, &tmap_v, fbar, col_h, static_cast<int32_t>(j * kAttnBK), static_cast<int32_t>(b), kEvictLast);
+        if (++stage == 2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && !cta_dead) {
+      mbar_wait(smem_u32(&bars->fixed_full), 0);
+      tc_fence_after();
+      const uint64_t qdesc = smem_desc_sw128(smem_base + off_q);
+      const uint64_t dodesc = smem_desc_sw128(smem_base + off_do);
+      uint32_t stage = 0, phase = 0, n = 0;
+      for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1), ++n) {
+        mbar_wait(smem_u32(&bars->ring_full[stage]), phase);
+        mbar_wait(smem_u32(&bars->sdp_empty), (n & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t kbase = smem_base + off_ring + stage * 2 * kTile;
+        const uint64_t kdesc = smem_desc_sw128(kbase), vdesc = smem_desc_sw128(kbase + kTile);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // S = Q . K^T
+          mma_f16_ss(tmem_s, qdesc + static_cast<uint64_t>(kk * 2), kdesc + static_cast<uint64_t>(kk * 2),
+                     a.idesc_s, kk != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // dP = dO . V^T
+          mma_f16_ss(tmem_dp, dodesc + static_cast<uint64_t>(kk * 2), vdesc + static_cast<uint64_t>(kk * 2),
+                     a.idesc_s, kk != 0 ? 1u : 0u);
+        mma_commit(smem_u32(&bars->sdp_full));
+        mbar_wait(smem_u32(&bars->pds_full), n & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // dQ += dS . K   (A = dS K-major, B = K MN-major)
+          const uint64_t dsdesc = smem_desc_sw128(smem_base + off_ds + (ks >> 2) * kTile) +
+                                  static_cast<uint64_t>((ks & 3) * 2);
+          const uint64_t kmn = smem_desc_sw128_mn(kbase + ks * 2048, 1024, 1024);
+          mma_f16_ss(tmem_dq, dsdesc, kmn, a.idesc_o, (n != 0 || ks != 0) ? 1u : 0u);
+        }
+        mma_commit(smem_u32(&bars->ring_empty[stage]));
+        mma_commit(smem_u32(&bars->acc_done));
+        if (++stage == 2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const uint32_t quad = warp & 3, row = quad * 32 + lane, qi = q0 + row;
+    const uint32_t lane_tmem = (quad * 32) << 16;
+    const bool row_active = qi < a.sq;
+    uint8_t* ds_row = smem + off_ds + row * 128u;
+    if (cta_dead) {
+      uint8_t* o_row = smem + off_q + row * 128u;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(o_row + g * 16) = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async_smem();
+    } else {
+      const bool q_is_pad = row_active && a.q_pad && a.q_pad[static_cast<size_t>(b) * a.sq + qi] != 0;
+      const size_t stat = (static_cast<size_t>(b) * a.heads + head) * a.sq + (row_active ? qi : 0);
+      const float lse2 = a.lse[stat] * kLog2e;
+      const float dsum = a.dvec[stat];
+      uint32_t n = 0;
+      for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1), ++n) {
+        const uint32_t kb0 = j * kAttnBK;
+        uint32_t km[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t idx = kb0 + c * 32 + lane;
+          const bool f = a.k_pad && idx < a.sk && a.k_pad[static_cast<size_t>(b) * a.sk + idx] != 0;
+          km[c] = __ballot_sync(kFull, f);
+        }
+        const uint32_t valid = min(static_cast<uint32_t>(kAttnBK), a.sk - kb0);
+        mbar_wait(smem_u32(&bars->sdp_full), n & 1);
+        tc_fence_after();
+        if (n > 0) {   // dS buffer is free once the previous dQ product has consumed it
+          mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t s[64], dp[64];
+          tmem_ld_32x32b_x32(tmem_s + lane_tmem + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          tmem_ld_32x32b_x32(tmem_s + lane_tmem + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+          tmem_ld_32x32b_x32(tmem_dp + lane_tmem + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
+          tmem_ld_32x32b_x32(tmem_dp + lane_tmem + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float ds[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = g * 8 + i;
+              const uint32_t cc = half * 64 + c;
+              const bool masked = q_is_pad || ((km[cc >> 5] >> (cc & 31)) & 1u) || (a.causal && kb0 + cc > qi);
+              const float p = ex2(__uint_as_float(s[c]) * a.scale_log2 - lse2);
+              const float d = p * (__uint_as_float(dp[c]) - dsum) * a.scale;
+              ds[i] = (masked || cc >= valid || !row_active) ? 0.f : d;
+            }
+            const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+            *reinterpret_cast<uint4*>(ds_row + half * kTile + phys) =
+                make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
+                           pack2<kBf16>(ds[6], ds[7]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&bars->sdp_empty));
+          mbar_arrive(smem_u32(&bars->pds_full));
+        }
+      }
+      mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
+      tc_fence_after();
+      uint8_t* o_row = smem + off_q + row * 128u;   // Q is dead now
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tmem_dq + lane_tmem + half * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t phys = (static_cast<uint32_t>(half * 4 + g) ^ (row & 7u)) * 16u;
+          *reinterpret_cast<uint4*>(o_row + phys) = make_uint4(
+              pack2<kBf16>(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1])),
+              pack2<kBf16>(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
+              pack2<kBf16>(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
+              pack2<kBf16>(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7])));
+        }
+      }
+      fence_proxy_async_smem();
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 4 && lane == 0) {
+      tma_store_3d(&tmap_dq, smem_base + off_q, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b));
+      tma_store_commit();
+      tma_store_wait<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ============================================================================ dK, dV
+// smem: K 16K | V 16K | ring 2 x (Q 16K + dO 16K) | P^T 32K | dS^T 32K | stats 2 x 1K | bars
+constexpr int kDkvSmem = 2 * kTile + 2 * 2 * kTile + 2 * kTile + 2 * kTile + 2048 + 256;
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                         const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                         const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
+                         const AttnBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr uint32_t off_k = 0, off_v = kTile, off_ring = 2 * kTile, off_p = off_ring + 4 * kTile,
+                     off_ds = off_p + 2 * kTile, off_stat = off_ds + 2 * kTile, off_bar = off_stat + 2048;
+  BwdBars* bars = reinterpret_cast<BwdBars*>(smem + off_bar);
+  float* stat_smem = reinterpret_cast<float*>(smem + off_stat);   // [2][128] x {lse*log2e, D}
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t k0 = blockIdx.x * kAttnBK, head = blockIdx.y, b = blockIdx.z;
+  const uint32_t nqblk = (a.sq + kAttnBQ - 1) / kAttnBQ;
+  const int32_t col_h = static_cast<int32_t>(head * kAttnHeadDim);
+  const uint8_t* q_live = a.q_live ? a.q_live + static_cast<size_t>(b) * nqblk : nullptr;
+  auto next_live = [&](uint32_t i) {
+    while (i < nqblk && q_live && q_live[i] == 0) ++i;
+    return i;
+  };
+  const bool cta_dead = a.k_live && a.k_live[static_cast<size_t>(b) * gridDim.x + blockIdx.x] == 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars->fixed_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bars->ring_full[s]), 1);
+      mbar_init(smem_u32(&bars->ring_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bars->sdp_full), 1);
+    mbar_init(smem_u32(&bars->sdp_empty), 4);
+    mbar_init(smem_u32(&bars->pds_full), 4);
+    mbar_init(smem_u32(&bars->acc_done), 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320;
+
+  if (warp == 0) {
+    if (lane == 0 && !cta_dead) {
+      const uint32_t fb = smem_u32(&bars->fixed_full);
+      mbar_arrive_expect_tx(fb, 2 * kTile);
+      tma_load_3d(smem_base + off_k, &tmap_k, fb, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b), kEvictNormal);
+      tma_load_3d(smem_base + off_v, &tmap_v, fb, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b), kEvictNormal);
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t i = next_live(0); i < nqblk; i = next_live(i + 1)) {
+        mbar_wait(smem_u32(&bars->ring_empty[stage]), phase ^ 1);
+        const uint32_t fbar = smem_u32(&bars->ring_full[stage]);
+        mbar_arrive_expect_tx(fbar, 2 * kTile);
+        const uint32_t dst = smem_base + off_ring + stage * 2 * kTile;
+        tma_load_3d(dst, &tmap_q, fbar, col_h, static_cast<int32_t>(i * kAttnBQ), static_cast<int32_t>(b), kEvictLast);
+        tma_load_3d(dst + kTile, &tmap_do, fbar, col_h, static_cast<int32_t>(i * kAttnBQ), static_cast<int32_t>(b), kEvictLast);
+        if (++stage == 2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && !cta_dead) {
+      mbar_wait(smem_u32(&bars->fixed_full), 0);
+      tc_fence_after();
+      const uint64_t kdesc = smem_desc_sw128(smem_base + off_k);
+      const uint64_t vdesc = smem_desc_sw128(smem_base + off_v);
+      uint32_t stage = 0, phase = 0, n = 0;
+      for (uint32_t i = next_live(0); i < nqblk; i = next_live(i + 1), ++n) {
+        mbar_wait(smem_u32(&bars->ring_full[stage]), phase);
+        mbar_wait(smem_u32(&bars->sdp_empty), (n & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t qbase = smem_base + off_ring + stage * 2 * kTile;
+        const uint64_t qdesc = smem_desc_sw128(qbase), dodesc = smem_desc_sw128(qbase + kTile);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // S^T = K . Q^T   [keys x queries]
+          mma_f16_ss(tmem_s, kdesc + static_cast<uint64_t>(kk * 2), qdesc + static_cast<uint64_t>(kk * 2),
+                     a.idesc_s, kk != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // dP^T = V . dO^T
+          mma_f16_ss(tmem_dp, vdesc + static_cast<uint64_t>(kk * 2), dodesc + static_cast<uint64_t>(kk * 2),
+                     a.idesc_s, kk != 0 ? 1u : 0u);
+        mma_commit(smem_u32(&bars->sdp_full));
+        mbar_wait(smem_u32(&bars->pds_full), n & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t koff = static_cast<uint64_t>((ks & 3) * 2);
+          const uint64_t pdesc = smem_desc_sw128(smem_base + off_p + (ks >> 2) * kTile) + koff;
+          const uint64_t dsdesc = smem_desc_sw128(smem_base + off_ds + (ks >> 2) * kTile) + koff;
+          const uint64_t domn = smem_desc_sw128_mn(qbase + kTile + ks * 2048, 1024, 1024);
+          const uint64_t qmn = smem_desc_sw128_mn(qbase + ks * 2048, 1024, 1024);
+          const uint32_t acc = (n != 0 || ks != 0) ? 1u : 0u;
+          mma_f16_ss(tmem_dv, pdesc, domn, a.idesc_o, acc);    // dV += P^T . dO
+          mma_f16_ss(tmem_dk, dsdesc, qmn, a.idesc_o, acc);    // dK += dS^T . Q
+        }
+        mma_commit(smem_u32(&bars->ring_empty[stage]));
+        mma_commit(smem_u32(&bars->acc_done));
+        if (++stage == 2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const uint32_t quad = warp & 3, row = quad * 32 + lane, kj = k0 + row;   // row == key
+    const uint32_t lane_tmem = (quad * 32) << 16;
+    const bool row_active = kj < a.sk;
+    uint8_t* p_row = smem + off_p + row * 128u;
+    uint8_t* ds_row = smem + off_ds + row * 128u;
+    if (cta_dead) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        *reinterpret_cast<uint4*>(smem + off_k + row * 128u + g * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(smem + off_v + row * 128u + g * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+    } else {
+      const bool k_is_pad = row_active && a.k_pad && a.k_pad[static_cast<size_t>(b) * a.sk + kj] != 0;
+      uint32_t n = 0;
+      for (uint32_t i = next_live(0); i < nqblk; i = next_live(i + 1), ++n) {
+        const uint32_t qb0 = i * kAttnBQ;
+        // per-query statistics of this block -> shared memory (thread `row` loads query qb0 + row)
+        float* st = stat_smem + (n & 1) * 256;
+        {
+          const uint32_t qi = qb0 + row;
+          const size_t sidx = (static_cast<size_t>(b) * a.heads + head) * a.sq + (qi < a.sq ? qi : 0);
+          st[row] = a.lse[sidx] * kLog2e;
+          st[128 + row] = a.dvec[sidx];
+        }
+        uint32_t qm[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t idx = qb0 + c * 32 + lane;
+          const bool f = a.q_pad && idx < a.sq && a.q_pad[static_cast<size_t>(b) * a.sq + idx] != 0;
+          qm[c] = __ballot_sync(kFull, f);
+        }
+        const uint32_t valid = min(static_cast<uint32_t>(kAttnBQ), a.sq - qb0);
+        asm volatile("bar.sync 2, 128;" ::: "memory");   // statistics visible to all row threads
+        mbar_wait(smem_u32(&bars->sdp_full), n & 1);
+        tc_fence_after();
+        if (n > 0) mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t s[64], dp[64];
+          tmem_ld_32x32b_x32(tmem_s + lane_tmem + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          tmem_ld_32x32b_x32(tmem_s + lane_tmem + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+          tmem_ld_32x32b_x32(tmem_dp + lane_tmem + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
+          tmem_ld_32x32b_x32(tmem_dp + lane_tmem + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float pv[8], ds[8];
+            const float4 l0 = *reinterpret_cast<const float4*>(st + half * 64 + g * 8);
+            const float4 l1 = *reinterpret_cast<const float4*>(st + half * 64 + g * 8 + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(st + 128 + half * 64 + g * 8);
+            const float4 d1 = *reinterpret_cast<const float4*>(st + 128 + half * 64 + g * 8 + 4);
+            const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) {
+              const int c = g * 8 + i2;
+              const uint32_t cc = half * 64 + c;   // query column inside the block
+              const bool masked = k_is_pad || ((qm[cc >> 5] >> (cc & 31)) & 1u) || (a.causal && kj > qb0 + cc);
+              float t = __uint_as_float(s[c]) * a.scale_log2;
+              t = masked ? kMaskedLog2 : t;
+              float p = ex2(t - lv[i2]);
+              p = (cc < valid && row_active) ? p : 0.f;
+              const float d = p * (__uint_as_float(dp[c]) - dv[i2]) * a.scale;
+              pv[i2] = p;
+              ds[i2] = masked ? 0.f : d;
+            }
+            const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+            *reinterpret_cast<uint4*>(p_row + half * kTile + phys) =
+                make_uint4(pack2<kBf16>(pv[0], pv[1]), pack2<kBf16>(pv[2], pv[3]), pack2<kBf16>(pv[4], pv[5]),
+                           pack2<kBf16>(pv[6], pv[7]));
+            *reinterpret_cast<uint4*>(ds_row + half * kTile + phys) =
+                make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
+                           pack2<kBf16>(ds[6], ds[7]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&bars->sdp_empty));
+          mbar_arrive(smem_u32(&bars->pds_full));
+        }
+      }
+      mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {   // 0: dV -> V's tile, 1: dK -> K's tile (both dead now)
+        uint8_t* o_row = smem + (which == 0 ? off_v : off_k) + row * 128u;
+        const uint32_t taddr = (which == 0 ? tmem_dv : tmem_dk) + lane_tmem;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(taddr + half * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t phys = (static_cast<uint32_t>(half * 4 + g) ^ (row & 7u)) * 16u;
+            *reinterpret_cast<uint4*>(o_row + phys) = make_uint4(
+                pack2<kBf16>(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1])),
+                pack2<kBf16>(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
+                pack2<kBf16>(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
+                pack2<kBf16>(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7])));
+          }
+        }
+      }
+      fence_proxy_async_smem();
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 4 && lane == 0) {
+      tma_store_3d(&tmap_dv, smem_base + off_v, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b));
+      tma_store_3d(&tmap_dk, smem_base + off_k, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b));
+      tma_store_commit();
+      tma_store_wait<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+cudaError_t attention_bwd_prepare() {
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem);
+  return e;
+}
+
+cudaError_t launch_attention_bwd_prep(bool bf16, const void* dout, int64_t lddo, const void* out, int64_t ldo,
+                                      float* dvec, int batch, int heads, int sq, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(batch) * sq * heads;
+  if (total <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (bf16)
+    attention_bwd_prep_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(dout), lddo,
+                                                              static_cast<const uint16_t*>(out), ldo, dvec, batch,
+                                                              heads, sq);
+  else
+    attention_bwd_prep_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(dout), lddo,
+                                                               static_cast<const uint16_t*>(out), ldo, dvec, batch,
+                                                               heads, sq);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                                 const CUtensorMap& tdo, const CUtensorMap& tdq, const CUtensorMap& tdk,
+                                 const CUtensorMap& tdv, const AttnBwdArgs& a, bool bf16, cudaStream_t stream) {
+  dim3 gq((a.sq + kAttnBQ - 1) / kAttnBQ, a.heads, a.batch);
+  dim3 gk((a.sk + kAttnBK - 1) / kAttnBK, a.heads, a.batch);
+  if (bf16) {
+    attention_bwd_dq_kernel<true><<<gq, kAttnThreads, kDqSmem, stream>>>(tq, tk, tv, tdo, tdq, a);
+    attention_bwd_dkv_kernel<true><<<gk, kAttnThreads, kDkvSmem, stream>>>(tq, tk, tv, tdo, tdk, tdv, a);
+  } else {
+    attention_bwd_dq_kernel<false><<<gq, kAttnThreads, kDqSmem, stream>>>(tq, tk, tv, tdo, tdq, a);
+    attention_bwd_dkv_kernel<false><<<gk, kAttnThreads, kDkvSmem, stream>>>(tq, tk, tv, tdo, tdk, tdv, a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace emdr2

@@ -2,6 +2,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "../../include/emdr2_b200.h"
 #include "capi_common.cuh"
 #include "attention.cuh"
@@ -27,29 +29,78 @@ int require_b200(DeviceInfo* info) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- optional per-kernel-kind launch timing (emdr2_ops_timing): CUDA event pairs recorded on the
+// caller's stream around every launch of a kind, summed on request.  Host-thread local.
+struct KindTimer {
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  double flops = 0.0;   // algorithmic work of the timed launches (GEMM: 2mnk; attention: 4 b h sq sk d)
+};
+thread_local bool g_timing = false;
+thread_local KindTimer g_timers[EMDR2_KIND_COUNT];
+
+struct ScopedTimer {
+  KindTimer* t = nullptr;
+  cudaStream_t stream;
+  ScopedTimer(int kind, cudaStream_t s, double flops) : stream(s) {
+    if (!g_timing) return;
+    t = &g_timers[kind];
+    if (t->used + 2 > t->ev.size()) {
+      cudaEvent_t e0, e1;
+      if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+        t = nullptr;
+        return;
+      }
+      t->ev.push_back(e0);
+      t->ev.push_back(e1);
+    }
+    t->flops += flops;
+    cudaEventRecord(t->ev[t->used], stream);
+  }
+  ~ScopedTimer() {
+    if (!t) return;
+    cudaEventRecord(t->ev[t->used + 1], stream);
+    t->used += 2;
+  }
+};
+
 }  // namespace
 
 extern "C" {
 
-int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, int64_t ldb, void* d,
-               int64_t ldd, const void* bias, const void* residual, int64_t ldr, int m, int n,
-               int k, int flags, void* cuda_stream) {
+int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn,
+                  void* d, int64_t ldd, const void* bias, const void* aux, int64_t ld_aux, void* preact,
+                  int64_t ld_preact, int m, int n, int k, int flags, int splits, void* cuda_stream) {
   if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
     return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
   if (m < 0 || n < 0 || k < 0) return fail(EMDR2_EINVAL, "negative GEMM shape m=%d n=%d k=%d", m, n, k);
   if (m == 0 || n == 0) return EMDR2_OK;
   if (k == 0) return fail(EMDR2_EINVAL, "k=0 is not supported");
-  if ((n % 8) || (k % 8) || (lda % 8) || (ldb % 8) || (ldd % 8))
-    return fail(EMDR2_EINVAL, "n, k and the leading dimensions must be multiples of 8 (16-byte rows)");
-  if (lda < k || ldb < k || ldd < n) return fail(EMDR2_EINVAL, "leading dimension smaller than the row length");
+  const bool accum = (flags & EMDR2_GEMM_ACCUM_F32) != 0;
+  const int out_mult = accum ? 4 : 8;   // 16-byte rows: 8 16-bit or 4 fp32 elements
+  if ((n % 8) || (k % 8) || (lda % 8) || (ldb % 8) || (ldd % out_mult) || (a_mn && (m % 8)))
+    return fail(EMDR2_EINVAL, "m (if a is MN-major), n, k and the leading dimensions must be multiples of 8 (16-byte rows)");
+  if (lda < (a_mn ? m : k) || ldb < (b_mn ? n : k) || ldd < n)
+    return fail(EMDR2_EINVAL, "leading dimension smaller than the row length");
   if (!a || !b || !d) return fail(EMDR2_EINVAL, "NULL operand pointer");
   if (!aligned16(a) || !aligned16(b) || !aligned16(d)) return fail(EMDR2_EINVAL, "operands must be 16-byte aligned");
-  if (flags & ~(EMDR2_GEMM_BIAS | EMDR2_GEMM_GELU | EMDR2_GEMM_RESIDUAL))
-    return fail(EMDR2_EINVAL, "unknown GEMM epilogue flags 0x%x", flags);
+  if (a_mn && !b_mn) return fail(EMDR2_EUNSUPPORTED, "a MN-major with b K-major is not built");
+  const int known = EMDR2_GEMM_BIAS | EMDR2_GEMM_GELU | EMDR2_GEMM_RESIDUAL | EMDR2_GEMM_ACCUM_F32 |
+                    EMDR2_GEMM_GELU_BWD | EMDR2_GEMM_PREACT;
+  if (flags & ~known) return fail(EMDR2_EINVAL, "unknown GEMM epilogue flags 0x%x", flags);
   if ((flags & EMDR2_GEMM_BIAS) && (!bias || !aligned16(bias)))
     return fail(EMDR2_EINVAL, "EMDR2_GEMM_BIAS needs a 16-byte aligned bias pointer");
-  if ((flags & EMDR2_GEMM_RESIDUAL) && (!residual || !aligned16(residual) || (ldr % 8) || ldr < n))
-    return fail(EMDR2_EINVAL, "EMDR2_GEMM_RESIDUAL needs a 16-byte aligned residual with ldr %% 8 == 0, ldr >= n");
+  const bool has_aux = (flags & (EMDR2_GEMM_RESIDUAL | EMDR2_GEMM_GELU_BWD)) != 0;
+  if ((flags & EMDR2_GEMM_RESIDUAL) && (flags & EMDR2_GEMM_GELU_BWD))
+    return fail(EMDR2_EINVAL, "RESIDUAL and GELU_BWD both read the aux tile: pick one");
+  if (has_aux && (!aux || !aligned16(aux) || (ld_aux % 8) || ld_aux < n))
+    return fail(EMDR2_EINVAL, "RESIDUAL/GELU_BWD need a 16-byte aligned aux [m, n] with ld %% 8 == 0, ld >= n");
+  if ((flags & EMDR2_GEMM_PREACT) && (!preact || !aligned16(preact) || (ld_preact % 8) || ld_preact < n))
+    return fail(EMDR2_EINVAL, "PREACT needs a 16-byte aligned output [m, n] with ld %% 8 == 0, ld >= n");
+  if (accum && (flags & ~(EMDR2_GEMM_ACCUM_F32)))
+    return fail(EMDR2_EINVAL, "ACCUM_F32 cannot be combined with other epilogue flags");
+  if (splits < 1) splits = 1;
+  if (splits > 1 && !accum) return fail(EMDR2_EINVAL, "split-K needs EMDR2_GEMM_ACCUM_F32");
   DeviceInfo info;
   int rc = require_b200(&info);
   if (rc != EMDR2_OK) return rc;
@@ -58,13 +109,22 @@ int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, int64_t ldb
     CUDA_TRY(emdr2::gemm_prepare());
     prepared[info.device] = true;
   }
-  CUtensorMap ta, tb, td, tr;
-  if ((rc = make_tmap_2d(&ta, dtype, a, m, k, lda, emdr2::kGemmBM)) != EMDR2_OK) return rc;
-  if ((rc = make_tmap_2d(&tb, dtype, b, n, k, ldb, emdr2::kGemmBN)) != EMDR2_OK) return rc;
-  if ((rc = make_tmap_2d(&td, dtype, d, m, n, ldd, emdr2::kGemmBM)) != EMDR2_OK) return rc;
+  CUtensorMap ta, tb, td, tr, tp;
+  // K-major operand: [rows, k] with box rows x 64; MN-major: [k, rows] with 64 x 64 boxes
+  rc = a_mn ? make_tmap_2d(&ta, dtype, a, k, m, lda, 64) : make_tmap_2d(&ta, dtype, a, m, k, lda, emdr2::kGemmBM);
+  if (rc != EMDR2_OK) return rc;
+  rc = b_mn ? make_tmap_2d(&tb, dtype, b, k, n, ldb, 64) : make_tmap_2d(&tb, dtype, b, n, k, ldb, emdr2::kGemmBN);
+  if (rc != EMDR2_OK) return rc;
+  if (accum) {
+    td = tb;   // no 16-bit output map needed; any valid descriptor fills the unused slots
+  } else if ((rc = make_tmap_2d(&td, dtype, d, m, n, ldd, emdr2::kGemmBM)) != EMDR2_OK) {
+    return rc;
+  }
   tr = td;
-  if ((flags & EMDR2_GEMM_RESIDUAL) &&
-      (rc = make_tmap_2d(&tr, dtype, residual, m, n, ldr, emdr2::kGemmBM)) != EMDR2_OK)
+  tp = td;
+  if (has_aux && (rc = make_tmap_2d(&tr, dtype, aux, m, n, ld_aux, emdr2::kGemmBM)) != EMDR2_OK) return rc;
+  if ((flags & EMDR2_GEMM_PREACT) &&
+      (rc = make_tmap_2d(&tp, dtype, preact, m, n, ld_preact, emdr2::kGemmBM)) != EMDR2_OK)
     return rc;
   emdr2::GemmArgs ga;
   ga.M = m;
@@ -72,20 +132,38 @@ int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, int64_t ldb
   ga.K = k;
   ga.tiles_m = (m + emdr2::kGemmBM - 1) / emdr2::kGemmBM;
   ga.tiles_n = (n + emdr2::kGemmBN - 1) / emdr2::kGemmBN;
-  ga.idesc = emdr2::ptx::instr_desc_f16(dtype == EMDR2_DTYPE_BF16 ? 1 : 0, emdr2::kGemmBM, emdr2::kGemmBN);
+  ga.idesc = emdr2::ptx::instr_desc_f16(dtype == EMDR2_DTYPE_BF16 ? 1 : 0, emdr2::kGemmBM, emdr2::kGemmBN,
+                                        a_mn ? 1 : 0, b_mn ? 1 : 0);
   ga.flags = static_cast<uint32_t>(flags);
+  const uint32_t num_kb = (k + emdr2::kGemmBK - 1) / emdr2::kGemmBK;
+  if (static_cast<uint32_t>(splits) > num_kb) splits = static_cast<int>(num_kb);
+  ga.kb_per_split = (num_kb + splits - 1) / splits;
+  ga.splits = (num_kb + ga.kb_per_split - 1) / ga.kb_per_split;
+  ga.ldd32 = static_cast<uint32_t>(ldd);
   ga.bias = bias;
-  const uint32_t tiles = ga.tiles_m * ga.tiles_n;
-  const int grid = static_cast<int>(tiles < static_cast<uint32_t>(info.sm_count) ? tiles : info.sm_count);
-  emdr2::launch_gemm(ta, tb, td, tr, ga, dtype == EMDR2_DTYPE_BF16, grid, static_cast<cudaStream_t>(cuda_stream));
-  CUDA_TRY(cudaGetLastError());
+  ga.out32 = accum ? static_cast<float*>(d) : nullptr;
+  const uint32_t work = ga.tiles_m * ga.tiles_n * ga.splits;
+  const int grid = static_cast<int>(work < static_cast<uint32_t>(info.sm_count) ? work : info.sm_count);
+  ScopedTimer timer(EMDR2_KIND_GEMM, static_cast<cudaStream_t>(cuda_stream), 2.0 * m * n * k);
+  CUDA_TRY(emdr2::launch_gemm(ta, tb, td, tr, tp, ga, dtype == EMDR2_DTYPE_BF16, a_mn != 0, b_mn != 0, grid,
+                              static_cast<cudaStream_t>(cuda_stream)));
   return EMDR2_OK;
+}
+
+int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, int64_t ldb, void* d,
+               int64_t ldd, const void* bias, const void* residual, int64_t ldr, int m, int n,
+               int k, int flags, void* cuda_stream) {
+  if (flags & ~(EMDR2_GEMM_BIAS | EMDR2_GEMM_GELU | EMDR2_GEMM_RESIDUAL))
+    return fail(EMDR2_EINVAL, "unknown GEMM epilogue flags 0x%x", flags);
+  return emdr2_gemm_ex(dtype, a, lda, 0, b, ldb, 0, d, ldd, bias, residual, ldr, nullptr, 0, m, n, k, flags, 1,
+                       cuda_stream);
 }
 
 int emdr2_attention_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk,
                         const void* v, int64_t ldv, void* o, int64_t ldo, int batch, int heads,
-                        int sq, int sk, const uint8_t* q_pad, const uint8_t* k_pad, int causal,
-                        float scale, float* lse, void* cuda_stream) {
+                        int sq, int sk, const uint8_t* q_pad, const uint8_t* k_pad,
+                        const uint8_t* q_live, const uint8_t* k_live, int causal, float scale,
+                        float* lse, void* cuda_stream) {
   if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
     return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
   if (batch < 0 || heads < 1 || sq < 0 || sk < 0)
@@ -126,7 +204,11 @@ int emdr2_attention_fwd(int dtype, const void* q, int64_t ldq, const void* k, in
   aa.scale_log2 = scale * 1.4426950408889634f;
   aa.q_pad = q_pad;
   aa.k_pad = k_pad;
+  aa.q_live = q_live;
+  aa.k_live = k_live;
   aa.lse = lse;
+  ScopedTimer timer(EMDR2_KIND_ATTENTION, static_cast<cudaStream_t>(cuda_stream),
+                    4.0 * batch * heads * sq * static_cast<double>(sk) * emdr2::kAttnHeadDim);
   emdr2::launch_attention_fwd(tq, tk, tv, to, aa, fmt == 1, static_cast<cudaStream_t>(cuda_stream));
   CUDA_TRY(cudaGetLastError());
   return EMDR2_OK;
@@ -147,6 +229,7 @@ int emdr2_layernorm_fwd(int dtype, const void* x, int64_t ldx, const void* gamma
   DeviceInfo info;
   int rc = require_b200(&info);
   if (rc != EMDR2_OK) return rc;
+  ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
   CUDA_TRY(emdr2::launch_layernorm_fwd(dtype == EMDR2_DTYPE_BF16, x, ldx, gamma, beta, y, ldy, rows, h,
                                        eps, mean, rstd, static_cast<cudaStream_t>(cuda_stream)));
   return EMDR2_OK;
@@ -168,6 +251,7 @@ int emdr2_embedding_fwd(int dtype, const int64_t* ids, const int64_t* types, con
   DeviceInfo info;
   int rc = require_b200(&info);
   if (rc != EMDR2_OK) return rc;
+  ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
   CUDA_TRY(emdr2::launch_embedding_fwd(dtype == EMDR2_DTYPE_BF16, ids, types, word, pos, type_emb, out,
                                        tokens, seq, h, vocab, num_types,
                                        static_cast<cudaStream_t>(cuda_stream)));
@@ -187,8 +271,170 @@ int emdr2_token_logprob(int dtype, const void* logits, int64_t ld, const int64_t
   DeviceInfo info;
   int rc = require_b200(&info);
   if (rc != EMDR2_OK) return rc;
+  ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
   CUDA_TRY(emdr2::launch_token_logprob(dtype == EMDR2_DTYPE_BF16, logits, ld, labels, logprob, lse, rows,
                                        vocab, static_cast<cudaStream_t>(cuda_stream)));
+  return EMDR2_OK;
+}
+
+int emdr2_ops_timing(int enable) {
+  g_timing = enable != 0;
+  for (int k = 0; k < EMDR2_KIND_COUNT; ++k) {
+    g_timers[k].used = 0;
+    g_timers[k].flops = 0.0;
+  }
+  return EMDR2_OK;
+}
+
+int emdr2_ops_timing_read(int kind, int64_t* out_ns, int64_t* out_launches, double* out_flops) {
+  if (kind < 0 || kind >= EMDR2_KIND_COUNT) return fail(EMDR2_EINVAL, "unknown kernel kind %d", kind);
+  KindTimer& t = g_timers[kind];
+  double total_ms = 0.0;
+  for (size_t i = 0; i + 1 < t.used; i += 2) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventSynchronize(t.ev[i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]));
+    total_ms += ms;
+  }
+  if (out_ns) *out_ns = static_cast<int64_t>(total_ms * 1e6);
+  if (out_launches) *out_launches = static_cast<int64_t>(t.used / 2);
+  if (out_flops) *out_flops = t.flops;
+  t.used = 0;
+  t.flops = 0.0;
+  return EMDR2_OK;
+}
+
+int emdr2_attention_bwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                        int64_t ldv, const void* o, int64_t ldo, const void* dout, int64_t lddo, void* dq,
+                        int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int batch, int heads,
+                        int sq, int sk, const uint8_t* q_pad, const uint8_t* k_pad, const uint8_t* q_live,
+                        const uint8_t* k_live, int causal, float scale, const float* lse, float* dvec_ws,
+                        void* cuda_stream) {
+  if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
+    return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
+  if (batch < 0 || heads < 1 || sq < 0 || sk < 1)
+    return fail(EMDR2_EINVAL, "bad attention shape batch=%d heads=%d sq=%d sk=%d", batch, heads, sq, sk);
+  if (batch == 0 || sq == 0) return EMDR2_OK;
+  if (heads > 65535 || batch > 65535) return fail(EMDR2_EINVAL, "batch and heads must be <= 65535");
+  const void* ptrs[] = {q, k, v, o, dout, dq, dk, dv};
+  for (const void* p : ptrs)
+    if (!p || !aligned16(p)) return fail(EMDR2_EINVAL, "NULL or misaligned tensor passed to emdr2_attention_bwd");
+  if (!lse || !dvec_ws) return fail(EMDR2_EINVAL, "lse and the dvec workspace ([batch, heads, sq] fp32) are required");
+  const int64_t width = static_cast<int64_t>(heads) * emdr2::kAttnHeadDim;
+  const int64_t lds[] = {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv};
+  for (int64_t ld : lds)
+    if ((ld % 8) || ld < width) return fail(EMDR2_EINVAL, "row pitches must be multiples of 8 and >= heads*64");
+  DeviceInfo info;
+  int rc = require_b200(&info);
+  if (rc != EMDR2_OK) return rc;
+  static bool prepared[64] = {};
+  if (!prepared[info.device]) {
+    CUDA_TRY(emdr2::attention_bwd_prepare());
+    prepared[info.device] = true;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const bool bf16 = dtype == EMDR2_DTYPE_BF16;
+  ScopedTimer timer(EMDR2_KIND_ATTENTION, stream,
+                    14.0 * batch * heads * sq * static_cast<double>(sk) * emdr2::kAttnHeadDim);
+  CUDA_TRY(emdr2::launch_attention_bwd_prep(bf16, dout, lddo, o, ldo, dvec_ws, batch, heads, sq, stream));
+  CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
+  if ((rc = make_tmap_3d(&tq, dtype, q, batch, sq, width, ldq, 128)) != EMDR2_OK) return rc;
+  if ((rc = make_tmap_3d(&tk, dtype, k, batch, sk, width, ldk, 128)) != EMDR2_OK) return rc;
+  if ((rc = make_tmap_3d(&tv, dtype, v, batch, sk, width, ldv, 128)) != EMDR2_OK) return rc;
+  if ((rc = make_tmap_3d(&tdo, dtype, dout, batch, sq, width, lddo, 128)) != EMDR2_OK) return rc;
+  if ((rc = make_tmap_3d(&tdq, dtype, dq, batch, sq, width, lddq, 128)) != EMDR2_OK) return rc;
+  if ((rc = make_tmap_3d(&tdk, dtype, dk, batch, sk, width, lddk, 128)) != EMDR2_OK) return rc;
+  if ((rc = make_tmap_3d(&tdv, dtype, dv, batch, sk, width, lddv, 128)) != EMDR2_OK) return rc;
+  emdr2::AttnBwdArgs aa;
+  aa.batch = batch;
+  aa.heads = heads;
+  aa.sq = sq;
+  aa.sk = sk;
+  aa.causal = causal ? 1u : 0u;
+  const int fmt = bf16 ? 1 : 0;
+  aa.idesc_s = emdr2::ptx::instr_desc_f16(fmt, 128, 128);
+  aa.idesc_o = emdr2::ptx::instr_desc_f16(fmt, 128, emdr2::kAttnHeadDim, 0, 1);
+  aa.scale = scale;
+  aa.scale_log2 = scale * 1.4426950408889634f;
+  aa.q_pad = q_pad;
+  aa.k_pad = k_pad;
+  aa.q_live = q_live;
+  aa.k_live = k_live;
+  aa.lse = lse;
+  aa.dvec = dvec_ws;
+  CUDA_TRY(emdr2::launch_attention_bwd(tq, tk, tv, tdo, tdq, tdk, tdv, aa, bf16, stream));
+  return EMDR2_OK;
+}
+
+int emdr2_layernorm_bwd(int dtype, const void* dy, int64_t ldy, const void* x, int64_t ldx, const void* gamma,
+                        const float* mean, const float* rstd, const void* dres, int64_t ldr, void* dx,
+                        int64_t lddx, float* dgamma, float* dbeta, int rows, int h, void* cuda_stream) {
+  if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
+    return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
+  if (rows < 0 || h < 8 || (h % 8) || h > 1024)
+    return fail(EMDR2_EINVAL, "layernorm_bwd needs rows >= 0 and h a multiple of 8 in [8, 1024]");
+  if (rows == 0) return EMDR2_OK;
+  if (!dy || !x || !gamma || !mean || !rstd || !dx) return fail(EMDR2_EINVAL, "NULL pointer passed to emdr2_layernorm_bwd");
+  if (!aligned16(dy) || !aligned16(x) || !aligned16(gamma) || !aligned16(dx) || (dres && !aligned16(dres)) ||
+      (ldy % 8) || (ldx % 8) || (lddx % 8) || (dres && (ldr % 8)))
+    return fail(EMDR2_EINVAL, "layernorm_bwd operands must be 16-byte aligned with row pitches %% 8 == 0");
+  DeviceInfo info;
+  int rc = require_b200(&info);
+  if (rc != EMDR2_OK) return rc;
+  ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
+  CUDA_TRY(emdr2::launch_layernorm_bwd(dtype == EMDR2_DTYPE_BF16, dy, ldy, x, ldx, gamma, mean, rstd, dres, ldr, dx,
+                                       lddx, dgamma, dbeta, rows, h, info.sm_count,
+                                       static_cast<cudaStream_t>(cuda_stream)));
+  return EMDR2_OK;
+}
+
+int emdr2_colsum(int dtype, const void* dy, int64_t ld, float* out, int rows, int n, void* cuda_stream) {
+  if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
+    return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
+  if (rows < 0 || n < 0 || (n % 8) || (ld % 8) || ld < n) return fail(EMDR2_EINVAL, "colsum needs n %% 8 == 0, ld %% 8 == 0, ld >= n");
+  if (rows == 0 || n == 0) return EMDR2_OK;
+  if (!dy || !out || !aligned16(dy)) return fail(EMDR2_EINVAL, "NULL or misaligned pointer passed to emdr2_colsum");
+  DeviceInfo info;
+  int rc = require_b200(&info);
+  if (rc != EMDR2_OK) return rc;
+  ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
+  CUDA_TRY(emdr2::launch_colsum(dtype == EMDR2_DTYPE_BF16, dy, ld, out, rows, n, static_cast<cudaStream_t>(cuda_stream)));
+  return EMDR2_OK;
+}
+
+int emdr2_token_logprob_bwd(int dtype, const void* logits, int64_t ld, const int64_t* labels, const float* lse,
+                            const float* g, void* dlogits, int64_t ldd, int rows, int vocab, void* cuda_stream) {
+  if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
+    return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
+  if (rows < 0 || vocab < 8 || (vocab % 8) || (ld % 8) || (ldd % 8) || ld < vocab || ldd < vocab)
+    return fail(EMDR2_EINVAL, "token_logprob_bwd needs vocab %% 8 == 0 and row pitches %% 8 == 0, >= vocab");
+  if (rows == 0) return EMDR2_OK;
+  if (!logits || !labels || !lse || !g || !dlogits || !aligned16(logits) || !aligned16(dlogits))
+    return fail(EMDR2_EINVAL, "NULL or misaligned pointer passed to emdr2_token_logprob_bwd");
+  DeviceInfo info;
+  int rc = require_b200(&info);
+  if (rc != EMDR2_OK) return rc;
+  ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
+  CUDA_TRY(emdr2::launch_token_logprob_bwd(dtype == EMDR2_DTYPE_BF16, logits, ld, labels, lse, g, dlogits, ldd, rows,
+                                           vocab, static_cast<cudaStream_t>(cuda_stream)));
+  return EMDR2_OK;
+}
+
+int emdr2_embedding_bwd(int dtype, const void* dx, const int64_t* ids, const int64_t* types, float* dword,
+                        float* dpos, float* dtype_emb, int tokens, int seq, int h, int vocab, int num_types,
+                        void* cuda_stream) {
+  if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
+    return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
+  if (tokens < 0 || seq < 1 || h < 8 || (h % 8) || vocab < 1)
+    return fail(EMDR2_EINVAL, "bad embedding shape tokens=%d seq=%d h=%d vocab=%d", tokens, seq, h, vocab);
+  if (tokens == 0) return EMDR2_OK;
+  if (!dx || !ids || !aligned16(dx)) return fail(EMDR2_EINVAL, "NULL or misaligned pointer passed to emdr2_embedding_bwd");
+  DeviceInfo info;
+  int rc = require_b200(&info);
+  if (rc != EMDR2_OK) return rc;
+  ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
+  CUDA_TRY(emdr2::launch_embedding_bwd(dtype == EMDR2_DTYPE_BF16, dx, ids, types, dword, dpos, dtype_emb, tokens, seq,
+                                       h, vocab, num_types, static_cast<cudaStream_t>(cuda_stream)));
   return EMDR2_OK;
 }
 

@@ -62,11 +62,32 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <bool kBf16>
+// d/dx GeLU(x) = Phi(x) + x phi(x), same erf approximation as gelu_erf.
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));   // exp(-x^2/2)
+  const float q = 0.5f * poly * e;                 // 1 - Phi(|x|)
+  const float cdf = x >= 0.f ? 1.0f - q : q;
+  return fmaf(x * 0.3989422804014327f, e, cdf);    // + x * exp(-x^2/2) / sqrt(2 pi)
+}
+
+// kAMN / kBMN: that operand is stored with the contraction index as the ROW index ([k, m] resp.
+// [k, n] row-major, "MN-major"): its tile is fetched as 64x64-element boxes (one per 64-wide MN atom,
+// 8 KiB apart) and consumed through an MN-major UMMA descriptor — this is how the backward products
+// dX = dY.W and dW = dY^T.X read the forward's tensors without any transpose in memory.
+template <bool kBf16, bool kAMN, bool kBMN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
-            const GemmArgs a) {
+            const __grid_constant__ CUtensorMap tmap_p, const GemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -79,6 +100,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t num_tiles = a.tiles_m * a.tiles_n;
   const uint32_t num_kb = (a.K + kGemmBK - 1) / kGemmBK;
+  // work item w = tile * splits + split; a split owns k blocks [split * kb_per, ... + kb_per)
+  const uint32_t num_work = num_tiles * a.splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kGemmStages; ++s) {
@@ -112,17 +135,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ===================================================== TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (uint32_t w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const uint32_t t = w / a.splits, sp = w % a.splits;
         const int32_t m0 = static_cast<int32_t>((t / a.tiles_n) * kGemmBM);
         const int32_t n0 = static_cast<int32_t>((t % a.tiles_n) * kGemmBN);
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        const uint32_t kb0 = sp * a.kb_per_split;
+        const uint32_t kb1 = min(num_kb, kb0 + a.kb_per_split);
+        for (uint32_t kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
           const uint32_t fbar = smem_u32(&bars->full[stage]);
           mbar_arrive_expect_tx(fbar, kGemmStageBytes);
           const uint32_t sa = smem_base + stage * kGemmStageBytes;
-          tma_load_2d(sa, &tmap_a, fbar, static_cast<int32_t>(kb * kGemmBK), m0, kEvictNormal);
-          tma_load_2d(sa + kGemmStageA, &tmap_b, fbar, static_cast<int32_t>(kb * kGemmBK), n0,
-                      kEvictLast);
+          const int32_t k0 = static_cast<int32_t>(kb * kGemmBK);
+          if constexpr (kAMN) {
+#pragma unroll
+            for (int at = 0; at < kGemmBM / 64; ++at)
+              tma_load_2d(sa + at * 8192, &tmap_a, fbar, m0 + at * 64, k0, kEvictNormal);
+          } else {
+            tma_load_2d(sa, &tmap_a, fbar, k0, m0, kEvictNormal);
+          }
+          if constexpr (kBMN) {
+#pragma unroll
+            for (int at = 0; at < kGemmBN / 64; ++at)
+              tma_load_2d(sa + kGemmStageA + at * 8192, &tmap_b, fbar, n0 + at * 64, k0, kEvictLast);
+          } else {
+            tma_load_2d(sa + kGemmStageA, &tmap_b, fbar, k0, n0, kEvictLast);
+          }
           if (++stage == kGemmStages) {
             stage = 0;
             phase ^= 1;
@@ -134,21 +172,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ===================================================== MMA issuer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, it = 0;
-      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (uint32_t w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+        const uint32_t sp = w % a.splits;
+        const uint32_t kb0 = sp * a.kb_per_split;
+        const uint32_t kb1 = min(num_kb, kb0 + a.kb_per_split);
         const uint32_t buf = it & 1;
         mbar_wait(smem_u32(&bars->tmem_empty[buf]), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kGemmBN;
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        for (uint32_t kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bars->full[stage]), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * kGemmStageBytes;
-          const uint64_t adesc = smem_desc_sw128(sa);
-          const uint64_t bdesc = smem_desc_sw128(sa + kGemmStageA);
 #pragma unroll
-          for (int kk = 0; kk < kGemmBK / 16; ++kk)
-            mma_f16_ss(d_tmem, adesc + static_cast<uint64_t>(kk * 2),
-                       bdesc + static_cast<uint64_t>(kk * 2), a.idesc, (kb | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < kGemmBK / 16; ++kk) {
+            const uint64_t adesc = kAMN ? smem_desc_sw128_mn(sa + kk * 2048, 8192, 1024)
+                                        : smem_desc_sw128(sa) + static_cast<uint64_t>(kk * 2);
+            const uint64_t bdesc = kBMN ? smem_desc_sw128_mn(sa + kGemmStageA + kk * 2048, 8192, 1024)
+                                        : smem_desc_sw128(sa + kGemmStageA) + static_cast<uint64_t>(kk * 2);
+            mma_f16_ss(d_tmem, adesc, bdesc, a.idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
+          }
           mma_commit(smem_u32(&bars->empty[stage]));
           if (++stage == kGemmStages) {
             stage = 0;
@@ -169,7 +212,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const uint32_t bar_id = 1 + hh;
     const bool has_bias = (a.flags & kGemmBias) != 0;
     const bool has_gelu = (a.flags & kGemmGelu) != 0;
-    const bool has_res = (a.flags & kGemmResidual) != 0;
+    const bool has_res = (a.flags & (kGemmResidual | kGemmGeluBwd)) != 0;   // an aux tile comes in by TMA
+    const bool gelu_bwd = (a.flags & kGemmGeluBwd) != 0;
+    const bool store_pre = (a.flags & kGemmPreact) != 0;
+    const bool out_f32 = (a.flags & kGemmAccumF32) != 0;
     const uint16_t* bias = static_cast<const uint16_t*>(a.bias);
     const uint32_t res_bar = smem_u32(&bars->res_full[hh]);
     uint32_t res_phase = 0;
@@ -177,19 +223,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // The residual tile of a chunk is fetched by TMA into the chunk's own staging buffer (coalesced,
     // asynchronous) and the result overwrites it in place.  `load_residual(t, ch)` is called by the
     // issuer thread as soon as the buffer is free, i.e. one chunk ahead of its use.
-    auto chunk_live = [&](uint32_t t, uint32_t ch) {
-      return t < num_tiles && (t % a.tiles_n) * kGemmBN + hh * 128 + ch * 64 < a.N;
+    auto chunk_live = [&](uint32_t w, uint32_t ch) {
+      const uint32_t t = w / a.splits;
+      return w < num_work && (t % a.tiles_n) * kGemmBN + hh * 128 + ch * 64 < a.N;
     };
-    auto load_residual = [&](uint32_t t, uint32_t ch) {
+    auto load_residual = [&](uint32_t w, uint32_t ch) {
+      const uint32_t t = w / a.splits;
       mbar_arrive_expect_tx(res_bar, kGemmBM * 64 * 2);
       tma_load_2d(smem_base + stage_off, &tmap_r, res_bar,
                   static_cast<int32_t>((t % a.tiles_n) * kGemmBN + hh * 128 + ch * 64),
                   static_cast<int32_t>((t / a.tiles_n) * kGemmBM), kEvictNormal);
     };
-    if (has_res && issuer && chunk_live(blockIdx.x, 0)) load_residual(blockIdx.x, 0);
+    if (has_res && !out_f32 && issuer && chunk_live(blockIdx.x, 0)) load_residual(blockIdx.x, 0);
 
     uint32_t it = 0;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (uint32_t w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const uint32_t t = w / a.splits;
       const uint32_t buf = it & 1;
       const uint32_t m0 = (t / a.tiles_n) * kGemmBM;
       const uint32_t n0 = (t % a.tiles_n) * kGemmBN;
@@ -214,6 +263,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (!live) continue;
 
         const uint32_t gcol = n0 + col0;
+        if (out_f32) {
+          // split-K / gradient accumulation: fp32 atomic adds straight into the output matrix
+          if (m0 + row < a.M) {
+            float* orow = a.out32 + static_cast<size_t>(m0 + row) * a.ldd32 + gcol;
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+              if (gcol + g * 4 < a.N)
+                atomicAdd(reinterpret_cast<float4*>(orow + g * 4),
+                          make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
+                                      __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])));
+            }
+          }
+          continue;
+        }
+        if (store_pre) {
+          // training forward of the h -> 4h projection: also keep the pre-activation (bias added)
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, 128);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const bool col_ok = gcol + g * 8 < a.N;
+            const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
+            if (has_bias && col_ok) {
+              const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + gcol + g * 8));
+              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack2<kBf16>(bw[j]);
+                x[2 * j] += f.x;
+                x[2 * j + 1] += f.y;
+              }
+            }
+            *reinterpret_cast<uint4*>(stage_ptr + row * 128u + phys) =
+                make_uint4(pack2<kBf16>(x[0], x[1]), pack2<kBf16>(x[2], x[3]), pack2<kBf16>(x[4], x[5]),
+                           pack2<kBf16>(x[6], x[7]));
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (issuer) {
+            tma_store_2d(&tmap_p, smem_base + stage_off, static_cast<int32_t>(gcol), static_cast<int32_t>(m0));
+            tma_store_commit();
+          }
+        }
         if (has_res) {
           mbar_wait(res_bar, res_phase);   // residual box is in the staging buffer
           res_phase ^= 1;
@@ -250,8 +345,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 f = unpack2<kBf16>(rw[j]);
-              x[2 * j] += f.x;
-              x[2 * j + 1] += f.y;
+              if (gelu_bwd) {   // aux = pre-activation u: dU = dA * GeLU'(u)
+                x[2 * j] *= gelu_erf_grad(f.x);
+                x[2 * j + 1] *= gelu_erf_grad(f.y);
+              } else {
+                x[2 * j] += f.x;
+                x[2 * j + 1] += f.y;
+              }
             }
           }
           *slot = make_uint4(pack2<kBf16>(x[0], x[1]), pack2<kBf16>(x[2], x[3]),
@@ -264,9 +364,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                        static_cast<int32_t>(m0));
           tma_store_commit();
           if (has_res) {   // prefetch the residual of this group's next live chunk
-            uint32_t nt = t, nch = ch + 1;
+            uint32_t nt = w, nch = ch + 1;
             if (nch == 2 || !chunk_live(nt, nch)) {
-              nt = t + gridDim.x;
+              nt = w + gridDim.x;
               nch = 0;
             }
             if (chunk_live(nt, nch)) {
@@ -287,21 +387,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
 }  // namespace
 
-cudaError_t gemm_prepare() {
-  cudaError_t e = cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kGemmSmemBytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <bool kBf16, bool kAMN, bool kBMN>
+cudaError_t prepare_one() {
+  return cudaFuncSetAttribute(gemm_kernel<kBf16, kAMN, kBMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               kGemmSmemBytes);
 }
 
-void launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
-                 const CUtensorMap& tmap_r, const GemmArgs& args, bool bf16, int grid,
-                 cudaStream_t stream) {
-  if (bf16)
-    gemm_kernel<true><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(tmap_a, tmap_b, tmap_d, tmap_r, args);
-  else
-    gemm_kernel<false><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(tmap_a, tmap_b, tmap_d, tmap_r, args);
+cudaError_t gemm_prepare() {
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = prepare_one<true, false, false>();
+  if (e == cudaSuccess) e = prepare_one<true, false, true>();
+  if (e == cudaSuccess) e = prepare_one<true, true, true>();
+  if (e == cudaSuccess) e = prepare_one<false, false, false>();
+  if (e == cudaSuccess) e = prepare_one<false, false, true>();
+  if (e == cudaSuccess) e = prepare_one<false, true, true>();
+  return e;
+}
+
+cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
+                        const CUtensorMap& tmap_r, const CUtensorMap& tmap_p, const GemmArgs& args,
+                        bool bf16, bool a_mn, bool b_mn, int grid, cudaStream_t stream) {
+#define EMDR2_GEMM_LAUNCH(BF, AMN, BMN)                                                           \
+  gemm_kernel<BF, AMN, BMN><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(tmap_a, tmap_b, tmap_d, \
+                                                                           tmap_r, tmap_p, args)
+  if (a_mn && !b_mn) return cudaErrorInvalidValue;   // not needed by any forward/backward product
+  if (bf16) {
+    if (a_mn) EMDR2_GEMM_LAUNCH(true, true, true);
+    else if (b_mn) EMDR2_GEMM_LAUNCH(true, false, true);
+    else EMDR2_GEMM_LAUNCH(true, false, false);
+  } else {
+    if (a_mn) EMDR2_GEMM_LAUNCH(false, true, true);
+    else if (b_mn) EMDR2_GEMM_LAUNCH(false, false, true);
+    else EMDR2_GEMM_LAUNCH(false, false, false);
+  }
+#undef EMDR2_GEMM_LAUNCH
+  return cudaGetLastError();
 }
 
 }  // namespace emdr2

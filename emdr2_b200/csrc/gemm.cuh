@@ -42,20 +42,28 @@ constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + kGemmOutBytes + k
 constexpr uint32_t kGemmBias = 1u;
 constexpr uint32_t kGemmGelu = 2u;
 constexpr uint32_t kGemmResidual = 4u;
+constexpr uint32_t kGemmAccumF32 = 8u;    // D is fp32 [M, ldd32]; results are atomically ADDED (split-K, grad accumulation)
+constexpr uint32_t kGemmGeluBwd = 16u;    // D = acc * GeLU'(aux), aux [M, N] 16-bit arrives like the residual
+constexpr uint32_t kGemmPreact = 32u;     // also store acc + bias (before GeLU) through tmap_p
 
 struct GemmArgs {
   uint32_t M, N, K;
   uint32_t tiles_m, tiles_n;
   uint32_t idesc;
   uint32_t flags;
+  uint32_t splits;         // split-K factor (>1 only with kGemmAccumF32)
+  uint32_t kb_per_split;   // 64-wide k blocks per split
+  uint32_t ldd32;          // row pitch of out32 (elements)
   const void* bias;        // [N] 16-bit
+  float* out32;            // fp32 output for kGemmAccumF32
 };
 
 cudaError_t gemm_prepare();
-// tmap_r describes the residual [M, N] (box 128 x 64) and is only read with kGemmResidual; pass
-// tmap_d otherwise.
-void launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
-                 const CUtensorMap& tmap_r, const GemmArgs& args, bool bf16, int grid,
-                 cudaStream_t stream);
+// tmap_r: residual / GeLU-backward aux [M, N] (box 128 x 64), read only with those flags; tmap_p:
+// pre-activation output, written only with kGemmPreact; pass tmap_d for the unused ones.
+// a_mn / b_mn: operand stored [k, m] / [k, n] row-major (tensor maps with 64 x 64 boxes).
+cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
+                        const CUtensorMap& tmap_r, const CUtensorMap& tmap_p, const GemmArgs& args,
+                        bool bf16, bool a_mn, bool b_mn, int grid, cudaStream_t stream);
 
 }  // namespace emdr2

@@ -30,4 +30,24 @@ cudaError_t launch_token_logprob(bool bf16, const void* logits, int64_t ld, cons
                                  float* logprob, float* lse, int rows, int vocab,
                                  cudaStream_t stream);
 
+// ---- backward (rowops_bwd.cu).  Parameter gradients accumulate into fp32 buffers (atomic adds).
+// LayerNorm: dx = rstd (g - mean(g) - xhat mean(g xhat)) + dres, g = dy gamma; dgamma += sum dy xhat;
+// dbeta += sum dy.  dres (optional) is the gradient arriving on the residual branch of the pre-LN
+// layer (transformer.py:480-515), fused here instead of a separate add.
+cudaError_t launch_layernorm_bwd(bool bf16, const void* dy, int64_t ldy, const void* x, int64_t ldx,
+                                 const void* gamma, const float* mean, const float* rstd, const void* dres,
+                                 int64_t ldr, void* dx, int64_t lddx, float* dgamma, float* dbeta, int rows,
+                                 int h, int sm_count, cudaStream_t stream);
+// out[n] += sum_m dy[m, n]  (bias gradients)
+cudaError_t launch_colsum(bool bf16, const void* dy, int64_t ld, float* out, int rows, int n,
+                          cudaStream_t stream);
+// dlogits[r, v] = g[r] (1[v == label_r] - softmax(logits[r])_v): backward of launch_token_logprob
+cudaError_t launch_token_logprob_bwd(bool bf16, const void* logits, int64_t ld, const int64_t* labels,
+                                     const float* lse, const float* g, void* dlogits, int64_t ldd, int rows,
+                                     int vocab, cudaStream_t stream);
+// dword[ids[t]] += dx[t]; dpos[t % seq] += dx[t]; dtype_emb[types[t]] += dx[t]
+cudaError_t launch_embedding_bwd(bool bf16, const void* dx, const int64_t* ids, const int64_t* types,
+                                 float* dword, float* dpos, float* dtype_emb, int tokens, int seq, int h,
+                                 int vocab, int num_types, cudaStream_t stream);
+
 }  // namespace emdr2

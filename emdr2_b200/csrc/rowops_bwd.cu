@@ -1,0 +1,256 @@
+// Backward of the row-wise operators (see rowops.cuh): LayerNorm, bias (column sums), the token
+// log-probability / cross-entropy, and the embedding sum.  fp32 math; parameter gradients are
+// ACCUMULATED into fp32 buffers with atomics (main-grad style), activation gradients are 16-bit.
+#include "rowops.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace emdr2 {
+namespace {
+
+constexpr int kMaxChunks = 4;
+
+template <bool kBf16>
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 p;
+    if constexpr (kBf16) p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    else p = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = p.x;
+    f[2 * i + 1] = p.y;
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if constexpr (kBf16) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = dy * gamma, xhat = (x - mean) * rstd
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy.
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const uint16_t* __restrict__ dy, int64_t ldy, const uint16_t* __restrict__ x, int64_t ldx,
+                     const uint16_t* __restrict__ gamma, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const uint16_t* __restrict__ dres, int64_t ldr,
+                     uint16_t* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int rows, int h) {
+  __shared__ float s_red[8][kMaxChunks * 256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc_g[kMaxChunks][8], acc_b[kMaxChunks][8], gam[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (c * 32 + lane) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc_g[c][i] = acc_b[c][i] = 0.f;
+    if (col < h) unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(gamma + col)), gam[c]);
+  }
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[kMaxChunks][8], xh[kMaxChunks][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < h) {
+        float d[8], xv[8];
+        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * ldy + col)), d);
+        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx + col)), xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[c][i] = (xv[i] - mu) * rs;
+          g[c][i] = d[i] * gam[c][i];
+          s1 += g[c][i];
+          s2 = fmaf(g[c][i], xh[c][i], s2);
+          acc_g[c][i] = fmaf(d[i], xh[c][i], acc_g[c][i]);
+          acc_b[c][i] += d[i];
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) / static_cast<float>(h);
+    const float c2 = warp_sum(s2) / static_cast<float>(h);
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < h) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rs * (g[c][i] - c1 - xh[c][i] * c2);
+        if (dres) {
+          float r[8];
+          unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * ldr + col)), r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += r[i];
+        }
+        *reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * lddx + col) = pack8<kBf16>(o);
+      }
+    }
+  }
+  // block reduction of the parameter gradients, then one atomic per column per block
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < h) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_red[warp][col + i] = pass == 0 ? acc_g[c][i] : acc_b[c][i];
+      }
+    }
+    __syncthreads();
+    float* dst = pass == 0 ? dgamma : dbeta;
+    if (dst) {
+      for (int col = threadIdx.x; col < h; col += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_red[w][col];
+        atomicAdd(dst + col, t);
+      }
+    }
+  }
+}
+
+// out[n] += sum_m dy[m, n]   (bias gradient)
+template <bool kBf16>
+__global__ void __launch_bounds__(128)
+colsum_kernel(const uint16_t* __restrict__ dy, int64_t ld, float* __restrict__ out, int rows, int n) {
+  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (col >= n) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    float f[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * ld + col)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(out + col + i, acc[i]);
+}
+
+// dlogits[r, v] = g[r] * (1[v == label_r] - exp(logits[r, v] - lse[r])): backward of token_logprob.
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+token_logprob_bwd_kernel(const uint16_t* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
+                         const float* __restrict__ lse, const float* __restrict__ g,
+                         uint16_t* __restrict__ dlogits, int64_t ldd, int vocab) {
+  const int row = blockIdx.x;
+  const float gr = g[row], l = lse[row];
+  const int64_t lab = labels[row];
+  const bool lab_ok = lab >= 0 && lab < vocab;
+  const uint16_t* lr = logits + static_cast<size_t>(row) * ld;
+  uint16_t* dr = dlogits + static_cast<size_t>(row) * ldd;
+  for (int col = threadIdx.x * 8; col < vocab; col += 256 * 8) {
+    float f[8], o[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(lr + col)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float onehot = (lab_ok && lab == col + i) ? 1.f : 0.f;
+      o[i] = lab_ok ? gr * (onehot - __expf(f[i] - l)) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(dr + col) = pack8<kBf16>(o);
+  }
+}
+
+// dword[ids[t]] += dx[t], dpos[t % seq] += dx[t], dtype[types[t]] += dx[t]  (fp32 atomics)
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+embedding_bwd_kernel(const uint16_t* __restrict__ dx, const int64_t* __restrict__ ids,
+                     const int64_t* __restrict__ types, float* __restrict__ dword, float* __restrict__ dpos,
+                     float* __restrict__ dtype_emb, int tokens, int seq, int h, int vocab, int num_types) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= tokens) return;
+  int64_t id = ids[t];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  int64_t ty = (types && dtype_emb) ? types[t] : 0;
+  ty = ty < 0 ? 0 : (ty >= num_types ? num_types - 1 : ty);
+  for (int col = lane * 8; col < h; col += 256) {
+    float f[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dx + static_cast<size_t>(t) * h + col)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (dword) atomicAdd(dword + static_cast<size_t>(id) * h + col + i, f[i]);
+      if (dpos) atomicAdd(dpos + static_cast<size_t>(t % seq) * h + col + i, f[i]);
+      if (types && dtype_emb) atomicAdd(dtype_emb + static_cast<size_t>(ty) * h + col + i, f[i]);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_layernorm_bwd(bool bf16, const void* dy, int64_t ldy, const void* x, int64_t ldx,
+                                 const void* gamma, const float* mean, const float* rstd, const void* dres,
+                                 int64_t ldr, void* dx, int64_t lddx, float* dgamma, float* dbeta, int rows,
+                                 int h, int sm_count, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (h % 8 || h > kMaxChunks * 256) return cudaErrorInvalidValue;
+  int grid = (rows + 7) / 8;
+  if (grid > sm_count * 4) grid = sm_count * 4;
+  auto p = [](const void* v) { return static_cast<const uint16_t*>(v); };
+  if (bf16)
+    layernorm_bwd_kernel<true><<<grid, 256, 0, stream>>>(p(dy), ldy, p(x), ldx, p(gamma), mean, rstd, p(dres), ldr,
+                                                         static_cast<uint16_t*>(dx), lddx, dgamma, dbeta, rows, h);
+  else
+    layernorm_bwd_kernel<false><<<grid, 256, 0, stream>>>(p(dy), ldy, p(x), ldx, p(gamma), mean, rstd, p(dres), ldr,
+                                                          static_cast<uint16_t*>(dx), lddx, dgamma, dbeta, rows, h);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_colsum(bool bf16, const void* dy, int64_t ld, float* out, int rows, int n,
+                          cudaStream_t stream) {
+  if (rows <= 0 || n <= 0) return cudaSuccess;
+  if (n % 8) return cudaErrorInvalidValue;
+  dim3 grid((n / 8 + 127) / 128, rows < 256 ? rows : 256);
+  if (bf16) colsum_kernel<true><<<grid, 128, 0, stream>>>(static_cast<const uint16_t*>(dy), ld, out, rows, n);
+  else colsum_kernel<false><<<grid, 128, 0, stream>>>(static_cast<const uint16_t*>(dy), ld, out, rows, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_token_logprob_bwd(bool bf16, const void* logits, int64_t ld, const int64_t* labels,
+                                     const float* lse, const float* g, void* dlogits, int64_t ldd, int rows,
+                                     int vocab, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (vocab % 8) return cudaErrorInvalidValue;
+  if (bf16)
+    token_logprob_bwd_kernel<true><<<rows, 256, 0, stream>>>(static_cast<const uint16_t*>(logits), ld, labels, lse,
+                                                             g, static_cast<uint16_t*>(dlogits), ldd, vocab);
+  else
+    token_logprob_bwd_kernel<false><<<rows, 256, 0, stream>>>(static_cast<const uint16_t*>(logits), ld, labels, lse,
+                                                              g, static_cast<uint16_t*>(dlogits), ldd, vocab);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_embedding_bwd(bool bf16, const void* dx, const int64_t* ids, const int64_t* types,
+                                 float* dword, float* dpos, float* dtype_emb, int tokens, int seq, int h,
+                                 int vocab, int num_types, cudaStream_t stream) {
+  if (tokens <= 0) return cudaSuccess;
+  if (h % 8) return cudaErrorInvalidValue;
+  const int grid = (tokens + 7) / 8;
+  if (bf16)
+    embedding_bwd_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(dx), ids, types, dword, dpos,
+                                                         dtype_emb, tokens, seq, h, vocab, num_types);
+  else
+    embedding_bwd_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(dx), ids, types, dword, dpos,
+                                                          dtype_emb, tokens, seq, h, vocab, num_types);
+  return cudaGetLastError();
+}
+
+}  // namespace emdr2

@@ -12,6 +12,7 @@ post-gather arithmetic without a GPU.
 import torch
 import torch.nn.functional as F
 
+from . import autograd as ag
 from . import ops
 
 
@@ -58,6 +59,6 @@ def get_kl_div_retriever(lm_logits, topk_log_probs, labels, loss_mask):
 
 def reader_cross_entropy(lm_logits, labels, loss_mask):
     """CrossEntropyLoss(reduction='none', ignore_index=0) summed under loss_mask (:156-160)."""
-    lp, _ = ops.token_logprob(lm_logits, labels.clamp(min=0))
+    lp = ag.token_logprob(lm_logits, labels.clamp(min=0))       # differentiable w.r.t. the logits
     loss_ = torch.where(labels == 0, torch.zeros_like(lp), -lp)
     return torch.sum(loss_.reshape(-1) * loss_mask.reshape(-1)) / loss_mask.sum()

@@ -16,9 +16,9 @@ The steps are the reference's:
   8 one-context pass       -> logits [B, K, L, V] (training, --update-retriever)   :185-210
 
 Differences behind that surface: masks are never materialised (the kernels derive them from the
-ids, which is how the reference builds them: make_attention_mask_3d(ids, ids) < 0.5), the run is
-forward-only (no autograd graph is recorded yet), and configuration is passed explicitly instead of
-through the global get_args().
+ids, which is how the reference builds them: make_attention_mask_3d(ids, ids) < 0.5), gradients
+flow through emdr2_b200/autograd.py (library kernels for every backward op), and configuration is
+passed explicitly instead of through the global get_args().
 """
 import math
 
@@ -81,7 +81,6 @@ class EMDR2Model(nn.Module):
             return m.embed_text(m.context_model, tokens, mask, types)
         raise ValueError("Invalid embedder type.")
 
-    @torch.no_grad()
     def forward(self, query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5,
                 query_ids_t5_len, dec_ids, all_query_context_hidden_states=None,
                 all_query_context_ids_unflat=None, topk_log_probs=None):
@@ -94,11 +93,12 @@ class EMDR2Model(nn.Module):
 
         if all_query_context_hidden_states is None:
             query_logits = self.retriever_embedder(query_ids_bert, query_mask_bert, query_types, "query")
-            topk_evidence_data, _stale = self.evidence_retriever.get_topk(query_logits.clone().detach())
-            all_context_ids, all_context_types, all_query_extended_context_ids, query_one_context_ids = \
-                formatter.postprocess(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data,
-                                      topk, int(st["seq_length_ret"]), seq_length, st["cls_id"],
-                                      st["sep_id"], st["pad_id"], device=query_ids_bert.device)
+            with torch.no_grad():
+                topk_evidence_data, _stale = self.evidence_retriever.get_topk(query_logits.clone().detach())
+                all_context_ids, all_context_types, all_query_extended_context_ids, query_one_context_ids = \
+                    formatter.postprocess(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data,
+                                          topk, int(st["seq_length_ret"]), seq_length, st["cls_id"],
+                                          st["sep_id"], st["pad_id"], device=query_ids_bert.device)
             s_ret = all_context_ids.shape[-1]
             all_context_logits = self.retriever_embedder(all_context_ids.reshape(-1, s_ret), None,
                                                          all_context_types.reshape(-1, s_ret), "context")
@@ -118,9 +118,10 @@ class EMDR2Model(nn.Module):
         if self.training:
             lm_logits_one_context = None
             if st.get("update_retriever", False) and query_one_context_ids is not None:
-                dec_ids_repeated = torch.repeat_interleave(dec_ids, topk, dim=0)
-                flat, _ = self.language_model(query_one_context_ids, dec_ids_repeated)
-                lm_logits_one_context = flat.reshape(bsize, topk, flat.shape[1], flat.shape[2])
+                with torch.no_grad():       # "SG": no gradient through the one-context pass (:186)
+                    dec_ids_repeated = torch.repeat_interleave(dec_ids, topk, dim=0)
+                    flat, _ = self.language_model(query_one_context_ids, dec_ids_repeated)
+                    lm_logits_one_context = flat.reshape(bsize, topk, flat.shape[1], flat.shape[2])
             return lm_logits, topk_log_probs, lm_logits_one_context
         return lm_logits, topk_log_probs, all_query_context_hidden_states, all_query_context_ids_unflat
 

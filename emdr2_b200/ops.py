@@ -67,12 +67,28 @@ def linear(x, weight, bias=None, gelu=False, residual=None, out=None):
     return out
 
 
+def live_blocks(pad, block=128):
+    """uint8 [batch, ceil(s/block)]: 1 where the block holds at least one non-padding position of the
+    bool/uint8 padding mask [batch, s]; block 0 is always marked live.  This is what
+    attention(..., q_live=, k_live=) takes to skip all-padding blocks."""
+    b, s = pad.shape
+    nblk = -(-s // block)
+    live = (pad == 0)
+    if nblk * block != s:
+        live = torch.nn.functional.pad(live, (0, nblk * block - s))
+    live = live.view(b, nblk, block).any(dim=2)
+    live[:, 0] = True
+    return live.to(torch.uint8).contiguous()
+
+
 def attention(q, k, v, batch, heads, sq, sk, q_pad=None, k_pad=None, causal=False, scale=None,
-              out=None, return_lse=False):
+              out=None, return_lse=False, q_live=None, k_live=None):
     """Fused attention forward (head dim 64).  q/out: [batch*sq, >= heads*64] views, k/v:
     [batch*sk, >= heads*64] views (unit inner stride; e.g. column blocks of a fused QKV buffer).
     q_pad [batch, sq] / k_pad [batch, sk]: uint8/bool, 1 = padding.  Masked scores are replaced by
-    -10000 (the reference's attention_mask_func), not -inf."""
+    -10000 (the reference's attention_mask_func), not -inf.  q_live / k_live (uint8 block maps, see
+    live_blocks) switch on padding skipping: identical results at non-padding queries, zeros at
+    all-padding query blocks."""
     dtype, device = q.dtype, q.device
     if dtype not in _DTYPES or not q.is_cuda:
         raise TypeError("attention takes CUDA float16/bfloat16 tensors")
@@ -99,7 +115,8 @@ def attention(q, k, v, batch, heads, sq, sk, q_pad=None, k_pad=None, causal=Fals
         _lib.check(lib.emdr2_attention_fwd(
             _DTYPES[dtype], _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
             _ptr(out), out.stride(0), batch, heads, sq, sk, _ptr(masks[0]), _ptr(masks[1]),
-            1 if causal else 0, float(scale), _ptr(lse), _stream(device)), "emdr2_attention_fwd")
+            _ptr(q_live), _ptr(k_live), 1 if causal else 0, float(scale), _ptr(lse), _stream(device)),
+            "emdr2_attention_fwd")
     return (out, lse) if return_lse else out
 
 
@@ -171,3 +188,84 @@ def token_logprob(logits, labels):
                                            _ptr(lp), _ptr(lse), rows, vocab, _stream(device)),
                    "emdr2_token_logprob")
     return lp.view(labels.shape), lse.view(labels.shape)
+
+
+KIND_GEMM, KIND_ATTENTION, KIND_ROWOP = 0, 1, 2
+
+
+def timing(enable):
+    """Bracket every block-operator launch of this thread with CUDA events (measurement aid)."""
+    _lib.check(_lib.load().emdr2_ops_timing(1 if enable else 0), "emdr2_ops_timing")
+
+
+def timing_read(kind):
+    """(seconds, launches, algorithmic flops) of one kernel kind since the last read."""
+    ns, n, fl = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+    _lib.check(_lib.load().emdr2_ops_timing_read(kind, ctypes.byref(ns), ctypes.byref(n), ctypes.byref(fl)),
+               "emdr2_ops_timing_read")
+    return ns.value * 1e-9, n.value, fl.value
+
+
+GEMM_ACCUM_F32, GEMM_GELU_BWD, GEMM_PREACT = 8, 16, 32
+
+
+def gemm_ex(a, b, a_mn=False, b_mn=False, out=None, bias=None, gelu=False, residual=None,
+            gelu_bwd_aux=None, preact_out=None, accumulate_into=None, splits=1):
+    """General product out[m, n] = a . b^T with fp32 accumulation.
+
+    a is [m, k] (or [k, m] with a_mn=True), b is [n, k] (or [k, n] with b_mn=True): the *_mn forms
+    read a tensor whose ROW index is the contraction index, in place (no transpose copy):
+        dX = gemm_ex(dY, W, b_mn=True)                                   # [m,n] . [n,k]
+        gemm_ex(dY, X, a_mn=True, b_mn=True, accumulate_into=dW32, splits=8)   # dW += dY^T . X
+    accumulate_into: fp32 [m, n] tensor that receives atomic adds (split-K / grad accumulation).
+    gelu_bwd_aux: saved pre-activation u [m, n]; out = (a . b^T) * GeLU'(u).
+    preact_out: [m, n] 16-bit tensor that also receives a . b^T + bias before the GeLU."""
+    dtype, device = a.dtype, a.device
+    if dtype not in _DTYPES or not a.is_cuda:
+        raise TypeError("gemm_ex takes CUDA float16/bfloat16 tensors")
+    _check_2d("a", a, dtype, device)
+    _check_2d("b", b, dtype, device)
+    k, m = (a.shape if a_mn else (a.shape[1], a.shape[0]))
+    kb, n = (b.shape if b_mn else (b.shape[1], b.shape[0]))
+    if k != kb:
+        raise ValueError("contraction sizes differ: %d vs %d" % (k, kb))
+    flags = 0
+    aux, ld_aux = None, 0
+    if bias is not None:
+        flags |= GEMM_BIAS
+    if gelu:
+        flags |= GEMM_GELU
+    if residual is not None:
+        _check_2d("residual", residual, dtype, device)
+        flags |= GEMM_RESIDUAL
+        aux, ld_aux = residual, residual.stride(0)
+    if gelu_bwd_aux is not None:
+        _check_2d("gelu_bwd_aux", gelu_bwd_aux, dtype, device)
+        flags |= GEMM_GELU_BWD
+        aux, ld_aux = gelu_bwd_aux, gelu_bwd_aux.stride(0)
+    pre, ld_pre = None, 0
+    if preact_out is not None:
+        _check_2d("preact_out", preact_out, dtype, device)
+        flags |= GEMM_PREACT
+        pre, ld_pre = preact_out, preact_out.stride(0)
+    if accumulate_into is not None:
+        if accumulate_into.dtype != torch.float32 or tuple(accumulate_into.shape) != (m, n) \
+                or accumulate_into.stride(1) != 1 or accumulate_into.device != device:
+            raise ValueError("accumulate_into must be a float32 [m, n] tensor on the same device")
+        flags |= GEMM_ACCUM_F32
+        out = accumulate_into
+    elif out is None:
+        out = torch.empty((m, n), dtype=dtype, device=device)
+    else:
+        _check_2d("out", out, dtype, device)
+
+    def ld(t, inner):
+        return t.stride(0) if t.shape[0] > 1 else max(inner, t.stride(0))
+
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.emdr2_gemm_ex(
+            _DTYPES[dtype], _ptr(a), ld(a, a.shape[1]), 1 if a_mn else 0, _ptr(b), ld(b, b.shape[1]),
+            1 if b_mn else 0, _ptr(out), ld(out, n), _ptr(bias), _ptr(aux), ld_aux, _ptr(pre), ld_pre,
+            m, n, k, flags, int(splits), _stream(device)), "emdr2_gemm_ex")
+    return out

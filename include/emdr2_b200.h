@@ -127,6 +127,24 @@ EMDR2_API int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, i
                          int64_t ldd, const void* bias, const void* residual, int64_t ldr, int m,
                          int n, int k, int flags, void* cuda_stream);
 
+#define EMDR2_GEMM_ACCUM_F32 8  /* d is fp32 [m, ldd] and the product is atomically ADDED to it      */
+#define EMDR2_GEMM_GELU_BWD 16  /* d = acc * GeLU'(aux[m, n])  (aux = saved pre-activation)          */
+#define EMDR2_GEMM_PREACT 32    /* also store acc + bias (before GeLU) to preact[m, n]               */
+
+/* General form used by the training path.  a_mn / b_mn != 0: that operand is stored with the
+ * contraction index as its ROW index (a as [k, m], b as [k, n], row-major), so the backward products
+ * read the forward tensors in place:
+ *   dX[m,k] = dY[m,n] . W[n,k]      -> emdr2_gemm_ex(a = dY, b = W  with b_mn = 1)
+ *   dW[n,k] += dY[m,n]^T . X[m,k]   -> emdr2_gemm_ex(a = dY with a_mn = 1, b = X with b_mn = 1,
+ *                                      EMDR2_GEMM_ACCUM_F32, splits > 1: split-K over the tokens)
+ * (autograd of mpu.ColumnParallelLinear / RowParallelLinear, megatron/mpu/layers.py:170-363).
+ * aux: residual (EMDR2_GEMM_RESIDUAL) or saved pre-activation (EMDR2_GEMM_GELU_BWD, the backward of
+ * transformer.py:99-104 fused into the dA = dY . W2 product). */
+EMDR2_API int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb,
+                            int b_mn, void* d, int64_t ldd, const void* bias, const void* aux,
+                            int64_t ld_aux, void* preact, int64_t ld_preact, int m, int n, int k,
+                            int flags, int splits, void* cuda_stream);
+
 /* Fused attention forward, head dimension 64:
  *   o[b,i,h,:] = softmax_j(mask(scale * q[b,i,h,:].k[b,j,h,:])) . v[b,j,h,:]
  * q/o are [batch*sq, >= heads*64] and k/v [batch*sk, >= heads*64] row-major views (row pitches
@@ -136,12 +154,18 @@ EMDR2_API int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, i
  * attention_mask_func does (megatron/model/bert_model.py:31-33, t5_model.py:28-30), then softmax.
  * Replaces the baddbmm -> scale-mask-softmax -> bmm core of ParallelAttention.forward
  * (megatron/model/transformer.py:301-383) with attention dropout off.  lse (optional) receives
- * log(sum_j exp(masked score)) as [batch, heads, sq] fp32. */
+ * log(sum_j exp(masked score)) as [batch, heads, sq] fp32.
+ * q_live [batch, ceil(sq/128)] / k_live [batch, ceil(sk/128)] (optional bytes): 0 marks a block of
+ * 128 queries / keys that is all padding; such key blocks are skipped (their probabilities are
+ * exactly 0 for every non-padding query) and such query blocks store zeros; every batch entry needs
+ * at least one live key block.  Outputs at non-padding queries are unchanged; padding rows (which
+ * no consumer reads) are no longer the reference's uniform average.  NULL = exact reference
+ * behaviour everywhere. */
 EMDR2_API int emdr2_attention_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk,
                                   const void* v, int64_t ldv, void* o, int64_t ldo, int batch,
                                   int heads, int sq, int sk, const uint8_t* q_pad,
-                                  const uint8_t* k_pad, int causal, float scale, float* lse,
-                                  void* cuda_stream);
+                                  const uint8_t* k_pad, const uint8_t* q_live, const uint8_t* k_live,
+                                  int causal, float scale, float* lse, void* cuda_stream);
 
 /* y[r,:] = LayerNorm(x[r,:]) * gamma + beta with fp32 statistics (biased variance), h % 8 == 0,
  * h <= 1024: mpu.LayerNorm (megatron/mpu/layers.py:28-36).  mean/rstd: optional [rows] fp32. */
@@ -162,6 +186,52 @@ EMDR2_API int emdr2_embedding_fwd(int dtype, const int64_t* ids, const int64_t* 
  * logits [rows, vocab] 16-bit with row pitch ld; labels int64 [rows] (out of range -> logprob 0). */
 EMDR2_API int emdr2_token_logprob(int dtype, const void* logits, int64_t ld, const int64_t* labels,
                                   float* logprob, float* lse, int rows, int vocab, void* cuda_stream);
+
+/* ---- backward of the block operators (training path).  Activation gradients are 16-bit; parameter
+ * gradients are ACCUMULATED (atomic adds) into caller-owned fp32 buffers, Megatron main-grad style. */
+
+/* dq, dk, dv from dout and the forward's q, k, v, o, lse (autograd of transformer.py:301-383).
+ * Layouts, masks, live maps and scale as in emdr2_attention_fwd; dvec_ws: [batch, heads, sq] fp32
+ * scratch.  No gradient flows into masked scores (masked_fill semantics). */
+EMDR2_API int emdr2_attention_bwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                  const void* v, int64_t ldv, const void* o, int64_t ldo, const void* dout,
+                                  int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv,
+                                  int64_t lddv, int batch, int heads, int sq, int sk, const uint8_t* q_pad,
+                                  const uint8_t* k_pad, const uint8_t* q_live, const uint8_t* k_live,
+                                  int causal, float scale, const float* lse, float* dvec_ws,
+                                  void* cuda_stream);
+
+/* LayerNorm backward: dx = LN'(dy) (+ dres, the gradient on the residual branch); dgamma += ...,
+ * dbeta += ... (fp32, may be NULL).  mean/rstd from emdr2_layernorm_fwd. */
+EMDR2_API int emdr2_layernorm_bwd(int dtype, const void* dy, int64_t ldy, const void* x, int64_t ldx,
+                                  const void* gamma, const float* mean, const float* rstd, const void* dres,
+                                  int64_t ldr, void* dx, int64_t lddx, float* dgamma, float* dbeta, int rows,
+                                  int h, void* cuda_stream);
+
+/* out[n] += sum_m dy[m, n]: bias gradients. */
+EMDR2_API int emdr2_colsum(int dtype, const void* dy, int64_t ld, float* out, int rows, int n, void* cuda_stream);
+
+/* dlogits[r, :] = g[r] * (onehot(labels[r]) - softmax(logits[r, :])): backward of
+ * emdr2_token_logprob given g = dLoss/dlogprob and the saved lse. */
+EMDR2_API int emdr2_token_logprob_bwd(int dtype, const void* logits, int64_t ld, const int64_t* labels,
+                                      const float* lse, const float* g, void* dlogits, int64_t ldd, int rows,
+                                      int vocab, void* cuda_stream);
+
+/* dword[ids[t]] += dx[t]; dpos[t % seq] += dx[t]; dtype_emb[types[t]] += dx[t] (fp32, any may be NULL). */
+EMDR2_API int emdr2_embedding_bwd(int dtype, const void* dx, const int64_t* ids, const int64_t* types,
+                                  float* dword, float* dpos, float* dtype_emb, int tokens, int seq, int h,
+                                  int vocab, int num_types, void* cuda_stream);
+
+/* Measurement aid: with timing enabled every launch of the block operators made by the calling
+ * thread is bracketed by CUDA events on its stream.  emdr2_ops_timing_read sums the launch
+ * durations (ns), launch count and algorithmic FLOPs of one kernel kind since the last read and
+ * restarts the accumulation (blocks until the last timed launch has finished). */
+#define EMDR2_KIND_GEMM 0
+#define EMDR2_KIND_ATTENTION 1
+#define EMDR2_KIND_ROWOP 2
+#define EMDR2_KIND_COUNT 3
+EMDR2_API int emdr2_ops_timing(int enable);
+EMDR2_API int emdr2_ops_timing_read(int kind, int64_t* out_ns, int64_t* out_launches, double* out_flops);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,7 @@ def test_bert_tower_tiny_vs_reference_and_oracle(dtype):
     from emdr2_b200.blocks import BertTower
     from oracle import blocks as ob
     model = BertTower(_cfg(dtype)).to(DEV)
+    model.language_model.skip_padding = False        # reference values at padding positions too
     w32 = _fill(model, dtype)
     assert sorted(w32) == sorted(str(n) for n in _golden("bert")["names"])      # same parameter names
     inp = tiny_inputs()
@@ -67,6 +68,12 @@ def test_bert_tower_tiny_vs_reference_and_oracle(dtype):
     g = _golden("bert")
     _close(hidden, torch.from_numpy(g["hidden"]), dtype, scale=4.0)
     _close(pooled, torch.from_numpy(g["pooled"]), dtype, scale=4.0)
+    # padding skip (the default): every non-padding position is unchanged
+    model.language_model.skip_padding = True
+    fast = model.hidden_states(ids.to(DEV), types.to(DEV))
+    live = (ids > 0)
+    assert torch.equal(fast.cpu()[live], hidden.cpu()[live])
+    assert torch.equal(model(ids.to(DEV), None, types.to(DEV)), pooled)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
@@ -74,6 +81,7 @@ def test_t5_reader_tiny_vs_reference_and_oracle(dtype):
     from emdr2_b200.blocks import T5Reader
     from oracle import blocks as ob
     model = T5Reader(_cfg(dtype)).to(DEV)
+    model.language_model.skip_padding = False
     w32 = _fill(model, dtype)
     assert sorted(w32) == sorted(str(n) for n in _golden("t5")["names"])
     inp = tiny_inputs()
@@ -97,6 +105,16 @@ def test_t5_reader_tiny_vs_reference_and_oracle(dtype):
                             TINY["heads"], TINY["layers"])
     _close(fid_logits, want_fid, dtype)
     _close(fid_logits, torch.from_numpy(g["fid_logits"]), dtype, scale=4.0)
+    # padding skip (the default): logits at non-padding decoder positions and encoder states at
+    # non-padding positions are bit-identical
+    model.language_model.skip_padding = True
+    f_logits, f_enc = model(enc.to(DEV), dec.to(DEV))
+    assert torch.equal(f_enc.cpu()[enc > 0], enc_out.cpu()[enc > 0])
+    assert torch.equal(f_logits.cpu()[dec > 0], logits.cpu()[dec > 0])
+    f_fid, _ = model(fid_ids[:, :s], dec[:b].to(DEV), enc_hidden_states=f_enc.reshape(b, k * s, -1),
+                     enc_ids_for_mask=fid_ids)
+    assert torch.equal(f_fid.cpu()[dec[:b] > 0], fid_logits.cpu()[dec[:b] > 0])
+    model.language_model.skip_padding = False
     loss, _ = model(enc.to(DEV), dec.to(DEV), lm_labels=dec.to(DEV))
     want_loss = torch.nn.functional.cross_entropy(want_logits.reshape(-1, want_logits.shape[-1]),
                                                   dec.reshape(-1), reduction="none").view_as(dec)
@@ -110,6 +128,7 @@ def test_bert_base_shape_vs_oracle():
     dtype = torch.bfloat16
     cfg = dict(hidden=768, heads=12, layers=12, ffn=3072, vocab=1024, max_pos=256, dtype=dtype)
     model = BertTower(cfg).to(DEV)
+    model.language_model.skip_padding = False
     w32 = _fill(model, dtype)
     rng = np.random.RandomState(0)
     ids = torch.from_numpy(rng.randint(1, 1024, size=(4, 256)).astype(np.int64))

@@ -145,10 +145,13 @@ def test_retrieve_and_read_forward_tiny(tmp_path, dtype):
     enc = ob.t5_encode(ext_t, wt5, TINY["heads"], TINY["layers"])
     want_logits = ob.t5_decode(dec, enc.reshape(bsz, TOPK * S, -1), ext_t.reshape(bsz, TOPK * S), wt5,
                                TINY["heads"], TINY["layers"])
-    assert torch.allclose(lm_logits.float().cpu(), want_logits, rtol=2e-2, atol=2e-2)
+    live = dec > 0      # padding decoder positions are masked by the loss and not compared (skip_padding)
+    assert torch.allclose(lm_logits.float().cpu()[live], want_logits[live], rtol=2e-2, atol=2e-2)
     want_one, _ = ob.t5_forward(one_t, torch.repeat_interleave(dec, TOPK, dim=0), wt5, TINY["heads"], TINY["layers"])
     assert one_ctx.shape == (bsz, TOPK, L, TINY["vocab"])
-    assert torch.allclose(one_ctx.float().cpu().view(-1, L, TINY["vocab"]), want_one, rtol=2e-2, atol=2e-2)
+    live_rep = torch.repeat_interleave(live, TOPK, dim=0)
+    assert torch.allclose(one_ctx.float().cpu().view(-1, L, TINY["vocab"])[live_rep], want_one[live_rep],
+                          rtol=2e-2, atol=2e-2)
 
     # ---- losses (a10) on the GPU logits vs fp32 torch on the oracle logits
     lm_loss = losses.reader_cross_entropy(lm_logits, labels.to(DEV), loss_mask.to(DEV))

@@ -172,3 +172,81 @@ def test_embedding_forward(dtype):
     assert torch.equal(got.view(b, s, h), want)
     got2 = embedding(ids, word, pos)
     assert torch.equal(got2.view(b, s, h), word[ids] + pos[:s][None])
+
+
+def test_attention_padding_skip_changes_only_padding_rows():
+    """q_live / k_live block maps: identical outputs at non-padding queries, zeros where a whole
+    128-query block is padding (FiD-style interleaved padding on the key side)."""
+    from emdr2_b200.ops import attention, live_blocks
+    dtype = torch.bfloat16
+    batch, heads, sq, sk = 3, 4, 384, 1024
+    w = heads * 64
+    q, k, v = _rand((batch * sq, w), dtype, 41), _rand((batch * sk, w), dtype, 42), _rand((batch * sk, w), dtype, 43)
+    q_pad = torch.zeros(batch, sq, dtype=torch.bool, device=DEV)
+    q_pad[0, 100:] = True          # blocks 1, 2 dead
+    q_pad[1, 300:] = True          # block 2 partially live
+    k_pad = torch.zeros(batch, sk, dtype=torch.bool, device=DEV)
+    for p0 in range(0, sk, 256):   # 4 "passages" of 256 keys, each padded after 90..150 real tokens
+        k_pad[:, p0 + 90 + p0 // 16:p0 + 256] = True
+    k_pad[2, :] = True             # a batch entry with no real key at all
+    exact = attention(q, k, v, batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad)
+    fast = attention(q, k, v, batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad,
+                     q_live=live_blocks(q_pad), k_live=live_blocks(k_pad))
+    live_rows = (~q_pad).view(-1)
+    live_rows[2 * sq:] = False     # batch 2: every key is padding -> all rows are "uniform" rows
+    assert torch.equal(fast[live_rows], exact[live_rows])
+    assert (fast.view(batch, sq, w)[0, 128:] == 0).all()
+    want, _ = _ref_attention(q, k, v, batch, heads, sq, sk, q_pad, k_pad, False)
+    assert torch.allclose(exact.float(), want, rtol=2 ** -7, atol=2 ** -7)
+
+
+# ---------------------------------------------------------------- general GEMM (training path)
+@pytest.mark.parametrize("m,n,k", [(512, 768, 256), (1000, 520, 328), (4096, 3072, 768), (130, 72, 64)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_gemm_ex_mn_major_operands(m, n, k, dtype):
+    """dX = dY . W (b stored [k_contract, n]) and dW = dY^T . X (both operands stored with the
+    contraction index as the row index), vs fp32 matmul."""
+    from emdr2_b200.ops import gemm_ex
+    tol = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    a = _rand((m, k), dtype, 51)
+    b_kn = _rand((k, n), dtype, 52, scale=k ** -0.5)
+    got = gemm_ex(a, b_kn, b_mn=True).float()
+    want = a.float() @ b_kn.float()
+    assert torch.allclose(got, want, rtol=tol, atol=tol), (got - want).abs().max().item()
+    # a stored [k, m], b stored [k, n]: out[m, n] = a^T . b, accumulated in fp32 with split-K
+    a_km = _rand((k, m), dtype, 53, scale=k ** -0.5)
+    want2 = a_km.float().T @ b_kn.float()
+    for splits in (1, 3):
+        acc = torch.ones((m, n), dtype=torch.float32, device=DEV)
+        gemm_ex(a_km, b_kn, a_mn=True, b_mn=True, accumulate_into=acc, splits=splits)
+        assert torch.allclose(acc - 1.0, want2, rtol=1e-4, atol=1e-4), (acc - 1 - want2).abs().max().item()
+
+
+def test_gemm_ex_weight_gradient_shape_split_k():
+    """dW[n_out, k_in] += dY[tokens, n_out]^T . X[tokens, k_in] with tokens = 20000 split 16 ways."""
+    from emdr2_b200.ops import gemm_ex
+    dtype = torch.bfloat16
+    dy, x = _rand((20000, 768), dtype, 61, scale=0.05), _rand((20000, 3072), dtype, 62)
+    acc = torch.zeros((768, 3072), dtype=torch.float32, device=DEV)
+    gemm_ex(dy, x, a_mn=True, b_mn=True, accumulate_into=acc, splits=16)
+    want = dy.float().T @ x.float()
+    assert torch.allclose(acc, want, rtol=2e-4, atol=2e-3), (acc - want).abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_gemm_ex_preactivation_and_gelu_backward(dtype):
+    from emdr2_b200.ops import gemm_ex
+    tol = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    m, n, k = 900, 1024, 256
+    x, w, b = _rand((m, k), dtype, 71), _rand((n, k), dtype, 72, scale=k ** -0.5), _rand((n,), dtype, 73)
+    pre = torch.empty((m, n), dtype=dtype, device=DEV)
+    act = gemm_ex(x, w, bias=b, gelu=True, preact_out=pre)
+    u = x.float() @ w.float().T + b.float()
+    assert torch.allclose(pre.float(), u, rtol=tol, atol=tol)
+    assert torch.allclose(act.float(), torch.nn.functional.gelu(u), rtol=tol, atol=tol)
+    # backward through the activation fused into dA = dY . W2: out = (dy . w2) * gelu'(pre)
+    dy, w2 = _rand((m, k), dtype, 74), _rand((k, n), dtype, 75, scale=k ** -0.5)
+    got = gemm_ex(dy, w2, b_mn=True, gelu_bwd_aux=pre).float()
+    uu = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(uu).backward(dy.float() @ w2.float())
+    assert torch.allclose(got, uu.grad, rtol=2 * tol, atol=2 * tol), (got - uu.grad).abs().max().item()
