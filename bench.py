@@ -60,6 +60,9 @@ def parse_args():
     p.add_argument("--dec", type=int, default=32)
     p.add_argument("--layers", type=int, default=12)
     p.add_argument("--retrieve-only", action="store_true")
+    p.add_argument("--train", action="store_true",
+                   help="time the full EMDR2 training step: forward (incl. the no-grad one-context pass), "
+                        "losses, backward, gradient all-reduce and a fused AdamW update on fp32 masters")
     p.add_argument("--model-dtype", default="bf16", choices=["fp16", "bf16"])
     p.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     p.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
@@ -352,6 +355,8 @@ def run_reference_arm(a):
 def metric_name(a):
     if a.retrieve_only:
         return "queries/sec retrieve (brute-force MIPS top-%d) @%.0fM docs" % (a.k, a.rows / 1e6)
+    if getattr(a, "train", False):
+        return "queries/sec retrieve+read training step (fwd+bwd+optimizer) @%.0fM docs" % (a.rows / 1e6)
     return "queries/sec retrieve+read (forward) @%.0fM docs" % (a.rows / 1e6)
 
 
@@ -544,9 +549,10 @@ def run_retrieve_read(a):
     # ---- model: 2 x BERT-base towers + T5-base-shaped reader, random init N(0, 0.02)
     cfg = dict(hidden=a.dim, heads=a.dim // 64, layers=a.layers, ffn=4 * a.dim, vocab=30720, max_pos=512, dtype=mdtype)
     settings = dict(topk_retrievals=a.k, seq_length=a.seq, seq_length_ret=a.seq_ret, retriever_score_scaling=True,
-                    update_retriever=False, cls_id=101, sep_id=102, pad_id=0)
+                    update_retriever=a.train, cls_id=101, sep_id=102, pad_id=0)
     torch.manual_seed(1234)
-    model = EMDR2Model(cfg, retriever, settings, t5_vocab_size=30720, bert_vocab_size=30592).to(device).eval()
+    model = EMDR2Model(cfg, retriever, settings, t5_vocab_size=30720, bert_vocab_size=30592).to(device)
+    model.train(a.train)
     with torch.no_grad():
         for name, p in model.named_parameters():
             if "layernorm" in name:
@@ -565,15 +571,59 @@ def run_retrieve_read(a):
     def forward(x):
         return model(x["uid"], x["q_bert"], x["q_types"], None, x["q_t5"], x["q_len"], x["dec"])
 
-    def resident_step(i):
-        return forward(dev)
+    if a.train:
+        from emdr2_b200 import losses
+        params = [p for p in model.parameters()]
+        masters = [p.detach().float().clone().requires_grad_(True) for p in params]   # fp32 master weights
+        optimizer = torch.optim.AdamW(masters, lr=2e-5, weight_decay=0.01, fused=True)
+        labels_host = host["dec"].roll(-1, dims=1)
+        labels_host[:, -1] = 0
+        host["labels"] = labels_host
+        pinned["labels"] = labels_host.pin_memory()
+        dev["labels"] = labels_host.to(device)
+        out_loss = torch.empty(2, dtype=torch.float32).pin_memory()
 
-    def e2e_step(i):
-        x = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
-        lm_logits, topk_log_probs, _, _ = forward(x)
-        out_ids.copy_(lm_logits.argmax(dim=-1), non_blocking=True)
-        out_lp.copy_(topk_log_probs, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        def train_step(x):
+            lm_logits, topk_log_probs, one_ctx = forward(x)
+            mask = (x["labels"] > 0).float()
+            lm_loss = losses.reader_cross_entropy(lm_logits, x["labels"], mask)
+            r_loss, _, _ = losses.get_loss_and_retriever_utility(one_ctx, topk_log_probs, x["labels"], mask, 30523)
+            (lm_loss + r_loss).backward()
+            grads = [p.grad for p in params]
+            if world > 1:     # local DDP: one flat all-reduce of the gradients (model/distributed.py:35-63)
+                flat = torch._utils._flatten_dense_tensors(grads)
+                flat.div_(world)
+                d.dist.all_reduce(flat)
+                for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                    g.copy_(f)
+            for m, g in zip(masters, grads):
+                m.grad = g.float()
+            optimizer.step()
+            torch._foreach_copy_(params, masters)
+            for p in params:
+                p.grad = None
+            return lm_loss, r_loss
+
+        def resident_step(i):
+            return train_step(dev)
+
+        def e2e_step(i):
+            x = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
+            lm_loss, r_loss = train_step(x)
+            out_loss.copy_(torch.stack([lm_loss.detach(), r_loss.detach()]), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    else:
+        def resident_step(i):
+            with torch.no_grad():
+                return forward(dev)
+
+        def e2e_step(i):
+            x = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
+            with torch.no_grad():
+                lm_logits, topk_log_probs, _, _ = forward(x)
+            out_ids.copy_(lm_logits.argmax(dim=-1), non_blocking=True)
+            out_lp.copy_(topk_log_probs, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
     warm = max(3, a.warmup)
     for i in range(warm):
@@ -612,10 +662,14 @@ def run_retrieve_read(a):
             "exchange": "none" if world == 1 else "all-gather of queries [B,768] + all-gather of [nq,k] (score,id) pairs + merge",
             "l2": "inputs larger than L2 (%.2f GB evidence + %.1f GB of activations streamed per step vs 126 MB L2)" % (
                 (hi - lo) * a.dim * 2 / 1e9, tokens * a.dim * 2 * 40 / 1e9),
-            "stage": "retrieve + read FORWARD (EMDR2Model.forward eval path); no backward/optimizer in the timed region"},
+            "stage": ("full training step: forward incl. no-grad one-context pass, reader + retriever losses, backward, "
+                      "flat gradient all-reduce, fused AdamW on fp32 masters (torch.optim, library — the reference uses apex FusedAdam)")
+            if a.train else "retrieve + read FORWARD (EMDR2Model.forward eval path); no backward/optimizer in the timed region"},
         "e2e": {"value": a.batch * world / (ms_e2e / a.steps * 1e-3), "unit": "queries/s",
                 "h2d_bytes_per_step": in_bytes + fmt_h2d, "d2h_bytes_per_step": out_ids.numel() * 8 + out_lp.numel() * 4 + a.batch * a.k * 4,
-                "api": "EMDR2Model.forward (pinned host question tensors in; greedy token ids + passage log-probs out); includes the host-side passage lookup/formatting"},
+                "api": ("EMDR2Model.forward + losses + backward + optimizer (pinned host batch in; the two losses out)" if a.train else
+                        "EMDR2Model.forward (pinned host question tensors in; greedy token ids + passage log-probs out)") +
+                       "; includes the host-side passage lookup/formatting"},
         "gpu_launches": int(launches_step * a.steps),
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_t, "unit": "TFLOP/s", "frac": gemm_tf / peak_t,
                      "traffic": None, "kernel": "emdr2::gemm_kernel", "algorithmic_flops_per_step": gemm_fl / a.steps,

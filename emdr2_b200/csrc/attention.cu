@@ -263,15 +263,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // only 64 scores are ever live next to the 64 output accumulators.
       auto load_scores = [&](auto half_c) -> float {
         constexpr int half = decltype(half_c)::value;
-        if (constant) {   // warp-divergent but cheap: nothing to read, nothing to compare
-#pragma unroll
-          for (int c = 0; c < 64; ++c) t[c] = __float_as_uint(kMaskedLog2);
-          return kMaskedLog2;
-        }
+        // tcgen05.ld is .sync.aligned: every lane of the warp executes it, whatever its row needs
         const uint32_t s_addr = tmem_base + lane_tmem + half * 64;
         tmem_ld_32x32b_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&t[0]));
         tmem_ld_32x32b_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&t[32]));
         tmem_ld_wait();
+        if (constant) {   // per-row (divergent) from here on: nothing to scale, nothing to compare
+#pragma unroll
+          for (int c = 0; c < 64; ++c) t[c] = __float_as_uint(kMaskedLog2);
+          return kMaskedLog2;
+        }
         float mx = __uint_as_float(0xff800000u);
         if (plain) {
 #pragma unroll
@@ -294,7 +295,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
           for (int c = 0; c < 64; ++c) {
             const uint32_t cc = half * 64 + c;
             float x = __uint_as_float(t[c]) * a.scale_log2;
-            const bool masked = ((km[cc >> 5] >> (cc & 31)) & 1u) || (a.causal && kb0 + cc > qi);
+            const bool masked = q_is_pad || ((km[cc >> 5] >> (cc & 31)) & 1u) ||
+                                (a.causal && kb0 + cc > qi);
             x = masked ? kMaskedLog2 : x;
             x = (cc < valid) ? x : __uint_as_float(0xff800000u);
             t[c] = __float_as_uint(x);

@@ -89,6 +89,15 @@ int current_device_info(DeviceInfo* out) {
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(EMDR2_EINVAL, "device ordinal %d out of range", dev);
+  // Bind the device's primary context to THIS host thread: driver entry points such as
+  // cuTensorMapEncodeTiled need a current context, and callers like PyTorch's autograd engine run
+  // backward passes on worker threads that have only ever used the runtime API lazily.
+  static thread_local int bound_dev = -1;
+  if (bound_dev != dev) {
+    CUDA_TRY(cudaSetDevice(dev));
+    CUDA_TRY(cudaFree(nullptr));
+    bound_dev = dev;
+  }
   if (cache[dev].device != dev) {
     DeviceInfo d;
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));

@@ -78,8 +78,8 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
   if (k == 0) return fail(EMDR2_EINVAL, "k=0 is not supported");
   const bool accum = (flags & EMDR2_GEMM_ACCUM_F32) != 0;
   const int out_mult = accum ? 4 : 8;   // 16-byte rows: 8 16-bit or 4 fp32 elements
-  if ((n % 8) || (k % 8) || (lda % 8) || (ldb % 8) || (ldd % out_mult) || (a_mn && (m % 8)))
-    return fail(EMDR2_EINVAL, "m (if a is MN-major), n, k and the leading dimensions must be multiples of 8 (16-byte rows)");
+  if ((n % 8) || (lda % 8) || (ldb % 8) || (ldd % out_mult))
+    return fail(EMDR2_EINVAL, "n and the leading dimensions must be multiples of 8 (16-byte rows)");
   if (lda < (a_mn ? m : k) || ldb < (b_mn ? n : k) || ldd < n)
     return fail(EMDR2_EINVAL, "leading dimension smaller than the row length");
   if (!a || !b || !d) return fail(EMDR2_EINVAL, "NULL operand pointer");

@@ -56,7 +56,8 @@ class IndexBuilder(object):
         tower = self._context_tower()
         for row_id, tokens, types in self.batches:
             dev = next(tower.parameters()).device
-            emb = tower(tokens.to(dev, non_blocking=True), None, types.to(dev, non_blocking=True))
+            with torch.no_grad():
+                emb = tower(tokens.to(dev, non_blocking=True), None, types.to(dev, non_blocking=True))
             self.track_and_report_progress(batch_size=len(row_id))
             yield row_id, emb
 

@@ -122,7 +122,7 @@ EMDR2_API int emdr2_mips_destroy(void* handle);
  * RowParallelLinear at model-parallel size 1 (megatron/mpu/layers.py:170-363) with the bias-GeLU
  * (megatron/model/transformer.py:99-104) and bias-dropout-add at p=0 (:397-419) of the reference's
  * layer, and parallel_lm_logits (megatron/model/language_model.py:28-42).  lda/ldb/ldd/ldr are row
- * pitches in elements (multiples of 8); n and k multiples of 8. */
+ * pitches in elements (multiples of 8); n a multiple of 8. */
 EMDR2_API int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, int64_t ldb, void* d,
                          int64_t ldd, const void* bias, const void* residual, int64_t ldr, int m,
                          int n, int k, int flags, void* cuda_stream);

@@ -110,15 +110,17 @@ def test_retrieve_and_read_forward_tiny(tmp_path, dtype):
         labels[i, :ln] = torch.from_numpy(rng.randint(5, TINY["vocab"], size=ln))
     loss_mask = (labels > 0).float()
 
-    q_emb = model.retriever_embedder(q_bert.to(DEV), None, q_types.to(DEV), "query")
+    with torch.no_grad():
+        q_emb = model.retriever_embedder(q_bert.to(DEV), None, q_types.to(DEV), "query")
     got_topk, _ = retriever.get_topk(q_emb)
     uid = torch.tensor([-1, int(got_topk[1][0][1]), -3])            # query 1 came from its rank-1 passage
 
     # retrieval parity: oracle MIPS over the SAME stored fp16 rows and the SAME query embeddings
-    want_s, want_i, ties = om.mips_topk(rows_arr, q_emb.cpu().numpy(), TOPK + 1, ids=ids_arr, want_ties=True)
+    want_s, want_i, ties = om.mips_topk(rows_arr, q_emb.detach().cpu().numpy(), TOPK + 1, ids=ids_arr, want_ties=True)
     got_ids = np.array([t[0] for t in got_topk])
     assert np.array_equal(got_ids[ties == 0], want_i[ties == 0])
 
+    torch.set_grad_enabled(False)
     model.train()
     lm_logits, topk_log_probs, one_ctx = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV),
                                                torch.tensor(q_len).to(DEV), dec.to(DEV))
@@ -167,3 +169,27 @@ def test_retrieve_and_read_forward_tiny(tmp_path, dtype):
                                                                          TINY["vocab"] - 2)
     assert abs(float(r_loss) - float(want_r)) < 3e-2 and abs(float(null_loss) - float(want_n)) < 3e-2
     assert abs(float(util) - float(want_u)) < 3e-2
+    torch.set_grad_enabled(True)
+
+    # ---- one full training step through autograd: every parameter that the loss depends on gets a
+    # finite gradient and the reader loss decreases after a plain SGD step
+    model.train()
+    out = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV), torch.tensor(q_len).to(DEV),
+                dec.to(DEV))
+    l0 = losses.reader_cross_entropy(out[0], labels.to(DEV), loss_mask.to(DEV))
+    r0, _, _ = losses.get_loss_and_retriever_utility(out[2], out[1], labels.to(DEV), loss_mask.to(DEV),
+                                                     eos_id=TINY["vocab"] - 2)
+    (l0 + r0).backward()
+    with_grad = [n for n, p in model.named_parameters() if p.grad is not None]
+    assert any("retriever_model.query_model" in n for n in with_grad)
+    assert any("retriever_model.context_model" in n for n in with_grad)
+    assert any("language_model.language_model.decoder" in n for n in with_grad)
+    assert all(torch.isfinite(p.grad.float()).all() for p in model.parameters() if p.grad is not None)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.grad is not None:
+                p.add_(p.grad.float().clamp(-1, 1).to(p.dtype), alpha=-0.02)
+        out2 = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV), torch.tensor(q_len).to(DEV),
+                     dec.to(DEV))
+        l1 = losses.reader_cross_entropy(out2[0], labels.to(DEV), loss_mask.to(DEV))
+    assert float(l1) < float(l0)
