@@ -589,15 +589,15 @@ def run_retrieve_read(a):
             lm_loss = losses.reader_cross_entropy(lm_logits, x["labels"], mask)
             r_loss, _, _ = losses.get_loss_and_retriever_utility(one_ctx, topk_log_probs, x["labels"], mask, 30523)
             (lm_loss + r_loss).backward()
-            grads = [p.grad for p in params]
+            grads = [p.grad for p in params if p.grad is not None]
             if world > 1:     # local DDP: one flat all-reduce of the gradients (model/distributed.py:35-63)
                 flat = torch._utils._flatten_dense_tensors(grads)
                 flat.div_(world)
                 d.dist.all_reduce(flat)
                 for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
                     g.copy_(f)
-            for m, g in zip(masters, grads):
-                m.grad = g.float()
+            for m, p in zip(masters, params):
+                m.grad = None if p.grad is None else p.grad.float()
             optimizer.step()
             torch._foreach_copy_(params, masters)
             for p in params:

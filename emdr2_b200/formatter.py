@@ -67,10 +67,64 @@ def query_single_context_t5_format(query_ids, title_ids, context_ids, max_seq_le
     return enc + [pad_id] * (max_seq_length - len(enc))
 
 
+def _context_pieces(docs, main_doc_idx, room):
+    """Array form of `_fill_context`: the list of int64 array slices whose concatenation is the
+    passage plus as much of its neighbours as fits in `room` tokens."""
+    main = docs[main_doc_idx]
+    if len(main) > room or len(docs) == 1:
+        return [main[:room]]
+    spare = room - len(main)
+    if main_doc_idx == 0:
+        out = [main]
+        for doc in docs[1:]:
+            if spare <= 0:
+                break
+            out.append(doc[:spare])
+            spare -= len(doc)
+        return out
+    if main_doc_idx == -1:
+        head = docs[:-1]
+        total = sum(len(d) for d in head)
+        if total > spare:                     # the reference keeps the last spare-1 tokens here
+            drop = total - spare + 1
+            kept = []
+            for d in head:
+                if drop >= len(d):
+                    drop -= len(d)
+                    continue
+                kept.append(d[drop:])
+                drop = 0
+            head = kept
+        return list(head) + [main]
+    left = docs[0]
+    if len(left) > spare:
+        return [left[len(left) - spare + 1:], main]
+    out = [left, main]
+    if len(docs) == 3:
+        out.append(docs[2][:spare - len(left)])
+    return out
+
+
+def _put(row, pieces, limit):
+    """Write the concatenation of `pieces` into row[:limit] (truncating); returns the length written."""
+    pos = 0
+    for p in pieces:
+        n = min(len(p), limit - pos)
+        if n <= 0:
+            if pos >= limit:
+                break
+            continue                      # an empty piece (e.g. a neighbour cut to nothing)
+        row[pos:pos + n] = p[:n]
+        pos += n
+    return pos
+
+
 def postprocess_arrays(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data, topk_retrievals,
                        seq_length_ret, seq_length, cls_id, sep_id, pad_id):
     """numpy version of `postprocess`: returns (context_ids [B,K,S_ret], context_types [B,K,S_ret],
-    extended [B*K,S], single [B*K,S]) as int64 arrays."""
+    extended [B*K,S], single [B*K,S]) as int64 arrays.  Rows are assembled by slice assignment of
+    int64 array pieces (passages may be given as lists or as arrays, e.g. straight from the
+    memory-mapped token store); element-identical to the three `*_format` functions above."""
     uids = [int(u) for u in query_uid]
     bsz = len(uids)
     k_keep = int(topk_retrievals)
@@ -78,22 +132,32 @@ def postprocess_arrays(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_
     ctx_types = np.zeros((bsz, k_keep, seq_length_ret), dtype=np.int64)
     extended = np.full((bsz * k_keep, seq_length), pad_id, dtype=np.int64)
     single = np.full((bsz * k_keep, seq_length), pad_id, dtype=np.int64)
+    sep = np.array([sep_id], dtype=np.int64)
+    cls = np.array([cls_id], dtype=np.int64)
+    arr = lambda x: x if isinstance(x, np.ndarray) else np.asarray(x, dtype=np.int64)   # noqa: E731
     row = 0
     for bi, (qid, (topkids, text_list)) in enumerate(zip(uids, topk_evidence_data)):
-        query = [int(t) for t in query_ids_t5[bi][:int(query_ids_t5_len[bi])]]
+        query = arr(query_ids_t5[bi])[:int(query_ids_t5_len[bi])]
         kept = 0
         for eid, (doc_list, main_idx, title_ids) in zip(topkids, text_list):
             if qid == eid or kept >= k_keep:        # drop the passage the question came from
                 continue
-            passage = doc_list[main_idx]
-            ids, types, _ = build_tokens_types_paddings_from_ids(
-                list(title_ids) + [sep_id] + list(passage), seq_length_ret, cls_id, sep_id, pad_id)
-            ctx_ids[bi, kept] = ids
-            ctx_types[bi, kept] = types
-            extended[row] = query_extended_context_t5_format(query, title_ids, doc_list, main_idx,
-                                                             seq_length, sep_id, pad_id)
-            single[row] = query_single_context_t5_format(query, title_ids, passage, seq_length,
-                                                         sep_id, pad_id)
+            docs = [arr(d) for d in doc_list]
+            title = arr(title_ids)
+            passage = docs[main_idx]
+            # [CLS] title [SEP] passage (cut to S_ret - 1) [SEP]
+            n = _put(ctx_ids[bi, kept], (cls, title, sep, passage), seq_length_ret - 1)
+            ctx_ids[bi, kept, n] = sep_id
+            # query title [SEP] passage(+neighbours) [SEP]
+            head_len = len(query) + len(title) + 1
+            room = max(0, seq_length - head_len - 1)
+            pieces = [query, title, sep] + _context_pieces(docs, main_idx, room) + [sep]
+            if head_len + 1 > seq_length or sum(len(p) for p in pieces) > seq_length:
+                raise ValueError("question + title do not fit in seq_length=%d" % seq_length)
+            _put(extended[row], pieces, seq_length)
+            # query title [SEP] passage, cut to S - 1, [SEP]
+            n = _put(single[row], (query, title, sep, passage), seq_length - 1)
+            single[row, n] = sep_id
             kept += 1
             row += 1
         if kept != k_keep:

@@ -49,6 +49,22 @@ def test_formats_against_the_live_reference_on_fresh_random_cases():
                                            c["max_len"], 3, 0)
 
 
+def test_array_fast_path_is_identical_to_the_reference_on_every_golden_case():
+    """postprocess_arrays assembles rows from array slices; it must reproduce the reference's three
+    formats element for element (including every neighbour-fill branch)."""
+    cs = cases()
+    for c in cs:
+        if len(c["query"]) + len(c["title"]) + 2 > c["max_len"]:
+            continue                        # the reference itself overflows the row here
+        data = [([1], [([np.array(d, dtype=np.int64) for d in c["docs"]], c["main"], np.array(c["title"]))])]
+        q = c["query"] + [0] * 4
+        ctx, typ, ext, one = formatter.postprocess_arrays([-1], [q], [len(c["query"])], data, 1, c["max_len"],
+                                                          c["max_len"], 2, 3, 0)
+        assert ext[0].tolist() == c["extended"], c
+        assert one[0].tolist() == c["single"], c
+        assert ctx[0, 0].tolist() == c["bert"][0] and typ[0, 0].tolist() == c["bert"][1], c
+
+
 def test_postprocess_shapes_filtering_and_rows():
     cs = cases()[:12]
     b, k = 3, 3
