@@ -599,7 +599,8 @@ def run_retrieve_read(a):
             for m, p in zip(masters, params):
                 m.grad = None if p.grad is None else p.grad.float()
             optimizer.step()
-            torch._foreach_copy_(params, masters)
+            with torch.no_grad():
+                torch._foreach_copy_(params, masters)
             for p in params:
                 p.grad = None
             return lm_loss, r_loss

@@ -174,7 +174,7 @@ def postprocess(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data, t
     if torch.is_tensor(query_uid):
         query_uid = query_uid.tolist()
     if torch.is_tensor(query_ids_t5):
-        query_ids_t5 = query_ids_t5.tolist()
+        query_ids_t5 = query_ids_t5.cpu().numpy()
     if torch.is_tensor(query_ids_t5_len):
         query_ids_t5_len = query_ids_t5_len.tolist()
     arrays = postprocess_arrays(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data,

@@ -94,7 +94,11 @@ class EMDR2Model(nn.Module):
         if all_query_context_hidden_states is None:
             query_logits = self.retriever_embedder(query_ids_bert, query_mask_bert, query_types, "query")
             with torch.no_grad():
-                topk_evidence_data, _stale = self.evidence_retriever.get_topk(query_logits.clone().detach())
+                if getattr(self.evidence_retriever, "supports_arrays", False):
+                    topk_evidence_data, _stale = self.evidence_retriever.get_topk(query_logits.detach(),
+                                                                                  as_arrays=True)
+                else:
+                    topk_evidence_data, _stale = self.evidence_retriever.get_topk(query_logits.clone().detach())
                 all_context_ids, all_context_types, all_query_extended_context_ids, query_one_context_ids = \
                     formatter.postprocess(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data,
                                           topk, int(st["seq_length_ret"]), seq_length, st["cls_id"],

@@ -71,7 +71,13 @@ class B200EvidenceRetriever(object):
             allq = q
         return self.mips_index.search(allq, self.topk)
 
-    def get_topk(self, query_tensor):
+    #: EMDR2Model passes as_arrays=True when the retriever advertises it (skips ~B*K*4 .tolist() calls)
+    supports_arrays = True
+
+    def get_topk(self, query_tensor, as_arrays=False):
+        """(topk_data, distance) like the reference.  as_arrays=True keeps the passage / title tokens
+        as the int64 arrays the token store returns instead of converting them to Python lists
+        (emdr2_model.py:464-466 calls .tolist() on each); formatter.postprocess takes either."""
         local_bsize = query_tensor.shape[0]
         scores, ids = self.search_all(query_tensor)
         rank = self.mips_index.rank
@@ -87,7 +93,11 @@ class B200EvidenceRetriever(object):
             text_list = []
             for idx in topkarray:
                 doc_idxs, main_doc_idx = self.wikititledocmap.get_neighbour_paragraphs(idx)
-                doc_list = [self.passages_map[doc_id - 1].tolist() for doc_id in doc_idxs]
-                text_list.append((doc_list, main_doc_idx, self.title_map[idx - 1].tolist()))
+                if as_arrays:
+                    doc_list = [self.passages_map[doc_id - 1] for doc_id in doc_idxs]
+                    text_list.append((doc_list, main_doc_idx, self.title_map[idx - 1]))
+                else:
+                    doc_list = [self.passages_map[doc_id - 1].tolist() for doc_id in doc_idxs]
+                    text_list.append((doc_list, main_doc_idx, self.title_map[idx - 1].tolist()))
             topk_data.append((topkarray, text_list))
         return topk_data, distance
