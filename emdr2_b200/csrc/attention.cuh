@@ -60,8 +60,8 @@ struct AttnArgs {
 struct AttnBwdArgs {
   uint32_t batch, heads, sq, sk;
   uint32_t causal;
-  uint32_t idesc_s;        // M=128, N=128, A/B K-major
-  uint32_t idesc_o;        // M=128, N=64,  B MN-major
+  uint32_t idesc_s;        // M=128, N=64, A/B K-major   (S-type products over 64-row streamed blocks)
+  uint32_t idesc_o;        // M=128, N=64, B MN-major    (accumulating products)
   float scale, scale_log2;
   const uint8_t* q_pad;
   const uint8_t* k_pad;
@@ -74,9 +74,13 @@ struct AttnBwdArgs {
 cudaError_t attention_bwd_prepare();
 cudaError_t launch_attention_bwd_prep(bool bf16, const void* dout, int64_t lddo, const void* out, int64_t ldo,
                                       float* dvec, int batch, int heads, int sq, cudaStream_t stream);
-cudaError_t launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                                 const CUtensorMap& tdo, const CUtensorMap& tdq, const CUtensorMap& tdk,
-                                 const CUtensorMap& tdv, const AttnBwdArgs& a, bool bf16, cudaStream_t stream);
+// 3-D tensor maps of the backward: 128-row boxes for the tiles a CTA owns / stores, 64-row boxes for
+// the operand blocks it streams.
+struct AttnBwdMaps {
+  CUtensorMap q128, do128, dq128, k64, v64;        // dQ kernel
+  CUtensorMap k128, v128, dk128, dv128, q64, do64; // dK/dV kernel
+};
+cudaError_t launch_attention_bwd(const AttnBwdMaps& maps, const AttnBwdArgs& a, bool bf16, cudaStream_t stream);
 
 cudaError_t attention_prepare();
 void launch_attention_fwd(const CUtensorMap& tmap_q, const CUtensorMap& tmap_k,

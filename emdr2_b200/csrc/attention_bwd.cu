@@ -86,7 +86,7 @@ attention_bwd_prep_kernel(const uint16_t* __restrict__ dout, int64_t lddo, const
 
 struct BwdBars {
   uint64_t fixed_full;     // the CTA's own tiles (Q,dO resp. K,V)
-  uint64_t ring_full[2];   // streamed tiles (K,V resp. Q,dO)
+  uint64_t ring_full[2];   // streamed 64-row tiles (K,V resp. Q,dO)
   uint64_t ring_empty[2];
   uint64_t sdp_full;       // S and dP products landed in TMEM
   uint64_t sdp_empty;      // row threads have read them (4 warps)
@@ -95,27 +95,44 @@ struct BwdBars {
   uint32_t tmem_base;
 };
 
+constexpr int kBwdBlk = 64;               // streamed keys (dQ kernel) / queries (dK,dV kernel) per step
+constexpr int kHalfTile = kBwdBlk * 64 * 2;   // 64 x 64 x 2 B = 8 KiB
+
+template <int kRegs>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
+// Both kernels: 256 TMEM columns and < 113 KiB of shared memory per CTA so that two CTAs share an SM
+// (the second hides the first one's TMA -> MMA -> row-thread -> MMA latency chain), registers moved
+// from the TMA/MMA warps to the four row warps with setmaxnreg, streamed operand blocks of 64 rows.
+
 // ============================================================================ dQ
-// smem: Q 16K | dO 16K | ring 2 x (K 16K + V 16K) | dS 32K | bars
-constexpr int kDqSmem = 2 * kTile + 2 * 2 * kTile + 2 * kTile + 256;
+// smem: Q 16K | dO 16K | ring 2 x (K 8K + V 8K) | dS 16K | bars.   TMEM: S [0,64) dP [64,128) dQ [128,192)
+constexpr int kDqSmem = 2 * kTile + 2 * 2 * kHalfTile + kTile + 256;
 
 template <bool kBf16>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                         const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr uint32_t off_q = 0, off_do = kTile, off_ring = 2 * kTile, off_ds = off_ring + 4 * kTile,
-                     off_bar = off_ds + 2 * kTile;
+  constexpr uint32_t off_q = 0, off_do = kTile, off_ring = 2 * kTile, off_ds = off_ring + 4 * kHalfTile,
+                     off_bar = off_ds + kTile;
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + off_bar);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t q0 = blockIdx.x * kAttnBQ, head = blockIdx.y, b = blockIdx.z;
-  const uint32_t nblk = (a.sk + kAttnBK - 1) / kAttnBK;
+  const uint32_t nblk = (a.sk + kBwdBlk - 1) / kBwdBlk;        // 64-key steps
+  const uint32_t nlive = (a.sk + kAttnBK - 1) / kAttnBK;       // the live map is per 128 keys
   const int32_t col_h = static_cast<int32_t>(head * kAttnHeadDim);
-  const uint8_t* k_live = a.k_live ? a.k_live + static_cast<size_t>(b) * nblk : nullptr;
+  const uint8_t* k_live = a.k_live ? a.k_live + static_cast<size_t>(b) * nlive : nullptr;
   auto next_live = [&](uint32_t j) {
-    while (j < nblk && k_live && k_live[j] == 0) ++j;
+    while (j < nblk && k_live && k_live[j >> 1] == 0) ++j;
     return j;
   };
   const bool cta_dead = a.q_live && a.q_live[static_cast<size_t>(b) * gridDim.x + blockIdx.x] == 0;
@@ -134,75 +151,86 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     fence_proxy_async_smem();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_alloc(smem_u32(&bars->tmem_base), 256);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 64, tmem_dq = tmem_base + 128;
 
-  if (warp == 0) {
-    if (lane == 0 && !cta_dead) {
-      const uint32_t fb = smem_u32(&bars->fixed_full);
-      mbar_arrive_expect_tx(fb, 2 * kTile);
-      tma_load_3d(smem_base + off_q, &tmap_q, fb, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b), kEvictNormal);
-      tma_load_3d(smem_base + off_do, &tmap_do, fb, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b), kEvictNormal);
-      uint32_t stage = 0, phase = 0;
-      for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1)) {
-        mbar_wait(smem_u32(&bars->ring_empty[stage]), phase ^ 1);
-        const uint32_t fbar = smem_u32(&bars->ring_full[stage]);
-        mbar_arrive_expect_tx(fbar, 2 * kTile);
-        const uint32_t dst = smem_base + off_ring + stage * 2 * kTile;
-        tma_load_3d(dst, &tmap_k, fbar, col_h, static_cast<int32_t>(j * kAttnBK), static_cast<int32_t>(b), kEvictLast);
-        tma_load_3d(dst + kTile, &tmap_v, fbar, col_h, static_cast<int32_t>(j * kAttnBK), static_cast<int32_t>(b), kEvictLast);
-        if (++stage == 2) {
-          stage = 0;
-          phase ^= 1;
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0) {
+      if (lane == 0 && !cta_dead) {
+        const uint32_t fb = smem_u32(&bars->fixed_full);
+        mbar_arrive_expect_tx(fb, 2 * kTile);
+        tma_load_3d(smem_base + off_q, &tmap_q, fb, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b), kEvictNormal);
+        tma_load_3d(smem_base + off_do, &tmap_do, fb, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b), kEvictNormal);
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1)) {
+          mbar_wait(smem_u32(&bars->ring_empty[stage]), phase ^ 1);
+          const uint32_t fbar = smem_u32(&bars->ring_full[stage]);
+          mbar_arrive_expect_tx(fbar, 2 * kHalfTile);
+          const uint32_t dst = smem_base + off_ring + stage * 2 * kHalfTile;
+          tma_load_3d(dst, &tmap_k, fbar, col_h, static_cast<int32_t>(j * kBwdBlk), static_cast<int32_t>(b), kEvictLast);
+          tma_load_3d(dst + kHalfTile, &tmap_v, fbar, col_h, static_cast<int32_t>(j * kBwdBlk), static_cast<int32_t>(b), kEvictLast);
+          if (++stage == 2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0 && !cta_dead) {
+        mbar_wait(smem_u32(&bars->fixed_full), 0);
+        tc_fence_after();
+        const uint64_t qdesc = smem_desc_sw128(smem_base + off_q);
+        const uint64_t dodesc = smem_desc_sw128(smem_base + off_do);
+        uint32_t ld_stage = 0, ld_phase = 0;
+        auto issue_sdp = [&](uint32_t n) {   // S = Q.K^T and dP = dO.V^T of the n-th live block
+          mbar_wait(smem_u32(&bars->ring_full[ld_stage]), ld_phase);
+          mbar_wait(smem_u32(&bars->sdp_empty), (n & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t kbase = smem_base + off_ring + ld_stage * 2 * kHalfTile;
+          const uint64_t kdesc = smem_desc_sw128(kbase), vdesc = smem_desc_sw128(kbase + kHalfTile);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_f16_ss(tmem_s, qdesc + static_cast<uint64_t>(kk * 2), kdesc + static_cast<uint64_t>(kk * 2),
+                       a.idesc_s, kk != 0 ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_f16_ss(tmem_dp, dodesc + static_cast<uint64_t>(kk * 2), vdesc + static_cast<uint64_t>(kk * 2),
+                       a.idesc_s, kk != 0 ? 1u : 0u);
+          mma_commit(smem_u32(&bars->sdp_full));
+          if (++ld_stage == 2) {
+            ld_stage = 0;
+            ld_phase ^= 1;
+          }
+        };
+        issue_sdp(0);
+        uint32_t stage = 0, n = 0;
+        for (uint32_t j = next_live(0); j < nblk; ++n) {
+          j = next_live(j + 1);
+          if (j < nblk) issue_sdp(n + 1);          // overlaps the row threads' work on block n
+          mbar_wait(smem_u32(&bars->pds_full), n & 1);
+          tc_fence_after();
+          const uint32_t kbase = smem_base + off_ring + stage * 2 * kHalfTile;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {   // dQ += dS . K   (A = dS K-major, B = K MN-major)
+            const uint64_t dsdesc = smem_desc_sw128(smem_base + off_ds) + static_cast<uint64_t>(ks * 2);
+            const uint64_t kmn = smem_desc_sw128_mn(kbase + ks * 2048, 1024, 1024);
+            mma_f16_ss(tmem_dq, dsdesc, kmn, a.idesc_o, (n != 0 || ks != 0) ? 1u : 0u);
+          }
+          mma_commit(smem_u32(&bars->ring_empty[stage]));
+          mma_commit(smem_u32(&bars->acc_done));
+          if (++stage == 2) stage = 0;
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && !cta_dead) {
-      mbar_wait(smem_u32(&bars->fixed_full), 0);
-      tc_fence_after();
-      const uint64_t qdesc = smem_desc_sw128(smem_base + off_q);
-      const uint64_t dodesc = smem_desc_sw128(smem_base + off_do);
-      uint32_t stage = 0, phase = 0, n = 0;
-      for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1), ++n) {
-        mbar_wait(smem_u32(&bars->ring_full[stage]), phase);
-        mbar_wait(smem_u32(&bars->sdp_empty), (n & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t kbase = smem_base + off_ring + stage * 2 * kTile;
-        const uint64_t kdesc = smem_desc_sw128(kbase), vdesc = smem_desc_sw128(kbase + kTile);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)   // S = Q . K^T
-          mma_f16_ss(tmem_s, qdesc + static_cast<uint64_t>(kk * 2), kdesc + static_cast<uint64_t>(kk * 2),
-                     a.idesc_s, kk != 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)   // dP = dO . V^T
-          mma_f16_ss(tmem_dp, dodesc + static_cast<uint64_t>(kk * 2), vdesc + static_cast<uint64_t>(kk * 2),
-                     a.idesc_s, kk != 0 ? 1u : 0u);
-        mma_commit(smem_u32(&bars->sdp_full));
-        mbar_wait(smem_u32(&bars->pds_full), n & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // dQ += dS . K   (A = dS K-major, B = K MN-major)
-          const uint64_t dsdesc = smem_desc_sw128(smem_base + off_ds + (ks >> 2) * kTile) +
-                                  static_cast<uint64_t>((ks & 3) * 2);
-          const uint64_t kmn = smem_desc_sw128_mn(kbase + ks * 2048, 1024, 1024);
-          mma_f16_ss(tmem_dq, dsdesc, kmn, a.idesc_o, (n != 0 || ks != 0) ? 1u : 0u);
-        }
-        mma_commit(smem_u32(&bars->ring_empty[stage]));
-        mma_commit(smem_u32(&bars->acc_done));
-        if (++stage == 2) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp >= 4) {
+  } else {
+    reg_alloc<216>();
     const uint32_t quad = warp & 3, row = quad * 32 + lane, qi = q0 + row;
     const uint32_t lane_tmem = (quad * 32) << 16;
     const bool row_active = qi < a.sq;
@@ -217,55 +245,55 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const size_t stat = (static_cast<size_t>(b) * a.heads + head) * a.sq + (row_active ? qi : 0);
       const float lse2 = a.lse[stat] * kLog2e;
       const float dsum = a.dvec[stat];
+      const bool row_dead = q_is_pad || !row_active;     // no gradient reaches any score of this row
       uint32_t n = 0;
       for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1), ++n) {
-        const uint32_t kb0 = j * kAttnBK;
-        uint32_t km[4];
+        const uint32_t kb0 = j * kBwdBlk;
+        uint32_t km[2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           const uint32_t idx = kb0 + c * 32 + lane;
           const bool f = a.k_pad && idx < a.sk && a.k_pad[static_cast<size_t>(b) * a.sk + idx] != 0;
           km[c] = __ballot_sync(kFull, f);
         }
-        const uint32_t valid = min(static_cast<uint32_t>(kAttnBK), a.sk - kb0);
+        const uint32_t valid = min(static_cast<uint32_t>(kBwdBlk), a.sk - kb0);
+        const bool plain = !row_dead && valid == kBwdBlk && (km[0] | km[1]) == 0u &&
+                           !(a.causal && kb0 + kBwdBlk - 1 > qi);
         mbar_wait(smem_u32(&bars->sdp_full), n & 1);
         tc_fence_after();
-        if (n > 0) {   // dS buffer is free once the previous dQ product has consumed it
-          mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t s[64], dp[64];
-          tmem_ld_32x32b_x32(tmem_s + lane_tmem + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-          tmem_ld_32x32b_x32(tmem_s + lane_tmem + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-          tmem_ld_32x32b_x32(tmem_dp + lane_tmem + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
-          tmem_ld_32x32b_x32(tmem_dp + lane_tmem + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float ds[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int c = g * 8 + i;
-              const uint32_t cc = half * 64 + c;
-              const bool masked = q_is_pad || ((km[cc >> 5] >> (cc & 31)) & 1u) || (a.causal && kb0 + cc > qi);
-              const float p = ex2(__uint_as_float(s[c]) * a.scale_log2 - lse2);
-              const float d = p * (__uint_as_float(dp[c]) - dsum) * a.scale;
-              ds[i] = (masked || cc >= valid || !row_active) ? 0.f : d;
-            }
-            const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
-            *reinterpret_cast<uint4*>(ds_row + half * kTile + phys) =
-                make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
-                           pack2<kBf16>(ds[6], ds[7]));
-          }
-        }
-        fence_proxy_async_smem();
+        uint32_t s[64], dp[64];
+        tmem_ld_32x32b_x32(tmem_s + lane_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_ld_32x32b_x32(tmem_s + lane_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+        tmem_ld_32x32b_x32(tmem_dp + lane_tmem, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
+        tmem_ld_32x32b_x32(tmem_dp + lane_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(smem_u32(&bars->sdp_empty));
-          mbar_arrive(smem_u32(&bars->pds_full));
+        if (lane == 0) mbar_arrive(smem_u32(&bars->sdp_empty));   // S/dP may be overwritten now
+        if (n > 0) mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);   // dS buffer consumed
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float ds[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = g * 8 + i;
+            const float p = ex2(fmaf(__uint_as_float(s[c]), a.scale_log2, -lse2));
+            float d = p * (__uint_as_float(dp[c]) - dsum) * a.scale;
+            if (!plain) {
+              const bool masked = row_dead || ((km[c >> 5] >> (c & 31)) & 1u) || (a.causal && kb0 + c > qi) ||
+                                  static_cast<uint32_t>(c) >= valid;
+              d = masked ? 0.f : d;
+            }
+            ds[i] = d;
+          }
+          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+          *reinterpret_cast<uint4*>(ds_row + phys) =
+              make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
+                         pack2<kBf16>(ds[6], ds[7]));
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->pds_full));
       }
       mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
       tc_fence_after();
@@ -296,32 +324,34 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
 // ============================================================================ dK, dV
-// smem: K 16K | V 16K | ring 2 x (Q 16K + dO 16K) | P^T 32K | dS^T 32K | stats 2 x 1K | bars
-constexpr int kDkvSmem = 2 * kTile + 2 * 2 * kTile + 2 * kTile + 2 * kTile + 2048 + 256;
+// smem: K 16K | V 16K | ring 2 x (Q 8K + dO 8K) | P^T 16K | dS^T 16K | stats 2 x 512 B | bars
+// TMEM: S^T [0,64) dP^T [64,128) dV [128,192) dK [192,256)
+constexpr int kDkvSmem = 2 * kTile + 2 * 2 * kHalfTile + 2 * kTile + 1024 + 256;
 
 template <bool kBf16>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                          const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
                          const AttnBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr uint32_t off_k = 0, off_v = kTile, off_ring = 2 * kTile, off_p = off_ring + 4 * kTile,
-                     off_ds = off_p + 2 * kTile, off_stat = off_ds + 2 * kTile, off_bar = off_stat + 2048;
+  constexpr uint32_t off_k = 0, off_v = kTile, off_ring = 2 * kTile, off_p = off_ring + 4 * kHalfTile,
+                     off_ds = off_p + kTile, off_stat = off_ds + kTile, off_bar = off_stat + 1024;
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + off_bar);
-  float* stat_smem = reinterpret_cast<float*>(smem + off_stat);   // [2][128] x {lse*log2e, D}
+  float* stat_smem = reinterpret_cast<float*>(smem + off_stat);   // [2][64] x {lse*log2e, D}
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t k0 = blockIdx.x * kAttnBK, head = blockIdx.y, b = blockIdx.z;
-  const uint32_t nqblk = (a.sq + kAttnBQ - 1) / kAttnBQ;
+  const uint32_t nqblk = (a.sq + kBwdBlk - 1) / kBwdBlk;       // 64-query steps
+  const uint32_t nlive = (a.sq + kAttnBQ - 1) / kAttnBQ;
   const int32_t col_h = static_cast<int32_t>(head * kAttnHeadDim);
-  const uint8_t* q_live = a.q_live ? a.q_live + static_cast<size_t>(b) * nqblk : nullptr;
+  const uint8_t* q_live = a.q_live ? a.q_live + static_cast<size_t>(b) * nlive : nullptr;
   auto next_live = [&](uint32_t i) {
-    while (i < nqblk && q_live && q_live[i] == 0) ++i;
+    while (i < nqblk && q_live && q_live[i >> 1] == 0) ++i;
     return i;
   };
   const bool cta_dead = a.k_live && a.k_live[static_cast<size_t>(b) * gridDim.x + blockIdx.x] == 0;
@@ -340,79 +370,91 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     fence_proxy_async_smem();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_alloc(smem_u32(&bars->tmem_base), 256);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 64, tmem_dv = tmem_base + 128, tmem_dk = tmem_base + 192;
 
-  if (warp == 0) {
-    if (lane == 0 && !cta_dead) {
-      const uint32_t fb = smem_u32(&bars->fixed_full);
-      mbar_arrive_expect_tx(fb, 2 * kTile);
-      tma_load_3d(smem_base + off_k, &tmap_k, fb, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b), kEvictNormal);
-      tma_load_3d(smem_base + off_v, &tmap_v, fb, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b), kEvictNormal);
-      uint32_t stage = 0, phase = 0;
-      for (uint32_t i = next_live(0); i < nqblk; i = next_live(i + 1)) {
-        mbar_wait(smem_u32(&bars->ring_empty[stage]), phase ^ 1);
-        const uint32_t fbar = smem_u32(&bars->ring_full[stage]);
-        mbar_arrive_expect_tx(fbar, 2 * kTile);
-        const uint32_t dst = smem_base + off_ring + stage * 2 * kTile;
-        tma_load_3d(dst, &tmap_q, fbar, col_h, static_cast<int32_t>(i * kAttnBQ), static_cast<int32_t>(b), kEvictLast);
-        tma_load_3d(dst + kTile, &tmap_do, fbar, col_h, static_cast<int32_t>(i * kAttnBQ), static_cast<int32_t>(b), kEvictLast);
-        if (++stage == 2) {
-          stage = 0;
-          phase ^= 1;
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0) {
+      if (lane == 0 && !cta_dead) {
+        const uint32_t fb = smem_u32(&bars->fixed_full);
+        mbar_arrive_expect_tx(fb, 2 * kTile);
+        tma_load_3d(smem_base + off_k, &tmap_k, fb, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b), kEvictNormal);
+        tma_load_3d(smem_base + off_v, &tmap_v, fb, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b), kEvictNormal);
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t i = next_live(0); i < nqblk; i = next_live(i + 1)) {
+          mbar_wait(smem_u32(&bars->ring_empty[stage]), phase ^ 1);
+          const uint32_t fbar = smem_u32(&bars->ring_full[stage]);
+          mbar_arrive_expect_tx(fbar, 2 * kHalfTile);
+          const uint32_t dst = smem_base + off_ring + stage * 2 * kHalfTile;
+          tma_load_3d(dst, &tmap_q, fbar, col_h, static_cast<int32_t>(i * kBwdBlk), static_cast<int32_t>(b), kEvictLast);
+          tma_load_3d(dst + kHalfTile, &tmap_do, fbar, col_h, static_cast<int32_t>(i * kBwdBlk), static_cast<int32_t>(b), kEvictLast);
+          if (++stage == 2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0 && !cta_dead) {
+        mbar_wait(smem_u32(&bars->fixed_full), 0);
+        tc_fence_after();
+        const uint64_t kdesc = smem_desc_sw128(smem_base + off_k);
+        const uint64_t vdesc = smem_desc_sw128(smem_base + off_v);
+        uint32_t ld_stage = 0, ld_phase = 0;
+        auto issue_sdp = [&](uint32_t n) {   // S^T = K.Q^T and dP^T = V.dO^T  [keys x queries]
+          mbar_wait(smem_u32(&bars->ring_full[ld_stage]), ld_phase);
+          mbar_wait(smem_u32(&bars->sdp_empty), (n & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t qbase = smem_base + off_ring + ld_stage * 2 * kHalfTile;
+          const uint64_t qdesc = smem_desc_sw128(qbase), dodesc = smem_desc_sw128(qbase + kHalfTile);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_f16_ss(tmem_s, kdesc + static_cast<uint64_t>(kk * 2), qdesc + static_cast<uint64_t>(kk * 2),
+                       a.idesc_s, kk != 0 ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_f16_ss(tmem_dp, vdesc + static_cast<uint64_t>(kk * 2), dodesc + static_cast<uint64_t>(kk * 2),
+                       a.idesc_s, kk != 0 ? 1u : 0u);
+          mma_commit(smem_u32(&bars->sdp_full));
+          if (++ld_stage == 2) {
+            ld_stage = 0;
+            ld_phase ^= 1;
+          }
+        };
+        issue_sdp(0);
+        uint32_t stage = 0, n = 0;
+        for (uint32_t i = next_live(0); i < nqblk; ++n) {
+          i = next_live(i + 1);
+          if (i < nqblk) issue_sdp(n + 1);
+          mbar_wait(smem_u32(&bars->pds_full), n & 1);
+          tc_fence_after();
+          const uint32_t qbase = smem_base + off_ring + stage * 2 * kHalfTile;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t koff = static_cast<uint64_t>(ks * 2);
+            const uint64_t pdesc = smem_desc_sw128(smem_base + off_p) + koff;
+            const uint64_t dsdesc = smem_desc_sw128(smem_base + off_ds) + koff;
+            const uint64_t domn = smem_desc_sw128_mn(qbase + kHalfTile + ks * 2048, 1024, 1024);
+            const uint64_t qmn = smem_desc_sw128_mn(qbase + ks * 2048, 1024, 1024);
+            const uint32_t acc = (n != 0 || ks != 0) ? 1u : 0u;
+            mma_f16_ss(tmem_dv, pdesc, domn, a.idesc_o, acc);    // dV += P^T . dO
+            mma_f16_ss(tmem_dk, dsdesc, qmn, a.idesc_o, acc);    // dK += dS^T . Q
+          }
+          mma_commit(smem_u32(&bars->ring_empty[stage]));
+          mma_commit(smem_u32(&bars->acc_done));
+          if (++stage == 2) stage = 0;
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && !cta_dead) {
-      mbar_wait(smem_u32(&bars->fixed_full), 0);
-      tc_fence_after();
-      const uint64_t kdesc = smem_desc_sw128(smem_base + off_k);
-      const uint64_t vdesc = smem_desc_sw128(smem_base + off_v);
-      uint32_t stage = 0, phase = 0, n = 0;
-      for (uint32_t i = next_live(0); i < nqblk; i = next_live(i + 1), ++n) {
-        mbar_wait(smem_u32(&bars->ring_full[stage]), phase);
-        mbar_wait(smem_u32(&bars->sdp_empty), (n & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t qbase = smem_base + off_ring + stage * 2 * kTile;
-        const uint64_t qdesc = smem_desc_sw128(qbase), dodesc = smem_desc_sw128(qbase + kTile);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)   // S^T = K . Q^T   [keys x queries]
-          mma_f16_ss(tmem_s, kdesc + static_cast<uint64_t>(kk * 2), qdesc + static_cast<uint64_t>(kk * 2),
-                     a.idesc_s, kk != 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)   // dP^T = V . dO^T
-          mma_f16_ss(tmem_dp, vdesc + static_cast<uint64_t>(kk * 2), dodesc + static_cast<uint64_t>(kk * 2),
-                     a.idesc_s, kk != 0 ? 1u : 0u);
-        mma_commit(smem_u32(&bars->sdp_full));
-        mbar_wait(smem_u32(&bars->pds_full), n & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t koff = static_cast<uint64_t>((ks & 3) * 2);
-          const uint64_t pdesc = smem_desc_sw128(smem_base + off_p + (ks >> 2) * kTile) + koff;
-          const uint64_t dsdesc = smem_desc_sw128(smem_base + off_ds + (ks >> 2) * kTile) + koff;
-          const uint64_t domn = smem_desc_sw128_mn(qbase + kTile + ks * 2048, 1024, 1024);
-          const uint64_t qmn = smem_desc_sw128_mn(qbase + ks * 2048, 1024, 1024);
-          const uint32_t acc = (n != 0 || ks != 0) ? 1u : 0u;
-          mma_f16_ss(tmem_dv, pdesc, domn, a.idesc_o, acc);    // dV += P^T . dO
-          mma_f16_ss(tmem_dk, dsdesc, qmn, a.idesc_o, acc);    // dK += dS^T . Q
-        }
-        mma_commit(smem_u32(&bars->ring_empty[stage]));
-        mma_commit(smem_u32(&bars->acc_done));
-        if (++stage == 2) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp >= 4) {
+  } else {
+    reg_alloc<216>();
     const uint32_t quad = warp & 3, row = quad * 32 + lane, kj = k0 + row;   // row == key
     const uint32_t lane_tmem = (quad * 32) << 16;
     const bool row_active = kj < a.sk;
@@ -429,73 +471,73 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       const bool k_is_pad = row_active && a.k_pad && a.k_pad[static_cast<size_t>(b) * a.sk + kj] != 0;
       uint32_t n = 0;
       for (uint32_t i = next_live(0); i < nqblk; i = next_live(i + 1), ++n) {
-        const uint32_t qb0 = i * kAttnBQ;
-        // per-query statistics of this block -> shared memory (thread `row` loads query qb0 + row)
-        float* st = stat_smem + (n & 1) * 256;
-        {
+        const uint32_t qb0 = i * kBwdBlk;
+        // per-query statistics of this block -> shared memory (threads 0..63 load query qb0 + row)
+        float* st = stat_smem + (n & 1) * 128;
+        if (row < kBwdBlk) {
           const uint32_t qi = qb0 + row;
           const size_t sidx = (static_cast<size_t>(b) * a.heads + head) * a.sq + (qi < a.sq ? qi : 0);
           st[row] = a.lse[sidx] * kLog2e;
-          st[128 + row] = a.dvec[sidx];
+          st[64 + row] = a.dvec[sidx];
         }
-        uint32_t qm[4];
+        uint32_t qm[2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           const uint32_t idx = qb0 + c * 32 + lane;
           const bool f = a.q_pad && idx < a.sq && a.q_pad[static_cast<size_t>(b) * a.sq + idx] != 0;
           qm[c] = __ballot_sync(kFull, f);
         }
-        const uint32_t valid = min(static_cast<uint32_t>(kAttnBQ), a.sq - qb0);
+        const uint32_t valid = min(static_cast<uint32_t>(kBwdBlk), a.sq - qb0);
+        const bool plain = row_active && !k_is_pad && valid == kBwdBlk && (qm[0] | qm[1]) == 0u &&
+                           !(a.causal && kj > qb0);
         asm volatile("bar.sync 2, 128;" ::: "memory");   // statistics visible to all row threads
         mbar_wait(smem_u32(&bars->sdp_full), n & 1);
         tc_fence_after();
-        if (n > 0) mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t s[64], dp[64];
-          tmem_ld_32x32b_x32(tmem_s + lane_tmem + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-          tmem_ld_32x32b_x32(tmem_s + lane_tmem + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-          tmem_ld_32x32b_x32(tmem_dp + lane_tmem + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
-          tmem_ld_32x32b_x32(tmem_dp + lane_tmem + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float pv[8], ds[8];
-            const float4 l0 = *reinterpret_cast<const float4*>(st + half * 64 + g * 8);
-            const float4 l1 = *reinterpret_cast<const float4*>(st + half * 64 + g * 8 + 4);
-            const float4 d0 = *reinterpret_cast<const float4*>(st + 128 + half * 64 + g * 8);
-            const float4 d1 = *reinterpret_cast<const float4*>(st + 128 + half * 64 + g * 8 + 4);
-            const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-            const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) {
-              const int c = g * 8 + i2;
-              const uint32_t cc = half * 64 + c;   // query column inside the block
-              const bool masked = k_is_pad || ((qm[cc >> 5] >> (cc & 31)) & 1u) || (a.causal && kj > qb0 + cc);
-              float t = __uint_as_float(s[c]) * a.scale_log2;
-              t = masked ? kMaskedLog2 : t;
-              float p = ex2(t - lv[i2]);
-              p = (cc < valid && row_active) ? p : 0.f;
-              const float d = p * (__uint_as_float(dp[c]) - dv[i2]) * a.scale;
-              pv[i2] = p;
-              ds[i2] = masked ? 0.f : d;
-            }
-            const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
-            *reinterpret_cast<uint4*>(p_row + half * kTile + phys) =
-                make_uint4(pack2<kBf16>(pv[0], pv[1]), pack2<kBf16>(pv[2], pv[3]), pack2<kBf16>(pv[4], pv[5]),
-                           pack2<kBf16>(pv[6], pv[7]));
-            *reinterpret_cast<uint4*>(ds_row + half * kTile + phys) =
-                make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
-                           pack2<kBf16>(ds[6], ds[7]));
-          }
-        }
-        fence_proxy_async_smem();
+        uint32_t s[64], dp[64];
+        tmem_ld_32x32b_x32(tmem_s + lane_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_ld_32x32b_x32(tmem_s + lane_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+        tmem_ld_32x32b_x32(tmem_dp + lane_tmem, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
+        tmem_ld_32x32b_x32(tmem_dp + lane_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(smem_u32(&bars->sdp_empty));
-          mbar_arrive(smem_u32(&bars->pds_full));
+        if (lane == 0) mbar_arrive(smem_u32(&bars->sdp_empty));
+        if (n > 0) mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float pv[8], ds[8];
+          const float4 l0 = *reinterpret_cast<const float4*>(st + g * 8);
+          const float4 l1 = *reinterpret_cast<const float4*>(st + g * 8 + 4);
+          const float4 d0 = *reinterpret_cast<const float4*>(st + 64 + g * 8);
+          const float4 d1 = *reinterpret_cast<const float4*>(st + 64 + g * 8 + 4);
+          const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+          for (int i2 = 0; i2 < 8; ++i2) {
+            const int c = g * 8 + i2;   // query column inside the block
+            float t = __uint_as_float(s[c]) * a.scale_log2;
+            bool masked = false;
+            if (!plain) {
+              masked = k_is_pad || ((qm[c >> 5] >> (c & 31)) & 1u) || (a.causal && kj > qb0 + c);
+              t = masked ? kMaskedLog2 : t;
+            }
+            float p = ex2(t - lv[i2]);
+            if (!plain) p = (static_cast<uint32_t>(c) < valid && row_active) ? p : 0.f;
+            const float d = p * (__uint_as_float(dp[c]) - dv[i2]) * a.scale;
+            pv[i2] = p;
+            ds[i2] = masked ? 0.f : d;
+          }
+          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+          *reinterpret_cast<uint4*>(p_row + phys) =
+              make_uint4(pack2<kBf16>(pv[0], pv[1]), pack2<kBf16>(pv[2], pv[3]), pack2<kBf16>(pv[4], pv[5]),
+                         pack2<kBf16>(pv[6], pv[7]));
+          *reinterpret_cast<uint4*>(ds_row + phys) =
+              make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
+                         pack2<kBf16>(ds[6], ds[7]));
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->pds_full));
       }
       mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
       tc_fence_after();
@@ -531,7 +573,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace
@@ -565,17 +607,17 @@ cudaError_t launch_attention_bwd_prep(bool bf16, const void* dout, int64_t lddo,
   return cudaGetLastError();
 }
 
-cudaError_t launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                                 const CUtensorMap& tdo, const CUtensorMap& tdq, const CUtensorMap& tdk,
-                                 const CUtensorMap& tdv, const AttnBwdArgs& a, bool bf16, cudaStream_t stream) {
+cudaError_t launch_attention_bwd(const AttnBwdMaps& m, const AttnBwdArgs& a, bool bf16, cudaStream_t stream) {
   dim3 gq((a.sq + kAttnBQ - 1) / kAttnBQ, a.heads, a.batch);
   dim3 gk((a.sk + kAttnBK - 1) / kAttnBK, a.heads, a.batch);
   if (bf16) {
-    attention_bwd_dq_kernel<true><<<gq, kAttnThreads, kDqSmem, stream>>>(tq, tk, tv, tdo, tdq, a);
-    attention_bwd_dkv_kernel<true><<<gk, kAttnThreads, kDkvSmem, stream>>>(tq, tk, tv, tdo, tdk, tdv, a);
+    attention_bwd_dq_kernel<true><<<gq, kAttnThreads, kDqSmem, stream>>>(m.q128, m.k64, m.v64, m.do128, m.dq128, a);
+    attention_bwd_dkv_kernel<true><<<gk, kAttnThreads, kDkvSmem, stream>>>(m.q64, m.k128, m.v128, m.do64, m.dk128,
+                                                                          m.dv128, a);
   } else {
-    attention_bwd_dq_kernel<false><<<gq, kAttnThreads, kDqSmem, stream>>>(tq, tk, tv, tdo, tdq, a);
-    attention_bwd_dkv_kernel<false><<<gk, kAttnThreads, kDkvSmem, stream>>>(tq, tk, tv, tdo, tdk, tdv, a);
+    attention_bwd_dq_kernel<false><<<gq, kAttnThreads, kDqSmem, stream>>>(m.q128, m.k64, m.v64, m.do128, m.dq128, a);
+    attention_bwd_dkv_kernel<false><<<gk, kAttnThreads, kDkvSmem, stream>>>(m.q64, m.k128, m.v128, m.do64, m.dk128,
+                                                                           m.dv128, a);
   }
   return cudaGetLastError();
 }

@@ -2,6 +2,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/emdr2_b200.h"
@@ -30,20 +32,24 @@ int require_b200(DeviceInfo* info) {
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- optional per-kernel-kind launch timing (emdr2_ops_timing): CUDA event pairs recorded on the
-// caller's stream around every launch of a kind, summed on request.  Host-thread local.
+// caller's stream around every launch of a kind, summed on request.  Process-wide (backward passes
+// run on PyTorch's autograd worker threads), guarded by a mutex; off by default.
 struct KindTimer {
   std::vector<cudaEvent_t> ev;
   size_t used = 0;
   double flops = 0.0;   // algorithmic work of the timed launches (GEMM: 2mnk; attention: 4 b h sq sk d)
 };
-thread_local bool g_timing = false;
-thread_local KindTimer g_timers[EMDR2_KIND_COUNT];
+std::atomic<bool> g_timing{false};
+std::mutex g_timer_mutex;
+KindTimer g_timers[EMDR2_KIND_COUNT];
 
 struct ScopedTimer {
   KindTimer* t = nullptr;
   cudaStream_t stream;
   ScopedTimer(int kind, cudaStream_t s, double flops) : stream(s) {
-    if (!g_timing) return;
+    if (!g_timing.load(std::memory_order_relaxed)) return;
+    g_timer_mutex.lock();
+    locked = true;
     t = &g_timers[kind];
     if (t->used + 2 > t->ev.size()) {
       cudaEvent_t e0, e1;
@@ -58,10 +64,13 @@ struct ScopedTimer {
     cudaEventRecord(t->ev[t->used], stream);
   }
   ~ScopedTimer() {
-    if (!t) return;
-    cudaEventRecord(t->ev[t->used + 1], stream);
-    t->used += 2;
+    if (t) {
+      cudaEventRecord(t->ev[t->used + 1], stream);
+      t->used += 2;
+    }
+    if (locked) g_timer_mutex.unlock();
   }
+  bool locked = false;
 };
 
 }  // namespace
@@ -278,6 +287,7 @@ int emdr2_token_logprob(int dtype, const void* logits, int64_t ld, const int64_t
 }
 
 int emdr2_ops_timing(int enable) {
+  std::lock_guard<std::mutex> guard(g_timer_mutex);
   g_timing = enable != 0;
   for (int k = 0; k < EMDR2_KIND_COUNT; ++k) {
     g_timers[k].used = 0;
@@ -288,6 +298,7 @@ int emdr2_ops_timing(int enable) {
 
 int emdr2_ops_timing_read(int kind, int64_t* out_ns, int64_t* out_launches, double* out_flops) {
   if (kind < 0 || kind >= EMDR2_KIND_COUNT) return fail(EMDR2_EINVAL, "unknown kernel kind %d", kind);
+  std::lock_guard<std::mutex> guard(g_timer_mutex);
   KindTimer& t = g_timers[kind];
   double total_ms = 0.0;
   for (size_t i = 0; i + 1 < t.used; i += 2) {
@@ -337,14 +348,14 @@ int emdr2_attention_bwd(int dtype, const void* q, int64_t ldq, const void* k, in
   ScopedTimer timer(EMDR2_KIND_ATTENTION, stream,
                     14.0 * batch * heads * sq * static_cast<double>(sk) * emdr2::kAttnHeadDim);
   CUDA_TRY(emdr2::launch_attention_bwd_prep(bf16, dout, lddo, o, ldo, dvec_ws, batch, heads, sq, stream));
-  CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
-  if ((rc = make_tmap_3d(&tq, dtype, q, batch, sq, width, ldq, 128)) != EMDR2_OK) return rc;
-  if ((rc = make_tmap_3d(&tk, dtype, k, batch, sk, width, ldk, 128)) != EMDR2_OK) return rc;
-  if ((rc = make_tmap_3d(&tv, dtype, v, batch, sk, width, ldv, 128)) != EMDR2_OK) return rc;
-  if ((rc = make_tmap_3d(&tdo, dtype, dout, batch, sq, width, lddo, 128)) != EMDR2_OK) return rc;
-  if ((rc = make_tmap_3d(&tdq, dtype, dq, batch, sq, width, lddq, 128)) != EMDR2_OK) return rc;
-  if ((rc = make_tmap_3d(&tdk, dtype, dk, batch, sk, width, lddk, 128)) != EMDR2_OK) return rc;
-  if ((rc = make_tmap_3d(&tdv, dtype, dv, batch, sk, width, lddv, 128)) != EMDR2_OK) return rc;
+  emdr2::AttnBwdMaps mp;
+  struct { CUtensorMap* m; const void* p; int rows; int64_t ld; uint32_t box; } specs[] = {
+      {&mp.q128, q, sq, ldq, 128}, {&mp.do128, dout, sq, lddo, 128}, {&mp.dq128, dq, sq, lddq, 128},
+      {&mp.k64, k, sk, ldk, 64},   {&mp.v64, v, sk, ldv, 64},        {&mp.k128, k, sk, ldk, 128},
+      {&mp.v128, v, sk, ldv, 128}, {&mp.dk128, dk, sk, lddk, 128},   {&mp.dv128, dv, sk, lddv, 128},
+      {&mp.q64, q, sq, ldq, 64},   {&mp.do64, dout, sq, lddo, 64}};
+  for (auto& sp : specs)
+    if ((rc = make_tmap_3d(sp.m, dtype, sp.p, batch, sp.rows, width, sp.ld, sp.box)) != EMDR2_OK) return rc;
   emdr2::AttnBwdArgs aa;
   aa.batch = batch;
   aa.heads = heads;
@@ -352,7 +363,7 @@ int emdr2_attention_bwd(int dtype, const void* q, int64_t ldq, const void* k, in
   aa.sk = sk;
   aa.causal = causal ? 1u : 0u;
   const int fmt = bf16 ? 1 : 0;
-  aa.idesc_s = emdr2::ptx::instr_desc_f16(fmt, 128, 128);
+  aa.idesc_s = emdr2::ptx::instr_desc_f16(fmt, 128, 64);
   aa.idesc_o = emdr2::ptx::instr_desc_f16(fmt, 128, emdr2::kAttnHeadDim, 0, 1);
   aa.scale = scale;
   aa.scale_log2 = scale * 1.4426950408889634f;
@@ -362,7 +373,7 @@ int emdr2_attention_bwd(int dtype, const void* q, int64_t ldq, const void* k, in
   aa.k_live = k_live;
   aa.lse = lse;
   aa.dvec = dvec_ws;
-  CUDA_TRY(emdr2::launch_attention_bwd(tq, tk, tv, tdo, tdq, tdk, tdv, aa, bf16, stream));
+  CUDA_TRY(emdr2::launch_attention_bwd(mp, aa, bf16, stream));
   return EMDR2_OK;
 }
 

@@ -128,21 +128,50 @@ layernorm_bwd_kernel(const uint16_t* __restrict__ dy, int64_t ldy, const uint16_
   }
 }
 
-// out[n] += sum_m dy[m, n]   (bias gradient)
+// out[n] += sum_m dy[m, n]   (bias gradient).  Block = 32 column groups (8 columns = 16 B each) x 8
+// row lanes; every thread keeps 4 independent 16-byte loads in flight, the 8 row lanes are folded
+// through shared memory and each block issues one atomic per column.
 template <bool kBf16>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 colsum_kernel(const uint16_t* __restrict__ dy, int64_t ld, float* __restrict__ out, int rows, int n) {
-  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
-  if (col >= n) return;
+  __shared__ float s_part[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-    float f[8];
-    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * ld + col)), f);
+  if (col < n) {
+    const int stride = gridDim.y * 8;
+    int r = blockIdx.y * 8 + ty;
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+      uint4 v[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      for (int u = 0; u < 4; ++u)
+        v[u] = __ldg(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r + u * stride) * ld + col));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8<kBf16>(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+    }
+    for (; r < rows; r += stride) {
+      float f[8];
+      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * ld + col)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) atomicAdd(out + col + i, acc[i]);
+  for (int i = 0; i < 8; ++i) s_part[ty][tx * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;           // 256 threads -> 256 columns of this block
+  const int gc = blockIdx.x * 256 + c;
+  if (gc < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_part[w][c];
+    atomicAdd(out + gc, t);
+  }
 }
 
 // dlogits[r, v] = g[r] * (1[v == label_r] - exp(logits[r, v] - lse[r])): backward of token_logprob.
@@ -169,27 +198,68 @@ token_logprob_bwd_kernel(const uint16_t* __restrict__ logits, int64_t ld, const 
   }
 }
 
-// dword[ids[t]] += dx[t], dpos[t % seq] += dx[t], dtype[types[t]] += dx[t]  (fp32 atomics)
+// dword[ids[t]] += dx[t]  (scattered fp32 atomics: rows of different tokens rarely collide)
 template <bool kBf16>
 __global__ void __launch_bounds__(256)
-embedding_bwd_kernel(const uint16_t* __restrict__ dx, const int64_t* __restrict__ ids,
-                     const int64_t* __restrict__ types, float* __restrict__ dword, float* __restrict__ dpos,
-                     float* __restrict__ dtype_emb, int tokens, int seq, int h, int vocab, int num_types) {
+embedding_bwd_word_kernel(const uint16_t* __restrict__ dx, const int64_t* __restrict__ ids,
+                          float* __restrict__ dword, int tokens, int h, int vocab) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (t >= tokens) return;
   int64_t id = ids[t];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-  int64_t ty = (types && dtype_emb) ? types[t] : 0;
-  ty = ty < 0 ? 0 : (ty >= num_types ? num_types - 1 : ty);
   for (int col = lane * 8; col < h; col += 256) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dx + static_cast<size_t>(t) * h + col));
+    if ((raw.x | raw.y | raw.z | raw.w) == 0u) continue;     // padding positions carry exact zeros
     float f[8];
-    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dx + static_cast<size_t>(t) * h + col)), f);
+    unpack8<kBf16>(raw, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (dword) atomicAdd(dword + static_cast<size_t>(id) * h + col + i, f[i]);
-      if (dpos) atomicAdd(dpos + static_cast<size_t>(t % seq) * h + col + i, f[i]);
-      if (types && dtype_emb) atomicAdd(dtype_emb + static_cast<size_t>(ty) * h + col + i, f[i]);
+    for (int i = 0; i < 8; ++i) atomicAdd(dword + static_cast<size_t>(id) * h + col + i, f[i]);
+  }
+}
+
+// dpos[p] += sum_b dx[b * seq + p];  dtype_emb[ty] += sum over tokens of that type.  One thread per
+// (position, 8 columns) walks the batch, so the hot rows (a position is shared by every sequence,
+// a token type by half of all tokens) see one atomic per thread instead of one per token.
+template <bool kBf16>
+__global__ void __launch_bounds__(128)
+embedding_bwd_pos_kernel(const uint16_t* __restrict__ dx, const int64_t* __restrict__ types,
+                         float* __restrict__ dpos, float* __restrict__ dtype_emb, int tokens, int seq, int h,
+                         int num_types) {
+  const int pos = blockIdx.x;
+  const int col = (blockIdx.y * 128 + threadIdx.x) * 8;
+  if (col >= h) return;
+  const int batch = tokens / seq;
+  float acc[4][8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  for (int b = 0; b < batch; ++b) {
+    const size_t tok = static_cast<size_t>(b) * seq + pos;
+    float f[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dx + tok * h + col)), f);
+    int ty = 0;
+    if (types && dtype_emb) {
+      const int64_t raw = types[tok];
+      ty = raw < 0 ? 0 : (raw >= num_types ? num_types - 1 : static_cast<int>(raw));
+      ty = ty > 3 ? 3 : ty;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (t == ty) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[t][i] += f[i];
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float total = acc[0][i] + acc[1][i] + acc[2][i] + acc[3][i];
+    if (dpos) atomicAdd(dpos + static_cast<size_t>(pos) * h + col + i, total);
+    if (types && dtype_emb) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (t < num_types && acc[t][i] != 0.f) atomicAdd(dtype_emb + static_cast<size_t>(t) * h + col + i, acc[t][i]);
     }
   }
 }
@@ -218,9 +288,14 @@ cudaError_t launch_colsum(bool bf16, const void* dy, int64_t ld, float* out, int
                           cudaStream_t stream) {
   if (rows <= 0 || n <= 0) return cudaSuccess;
   if (n % 8) return cudaErrorInvalidValue;
-  dim3 grid((n / 8 + 127) / 128, rows < 256 ? rows : 256);
-  if (bf16) colsum_kernel<true><<<grid, 128, 0, stream>>>(static_cast<const uint16_t*>(dy), ld, out, rows, n);
-  else colsum_kernel<false><<<grid, 128, 0, stream>>>(static_cast<const uint16_t*>(dy), ld, out, rows, n);
+  const int gx = (n + 255) / 256;
+  int gy = (rows + 63) / 64;                      // >= 8 rows per row lane
+  const int want = (148 * 8 + gx - 1) / gx;       // ~8 blocks per SM over the whole grid
+  if (gy > want) gy = want;
+  if (gy < 1) gy = 1;
+  dim3 grid(gx, gy);
+  if (bf16) colsum_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(dy), ld, out, rows, n);
+  else colsum_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(dy), ld, out, rows, n);
   return cudaGetLastError();
 }
 
@@ -242,14 +317,20 @@ cudaError_t launch_embedding_bwd(bool bf16, const void* dx, const int64_t* ids, 
                                  float* dword, float* dpos, float* dtype_emb, int tokens, int seq, int h,
                                  int vocab, int num_types, cudaStream_t stream) {
   if (tokens <= 0) return cudaSuccess;
-  if (h % 8) return cudaErrorInvalidValue;
-  const int grid = (tokens + 7) / 8;
-  if (bf16)
-    embedding_bwd_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(dx), ids, types, dword, dpos,
-                                                         dtype_emb, tokens, seq, h, vocab, num_types);
-  else
-    embedding_bwd_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(dx), ids, types, dword, dpos,
-                                                          dtype_emb, tokens, seq, h, vocab, num_types);
+  if (h % 8 || tokens % seq || num_types > 4) return cudaErrorInvalidValue;
+  auto d = static_cast<const uint16_t*>(dx);
+  if (dword) {
+    const int grid = (tokens + 7) / 8;
+    if (bf16) embedding_bwd_word_kernel<true><<<grid, 256, 0, stream>>>(d, ids, dword, tokens, h, vocab);
+    else embedding_bwd_word_kernel<false><<<grid, 256, 0, stream>>>(d, ids, dword, tokens, h, vocab);
+  }
+  if (dpos || (types && dtype_emb)) {
+    dim3 grid(seq, (h / 8 + 127) / 128);
+    if (bf16)
+      embedding_bwd_pos_kernel<true><<<grid, 128, 0, stream>>>(d, types, dpos, dtype_emb, tokens, seq, h, num_types);
+    else
+      embedding_bwd_pos_kernel<false><<<grid, 128, 0, stream>>>(d, types, dpos, dtype_emb, tokens, seq, h, num_types);
+  }
   return cudaGetLastError();
 }
 

@@ -222,8 +222,8 @@ EMDR2_API int emdr2_embedding_bwd(int dtype, const void* dx, const int64_t* ids,
                                   float* dword, float* dpos, float* dtype_emb, int tokens, int seq, int h,
                                   int vocab, int num_types, void* cuda_stream);
 
-/* Measurement aid: with timing enabled every launch of the block operators made by the calling
- * thread is bracketed by CUDA events on its stream.  emdr2_ops_timing_read sums the launch
+/* Measurement aid: with timing enabled every launch of the block operators made by this
+ * process is bracketed by CUDA events on its stream (backward passes run on autograd worker threads).  emdr2_ops_timing_read sums the launch
  * durations (ns), launch count and algorithmic FLOPs of one kernel kind since the last read and
  * restarts the accumulation (blocks until the last timed launch has finished). */
 #define EMDR2_KIND_GEMM 0
