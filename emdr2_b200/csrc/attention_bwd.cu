@@ -95,6 +95,7 @@ struct BwdBars {
   uint32_t tmem_base;
 };
 
+constexpr int kBwdThreads = 384;          // warps 0-3: TMA / MMA / TMEM allocator / spare; warps 4-11: row threads
 constexpr int kBwdBlk = 64;               // streamed keys (dQ kernel) / queries (dK,dV kernel) per step
 constexpr int kHalfTile = kBwdBlk * 64 * 2;   // 64 x 64 x 2 B = 8 KiB
 
@@ -108,15 +109,18 @@ __device__ __forceinline__ void reg_alloc() {
 }
 
 // Both kernels: 256 TMEM columns and < 113 KiB of shared memory per CTA so that two CTAs share an SM
-// (the second hides the first one's TMA -> MMA -> row-thread -> MMA latency chain), registers moved
-// from the TMA/MMA warps to the four row warps with setmaxnreg, streamed operand blocks of 64 rows.
+// (the second hides the first one's TMA -> MMA -> row-thread -> MMA latency chain), streamed operand
+// blocks of 64 rows, and EIGHT row warps: two threads per row, each owning 32 of the 64 streamed
+// columns (the backward needs no row reductions — L and D are known — so the split is free), which
+// doubles the warps available to hide MUFU / TMEM-load latency.  setmaxnreg moves registers from the
+// TMA/MMA warpgroup to the two row warpgroups.
 
 // ============================================================================ dQ
 // smem: Q 16K | dO 16K | ring 2 x (K 8K + V 8K) | dS 16K | bars.   TMEM: S [0,64) dP [64,128) dQ [128,192)
 constexpr int kDqSmem = 2 * kTile + 2 * 2 * kHalfTile + kTile + 256;
 
 template <bool kBf16>
-__global__ void __launch_bounds__(kAttnThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                         const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdArgs a) {
@@ -144,8 +148,8 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       mbar_init(smem_u32(&bars->ring_empty[s]), 1);
     }
     mbar_init(smem_u32(&bars->sdp_full), 1);
-    mbar_init(smem_u32(&bars->sdp_empty), 4);
-    mbar_init(smem_u32(&bars->pds_full), 4);
+    mbar_init(smem_u32(&bars->sdp_empty), 8);
+    mbar_init(smem_u32(&bars->pds_full), 8);
     mbar_init(smem_u32(&bars->acc_done), 1);
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -230,15 +234,16 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
     }
   } else {
-    reg_alloc<216>();
+    reg_alloc<96>();    // pool = 384 x 80 registers: 128 x 40 + 256 x 96 fits, 104 would deadlock
     const uint32_t quad = warp & 3, row = quad * 32 + lane, qi = q0 + row;
+    const uint32_t ch = (warp - 4) >> 2;            // which 32 of the 64 streamed columns this thread owns
     const uint32_t lane_tmem = (quad * 32) << 16;
     const bool row_active = qi < a.sq;
     uint8_t* ds_row = smem + off_ds + row * 128u;
     if (cta_dead) {
       uint8_t* o_row = smem + off_q + row * 128u;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(o_row + g * 16) = make_uint4(0u, 0u, 0u, 0u);
+      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(o_row + (ch * 4 + g) * 16) = make_uint4(0u, 0u, 0u, 0u);
       fence_proxy_async_smem();
     } else {
       const bool q_is_pad = row_active && a.q_pad && a.q_pad[static_cast<size_t>(b) * a.sq + qi] != 0;
@@ -261,18 +266,17 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                            !(a.causal && kb0 + kBwdBlk - 1 > qi);
         mbar_wait(smem_u32(&bars->sdp_full), n & 1);
         tc_fence_after();
-        uint32_t s[64], dp[64];
-        tmem_ld_32x32b_x32(tmem_s + lane_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-        tmem_ld_32x32b_x32(tmem_s + lane_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-        tmem_ld_32x32b_x32(tmem_dp + lane_tmem, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
-        tmem_ld_32x32b_x32(tmem_dp + lane_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_tmem + ch * 32, s);
+        tmem_ld_32x32b_x32(tmem_dp + lane_tmem + ch * 32, dp);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->sdp_empty));   // S/dP may be overwritten now
         if (n > 0) mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);   // dS buffer consumed
+        const uint32_t kmw = ch ? km[1] : km[0];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
           float ds[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -280,13 +284,13 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             const float p = ex2(fmaf(__uint_as_float(s[c]), a.scale_log2, -lse2));
             float d = p * (__uint_as_float(dp[c]) - dsum) * a.scale;
             if (!plain) {
-              const bool masked = row_dead || ((km[c >> 5] >> (c & 31)) & 1u) || (a.causal && kb0 + c > qi) ||
-                                  static_cast<uint32_t>(c) >= valid;
+              const uint32_t cc = ch * 32 + c;
+              const bool masked = row_dead || ((kmw >> c) & 1u) || (a.causal && kb0 + cc > qi) || cc >= valid;
               d = masked ? 0.f : d;
             }
             ds[i] = d;
           }
-          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+          const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
           *reinterpret_cast<uint4*>(ds_row + phys) =
               make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
                          pack2<kBf16>(ds[6], ds[7]));
@@ -298,14 +302,13 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
       tc_fence_after();
       uint8_t* o_row = smem + off_q + row * 128u;   // Q is dead now
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      {
         uint32_t o[32];
-        tmem_ld_32x32b_x32(tmem_dq + lane_tmem + half * 32, o);
+        tmem_ld_32x32b_x32(tmem_dq + lane_tmem + ch * 32, o);
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const uint32_t phys = (static_cast<uint32_t>(half * 4 + g) ^ (row & 7u)) * 16u;
+          const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
           *reinterpret_cast<uint4*>(o_row + phys) = make_uint4(
               pack2<kBf16>(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1])),
               pack2<kBf16>(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
@@ -315,7 +318,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
       fence_proxy_async_smem();
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (warp == 4 && lane == 0) {
       tma_store_3d(&tmap_dq, smem_base + off_q, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b));
       tma_store_commit();
@@ -333,7 +336,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 constexpr int kDkvSmem = 2 * kTile + 2 * 2 * kHalfTile + 2 * kTile + 1024 + 256;
 
 template <bool kBf16>
-__global__ void __launch_bounds__(kAttnThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                          const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
@@ -363,8 +366,8 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       mbar_init(smem_u32(&bars->ring_empty[s]), 1);
     }
     mbar_init(smem_u32(&bars->sdp_full), 1);
-    mbar_init(smem_u32(&bars->sdp_empty), 4);
-    mbar_init(smem_u32(&bars->pds_full), 4);
+    mbar_init(smem_u32(&bars->sdp_empty), 8);
+    mbar_init(smem_u32(&bars->pds_full), 8);
     mbar_init(smem_u32(&bars->acc_done), 1);
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -454,17 +457,18 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       }
     }
   } else {
-    reg_alloc<216>();
+    reg_alloc<96>();    // pool = 384 x 80 registers: 128 x 40 + 256 x 96 fits, 104 would deadlock
     const uint32_t quad = warp & 3, row = quad * 32 + lane, kj = k0 + row;   // row == key
+    const uint32_t ch = (warp - 4) >> 2;            // which 32 of the 64 streamed columns this thread owns
     const uint32_t lane_tmem = (quad * 32) << 16;
     const bool row_active = kj < a.sk;
     uint8_t* p_row = smem + off_p + row * 128u;
     uint8_t* ds_row = smem + off_ds + row * 128u;
     if (cta_dead) {
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        *reinterpret_cast<uint4*>(smem + off_k + row * 128u + g * 16) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(smem + off_v + row * 128u + g * 16) = make_uint4(0u, 0u, 0u, 0u);
+      for (int g = 0; g < 4; ++g) {
+        *reinterpret_cast<uint4*>(smem + off_k + row * 128u + (ch * 4 + g) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(smem + off_v + row * 128u + (ch * 4 + g) * 16) = make_uint4(0u, 0u, 0u, 0u);
       }
       fence_proxy_async_smem();
     } else {
@@ -474,7 +478,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const uint32_t qb0 = i * kBwdBlk;
         // per-query statistics of this block -> shared memory (threads 0..63 load query qb0 + row)
         float* st = stat_smem + (n & 1) * 128;
-        if (row < kBwdBlk) {
+        if (ch == 0 && row < kBwdBlk) {
           const uint32_t qi = qb0 + row;
           const size_t sidx = (static_cast<size_t>(b) * a.heads + head) * a.sq + (qi < a.sq ? qi : 0);
           st[row] = a.lse[sidx] * kLog2e;
@@ -490,44 +494,45 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const uint32_t valid = min(static_cast<uint32_t>(kBwdBlk), a.sq - qb0);
         const bool plain = row_active && !k_is_pad && valid == kBwdBlk && (qm[0] | qm[1]) == 0u &&
                            !(a.causal && kj > qb0);
-        asm volatile("bar.sync 2, 128;" ::: "memory");   // statistics visible to all row threads
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // statistics visible to all row threads
         mbar_wait(smem_u32(&bars->sdp_full), n & 1);
         tc_fence_after();
-        uint32_t s[64], dp[64];
-        tmem_ld_32x32b_x32(tmem_s + lane_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-        tmem_ld_32x32b_x32(tmem_s + lane_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-        tmem_ld_32x32b_x32(tmem_dp + lane_tmem, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
-        tmem_ld_32x32b_x32(tmem_dp + lane_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_tmem + ch * 32, s);
+        tmem_ld_32x32b_x32(tmem_dp + lane_tmem + ch * 32, dp);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->sdp_empty));
         if (n > 0) mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
+        const uint32_t qmw = ch ? qm[1] : qm[0];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
           float pv[8], ds[8];
-          const float4 l0 = *reinterpret_cast<const float4*>(st + g * 8);
-          const float4 l1 = *reinterpret_cast<const float4*>(st + g * 8 + 4);
-          const float4 d0 = *reinterpret_cast<const float4*>(st + 64 + g * 8);
-          const float4 d1 = *reinterpret_cast<const float4*>(st + 64 + g * 8 + 4);
+          const float* lp = st + ch * 32 + g * 8;
+          const float4 l0 = *reinterpret_cast<const float4*>(lp);
+          const float4 l1 = *reinterpret_cast<const float4*>(lp + 4);
+          const float4 d0 = *reinterpret_cast<const float4*>(lp + 64);
+          const float4 d1 = *reinterpret_cast<const float4*>(lp + 68);
           const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
           const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
           for (int i2 = 0; i2 < 8; ++i2) {
-            const int c = g * 8 + i2;   // query column inside the block
+            const int c = g * 8 + i2;                 // column inside this thread's 32
+            const uint32_t cc = ch * 32 + c;          // query column inside the 64-query block
             float t = __uint_as_float(s[c]) * a.scale_log2;
             bool masked = false;
             if (!plain) {
-              masked = k_is_pad || ((qm[c >> 5] >> (c & 31)) & 1u) || (a.causal && kj > qb0 + c);
+              masked = k_is_pad || ((qmw >> c) & 1u) || (a.causal && kj > qb0 + cc);
               t = masked ? kMaskedLog2 : t;
             }
             float p = ex2(t - lv[i2]);
-            if (!plain) p = (static_cast<uint32_t>(c) < valid && row_active) ? p : 0.f;
+            if (!plain) p = (cc < valid && row_active) ? p : 0.f;
             const float d = p * (__uint_as_float(dp[c]) - dv[i2]) * a.scale;
             pv[i2] = p;
             ds[i2] = masked ? 0.f : d;
           }
-          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+          const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
           *reinterpret_cast<uint4*>(p_row + phys) =
               make_uint4(pack2<kBf16>(pv[0], pv[1]), pack2<kBf16>(pv[2], pv[3]), pack2<kBf16>(pv[4], pv[5]),
                          pack2<kBf16>(pv[6], pv[7]));
@@ -544,26 +549,23 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 #pragma unroll
       for (int which = 0; which < 2; ++which) {   // 0: dV -> V's tile, 1: dK -> K's tile (both dead now)
         uint8_t* o_row = smem + (which == 0 ? off_v : off_k) + row * 128u;
-        const uint32_t taddr = (which == 0 ? tmem_dv : tmem_dk) + lane_tmem;
+        const uint32_t taddr = (which == 0 ? tmem_dv : tmem_dk) + lane_tmem + ch * 32;
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(taddr, o);
+        tmem_ld_wait();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(taddr + half * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t phys = (static_cast<uint32_t>(half * 4 + g) ^ (row & 7u)) * 16u;
-            *reinterpret_cast<uint4*>(o_row + phys) = make_uint4(
-                pack2<kBf16>(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1])),
-                pack2<kBf16>(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
-                pack2<kBf16>(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
-                pack2<kBf16>(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7])));
-          }
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
+          *reinterpret_cast<uint4*>(o_row + phys) = make_uint4(
+              pack2<kBf16>(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1])),
+              pack2<kBf16>(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
+              pack2<kBf16>(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
+              pack2<kBf16>(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7])));
         }
       }
       fence_proxy_async_smem();
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (warp == 4 && lane == 0) {
       tma_store_3d(&tmap_dv, smem_base + off_v, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b));
       tma_store_3d(&tmap_dk, smem_base + off_k, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b));
@@ -611,12 +613,12 @@ cudaError_t launch_attention_bwd(const AttnBwdMaps& m, const AttnBwdArgs& a, boo
   dim3 gq((a.sq + kAttnBQ - 1) / kAttnBQ, a.heads, a.batch);
   dim3 gk((a.sk + kAttnBK - 1) / kAttnBK, a.heads, a.batch);
   if (bf16) {
-    attention_bwd_dq_kernel<true><<<gq, kAttnThreads, kDqSmem, stream>>>(m.q128, m.k64, m.v64, m.do128, m.dq128, a);
-    attention_bwd_dkv_kernel<true><<<gk, kAttnThreads, kDkvSmem, stream>>>(m.q64, m.k128, m.v128, m.do64, m.dk128,
+    attention_bwd_dq_kernel<true><<<gq, kBwdThreads, kDqSmem, stream>>>(m.q128, m.k64, m.v64, m.do128, m.dq128, a);
+    attention_bwd_dkv_kernel<true><<<gk, kBwdThreads, kDkvSmem, stream>>>(m.q64, m.k128, m.v128, m.do64, m.dk128,
                                                                           m.dv128, a);
   } else {
-    attention_bwd_dq_kernel<false><<<gq, kAttnThreads, kDqSmem, stream>>>(m.q128, m.k64, m.v64, m.do128, m.dq128, a);
-    attention_bwd_dkv_kernel<false><<<gk, kAttnThreads, kDkvSmem, stream>>>(m.q64, m.k128, m.v128, m.do64, m.dk128,
+    attention_bwd_dq_kernel<false><<<gq, kBwdThreads, kDqSmem, stream>>>(m.q128, m.k64, m.v64, m.do128, m.dq128, a);
+    attention_bwd_dkv_kernel<false><<<gk, kBwdThreads, kDkvSmem, stream>>>(m.q64, m.k128, m.v128, m.do64, m.dk128,
                                                                            m.dv128, a);
   }
   return cudaGetLastError();
