@@ -210,7 +210,22 @@ class TransformerLanguageModel(nn.Module):
     #: non-padding position); False: the reference's values at padding positions too.
     skip_padding = True
 
-    def encode(self, ids, tokentype_ids=None):
+    @staticmethod
+    def trimmed_width(s, max_len):
+        """Columns to keep when the longest sequence of the batch has max_len tokens (multiple of 64)."""
+        if max_len is None:
+            return s
+        return min(s, max(64, -(-int(max_len) // 64) * 64))
+
+    def encode(self, ids, tokentype_ids=None, max_len=None):
+        """Encoder states [b, s', h]; with max_len (the longest non-padding length, known to the
+        caller on the host) only the first s' = roundup(max_len, 64) columns are computed — every
+        dropped column is padding in every sequence, so the kept positions are unchanged."""
+        s_keep = self.trimmed_width(ids.shape[1], max_len)
+        if s_keep != ids.shape[1]:
+            ids = ids[:, :s_keep].contiguous()
+            if tokentype_ids is not None:
+                tokentype_ids = tokentype_ids[:, :s_keep].contiguous()
         b, s = ids.shape
         pad = ids < 1
         x = self.embedding(ids, tokentype_ids)
@@ -245,9 +260,9 @@ class BertTower(nn.Module):
         super().__init__()
         self.language_model = TransformerLanguageModel(cfg, num_tokentypes, False, vocab_size)
 
-    def forward(self, input_ids, attention_mask=None, tokentype_ids=None):
+    def forward(self, input_ids, attention_mask=None, tokentype_ids=None, max_len=None):
         _require_cuda(input_ids)
-        return self.language_model.encode(input_ids, tokentype_ids)[:, 0, :]
+        return self.language_model.encode(input_ids, tokentype_ids, max_len=max_len)[:, 0, :]
 
     def hidden_states(self, input_ids, tokentype_ids=None):
         return self.language_model.encode(input_ids, tokentype_ids)
@@ -275,12 +290,13 @@ class T5Reader(nn.Module):
     def forward(self, encoder_input_ids, decoder_input_ids, encoder_attn_mask=None,
                 decoder_attn_mask=None, encoder_decoder_attn_mask=None, tokentype_ids=None,
                 lm_labels=None, enc_hidden_states=None, output_enc_hidden=False,
-                enc_ids_for_mask=None):
+                enc_ids_for_mask=None, enc_max_len=None):
         _require_cuda(encoder_input_ids)
         lm = self.language_model
         if enc_hidden_states is None:
-            enc = lm.encode(encoder_input_ids, tokentype_ids)
-            mask_ids = encoder_input_ids
+            # enc_max_len (opt-in): encoder states come back as [b, s', h] with s' = roundup(max_len, 64)
+            enc = lm.encode(encoder_input_ids, tokentype_ids, max_len=enc_max_len)
+            mask_ids = encoder_input_ids[:, :enc.shape[1]]
         else:
             enc = enc_hidden_states.to(lm.embedding.word_embeddings.weight.dtype)
             mask_ids = enc_ids_for_mask if enc_ids_for_mask is not None else encoder_input_ids

@@ -167,7 +167,7 @@ def postprocess_arrays(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_
 
 
 def postprocess(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data, topk_retrievals,
-                seq_length_ret, seq_length, cls_id, sep_id, pad_id, device=None):
+                seq_length_ret, seq_length, cls_id, sep_id, pad_id, device=None, return_lengths=False):
     """Drop-in for emdr2_model.py:250-303 with the tokenizer ids / lengths passed explicitly
     (the reference reads them from get_args()/get_t5_tokenizer()).  Returns four int64 tensors on
     `device` (default: current CUDA device)."""
@@ -187,4 +187,11 @@ def postprocess(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data, t
         if torch.device(device).type == "cuda":
             t = t.pin_memory().to(device, non_blocking=True)
         out.append(t)
+    if return_lengths:
+        # longest non-padding prefix of each tensor, known on the host for free: lets the caller run
+        # the towers on [:, :max_len] instead of the padded width without a device sync
+        def longest(a):
+            a2 = a.reshape(-1, a.shape[-1])
+            return int(((a2 != pad_id) * np.arange(1, a2.shape[1] + 1)).max()) if a2.size else 0
+        return tuple(out), (longest(arrays[0]), longest(arrays[2]), longest(arrays[3]))
     return tuple(out)

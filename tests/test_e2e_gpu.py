@@ -127,7 +127,9 @@ def test_retrieve_and_read_forward_tiny(tmp_path, dtype):
     model.eval()
     ev = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV), torch.tensor(q_len).to(DEV),
                dec.to(DEV))
-    assert torch.equal(ev[0], lm_logits) and ev[2].shape == (bsz, TOPK * S, TINY["hidden"])
+    assert torch.equal(ev[0], lm_logits)
+    assert ev[2].shape[0] == bsz and ev[2].shape[1] % TOPK == 0 and ev[2].shape[1] <= TOPK * S   # trimmed FiD axis
+    assert ev[3].shape == ev[2].shape[:2]
     again = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV), torch.tensor(q_len).to(DEV),
                   dec.to(DEV), all_query_context_hidden_states=ev[2], all_query_context_ids_unflat=ev[3],
                   topk_log_probs=ev[1])
@@ -154,6 +156,14 @@ def test_retrieve_and_read_forward_tiny(tmp_path, dtype):
     live_rep = torch.repeat_interleave(live, TOPK, dim=0)
     assert torch.allclose(one_ctx.float().cpu().view(-1, L, TINY["vocab"])[live_rep], want_one[live_rep],
                           rtol=2e-2, atol=2e-2)
+
+    # trimming padding columns never changes a non-padding position: same logits without it
+    model.settings["trim_padding"] = False
+    full = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV), torch.tensor(q_len).to(DEV),
+                 dec.to(DEV))
+    model.settings["trim_padding"] = True
+    assert full[2].shape == (bsz, TOPK * S, TINY["hidden"])
+    assert torch.equal(full[0][live], lm_logits[live]) and torch.equal(full[1], topk_log_probs)
 
     # ---- losses (a10) on the GPU logits vs fp32 torch on the oracle logits
     lm_loss = losses.reader_cross_entropy(lm_logits, labels.to(DEV), loss_mask.to(DEV))
