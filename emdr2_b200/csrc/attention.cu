@@ -57,7 +57,7 @@ __device__ __forceinline__ void reg_alloc() {
 }
 
 template <bool kBf16>
-__global__ void __launch_bounds__(kAttnFwdThreads, 2)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
                      const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v,
@@ -66,8 +66,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr uint32_t off_q = 0;
   constexpr uint32_t off_kv = kAttnTileBytes;
   constexpr uint32_t off_p = off_kv + kAttnStages * 2 * kAttnTileBytes;
-  constexpr uint32_t off_xchg = off_p + 2 * kAttnTileBytes;   // [2][128] bf16: row-max exchange
-  constexpr uint32_t off_bar = off_xchg + kAttnXchgBytes;
+  constexpr uint32_t off_bar = off_p + 2 * kAttnTileBytes;
   AttnBars* bars = reinterpret_cast<AttnBars*>(smem + off_bar);
   const uint32_t smem_base = smem_u32(smem);
 
@@ -97,8 +96,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(smem_u32(&bars->kv_empty[s]), 1);
     }
     mbar_init(smem_u32(&bars->s_full), 1);
-    mbar_init(smem_u32(&bars->s_empty), 8);
-    mbar_init(smem_u32(&bars->p_full), 8);
+    mbar_init(smem_u32(&bars->s_empty), 4);
+    mbar_init(smem_u32(&bars->p_full), 4);
     mbar_init(smem_u32(&bars->o_full), 1);
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -190,185 +189,214 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   }
   } else {
-    // ===================================================== softmax + output
-    // Eight warps, two threads per query row: thread (row, ch) owns keys [64 ch, 64 ch + 64) of every
-    // 128-key block and output columns [32 ch, 32 ch + 32).  The two partial row maxima meet through
-    // shared memory (one named barrier per block); the two partial sums meet once at the end.
-    reg_alloc<96>();   // pool = 384 x 80 registers: 128 x 40 + 256 x 96
+    // ===================================================== softmax + output (one thread per row)
+    reg_alloc<216>();
     const uint32_t quad = warp & 3;
-    const uint32_t ch = (warp - 4) >> 2;
     const uint32_t row = quad * 32 + lane;
     const uint32_t qi = q0 + row;
     const bool warp_active = q0 + quad * 32 < a.sq;
     const bool row_active = qi < a.sq;
     const bool q_is_pad = row_active && a.q_pad && a.q_pad[static_cast<size_t>(b) * a.sq + qi] != 0;
     const uint32_t lane_tmem = (quad * 32) << 16;
-    uint8_t* p_row = smem + off_p + ch * kAttnTileBytes + row * 128u;   // this thread's 64 keys
-    // Row-maximum exchange between the two threads of a row: [2 halves][128 rows] bf16, rounded UP.
-    // Both threads apply the same rounding to both values, so they agree on m_new, and m_new >= the
-    // true maximum (softmax is shift-invariant; the shift cancels in the final division by l).
-    __nv_bfloat16* xchg = reinterpret_cast<__nv_bfloat16*>(smem + off_xchg);
-    float* xsum = reinterpret_cast<float*>(smem + off_p);               // row-sum exchange: P is dead by then
+    uint8_t* p_row = smem + off_p + row * 128u;
+
+    float o_acc[kAttnHeadDim];
+#pragma unroll
+    for (int i = 0; i < kAttnHeadDim; ++i) o_acc[i] = 0.f;
+    float m_run = __uint_as_float(0xff800000u);  // -inf
+    float l_run = 0.f;
+    float alpha_prev = 0.f;
+
+    auto accumulate_o = [&](float alpha) {
+      uint32_t o[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld_32x32b_x32(tmem_o + lane_tmem + half * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          o_acc[half * 32 + i] = fmaf(o_acc[half * 32 + i], alpha, __uint_as_float(o[i]));
+      }
+    };
 
     if (cta_dead) {   // all-padding query block: zero rows, no attention work
       uint8_t* o_row = smem + off_q + row * 128u;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(o_row + (ch * 4 + g) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(o_row + g * 16) = make_uint4(0u, 0u, 0u, 0u);
       fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 4 && lane == 0) {
+        tma_store_3d(&tmap_o, smem_base + off_q, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b));
+        tma_store_commit();
+        tma_store_wait<0>();
+      }
     } else {
-      float o_acc[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
-      float m_run = __uint_as_float(0xff800000u);  // -inf
-      float l_run = 0.f;                           // partial: this thread's 64 keys of every block
-      float alpha_prev = 0.f;
-
-      auto accumulate_o = [&](float alpha) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tmem_o + lane_tmem + ch * 32, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(o[i]));
-      };
-
-      uint32_t n = 0;   // running index of the live key block
-      for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1), ++n) {
-        const uint32_t kb0 = j * kAttnBK + ch * 64;   // first key of this thread's half
-        mbar_wait(smem_u32(&bars->s_full), n & 1);
-        tc_fence_after();
-        if (n > 0) {   // O_{n-1} has landed and P's buffer is free
-          mbar_wait(smem_u32(&bars->o_full), (n - 1) & 1);
-          tc_fence_after();
-          if (warp_active) accumulate_o(alpha_prev);
-        }
-        float alpha = 1.f, m_new = m_run;
-        uint32_t km[2] = {0u, 0u};
-        uint32_t valid = 64;
-        bool plain = true, constant = false, causal_row = false;
-        if (warp_active) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t idx = kb0 + c * 32 + lane;
-            const bool f = a.k_pad && idx < a.sk && a.k_pad[static_cast<size_t>(b) * a.sk + idx] != 0;
-            km[c] = __ballot_sync(kFull, f);
-          }
-          valid = kb0 >= a.sk ? 0u : min(64u, a.sk - kb0);
-          causal_row = a.causal && (kb0 + 63 > qi);
-          plain = !q_is_pad && !causal_row && valid == 64 && (km[0] | km[1]) == 0u;
-          constant = valid == 64 && (q_is_pad || (km[0] & km[1]) == 0xffffffffu || (a.causal && kb0 > qi));
-        }
-        const uint32_t s_addr = tmem_base + lane_tmem + ch * 64;
-        uint32_t t[32];
-        // masked log2-domain score of column c (0..31) of chunk `part` from the raw accumulator bits
-        auto score = [&](uint32_t raw, uint32_t kmw, int part, int c) -> float {
-          float x = __uint_as_float(raw) * a.scale_log2;
-          const uint32_t cc = part * 32 + c;
-          const bool masked = q_is_pad || ((kmw >> c) & 1u) || (a.causal && kb0 + cc > qi);
-          x = masked ? kMaskedLog2 : x;
-          return (cc < valid) ? x : __uint_as_float(0xff800000u);
-        };
-        // ---- pass 1: maximum of this thread's 64 scores
-        float mx = __uint_as_float(0xff800000u);
-        if (warp_active) {
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            tmem_ld_32x32b_x32(s_addr + part * 32, t);   // .sync.aligned: all lanes, whatever the row needs
-            tmem_ld_wait();
-            if (constant) {
-              mx = kMaskedLog2;
-            } else if (plain) {
-              float r = __uint_as_float(t[0]);
-#pragma unroll
-              for (int c = 1; c < 32; ++c) r = fmaxf(r, __uint_as_float(t[c]));
-              mx = fmaxf(mx, r * a.scale_log2);          // scale > 0: max commutes with the scaling
-            } else {
-              const uint32_t kmw = part ? km[1] : km[0];
-#pragma unroll
-              for (int c = 0; c < 32; ++c) mx = fmaxf(mx, score(t[c], kmw, part, c));
-            }
-          }
-          const __nv_bfloat16 up = __float2bfloat16_ru(mx);
-          xchg[ch * 128 + row] = up;
-          mx = __bfloat162float(up);
-        }
-        asm volatile("bar.sync 3, 256;" ::: "memory");   // both halves of every row have their maximum
-        if (warp_active) {
-          m_new = fmaxf(m_run, fmaxf(mx, __bfloat162float(xchg[(ch ^ 1u) * 128 + row])));
-          alpha = ex2(m_run - m_new);
-          // ---- pass 2: probabilities of this thread's 64 keys -> P rows in shared memory
-          float sum = 0.f;
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            tmem_ld_32x32b_x32(s_addr + part * 32, t);
-            tmem_ld_wait();
-            const uint32_t kmw = part ? km[1] : km[0];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t w[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int c = g * 8 + 2 * i;
-                float p0, p1;
-                if (constant) {
-                  p0 = p1 = ex2(kMaskedLog2 - m_new);
-                } else if (plain) {
-                  p0 = ex2(fmaf(__uint_as_float(t[c]), a.scale_log2, -m_new));
-                  p1 = ex2(fmaf(__uint_as_float(t[c + 1]), a.scale_log2, -m_new));
-                } else {
-                  p0 = ex2(score(t[c], kmw, part, c) - m_new);
-                  p1 = ex2(score(t[c + 1], kmw, part, c + 1) - m_new);
-                }
-                sum += p0 + p1;
-                w[i] = pack2<kBf16>(p0, p1);
-              }
-              const uint32_t phys = (static_cast<uint32_t>(part * 4 + g) ^ (row & 7u)) * 16u;
-              *reinterpret_cast<uint4*>(p_row + phys) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
-          l_run = fmaf(l_run, alpha, sum);
-          m_run = m_new;
-          fence_proxy_async_smem();
-        }
-        alpha_prev = alpha;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(smem_u32(&bars->s_empty));
-          mbar_arrive(smem_u32(&bars->p_full));
-        }
-      }
-
-      mbar_wait(smem_u32(&bars->o_full), (n - 1) & 1);   // n >= 1: the host marks at least one block live
+    uint32_t n = 0;   // running index of the live key block
+    for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1), ++n) {
+      const uint32_t kb0 = j * kAttnBK;
+      mbar_wait(smem_u32(&bars->s_full), n & 1);
       tc_fence_after();
+      float alpha = 1.f;
+      float m_new = m_run;
+      uint32_t t[64];   // scores as raw fp32 bits (tcgen05.ld output registers)
+      // ---- key-side mask bits of this block (same in every warp), 32 keys per word
+      uint32_t km[4] = {0u, 0u, 0u, 0u};
+      uint32_t valid = kAttnBK;
+      bool plain = true;        // no masking at all in this block for this row
+      bool constant = false;    // every score of this row in this block is the masked value
+      bool causal_row = false;  // the causal diagonal crosses this block for this row
       if (warp_active) {
-        accumulate_o(alpha_prev);
-        xsum[ch * 128 + row] = l_run;
-      }
-      asm volatile("bar.sync 3, 256;" ::: "memory");
-      if (warp_active) {
-        const float l_tot = l_run + xsum[(ch ^ 1u) * 128 + row];
-        const float inv_l = 1.0f / l_tot;
-        uint8_t* o_row = smem + off_q + row * 128u;   // Q is dead: every MMA has completed
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t idx = kb0 + c * 32 + lane;
+          const bool f = a.k_pad && idx < a.sk && a.k_pad[static_cast<size_t>(b) * a.sk + idx] != 0;
+          km[c] = __ballot_sync(kFull, f);
+        }
+        valid = min(static_cast<uint32_t>(kAttnBK), a.sk - kb0);
+        causal_row = a.causal && (kb0 + kAttnBK - 1 > qi);
+        plain = !q_is_pad && !causal_row && valid == kAttnBK && (km[0] | km[1] | km[2] | km[3]) == 0u;
+        constant = valid == kAttnBK && (q_is_pad || (km[0] & km[1] & km[2] & km[3]) == 0xffffffffu ||
+                                        (a.causal && kb0 > qi));
+      }
+      // Loads the scores of keys [half*64, half*64+64) of the block into t as masked log2-domain
+      // values and returns their maximum.  Half 0 is read twice (max pass, then exp pass) so that
+      // only 64 scores are ever live next to the 64 output accumulators.
+      auto load_scores = [&](auto half_c) -> float {
+        constexpr int half = decltype(half_c)::value;
+        // tcgen05.ld is .sync.aligned: every lane of the warp executes it, whatever its row needs
+        const uint32_t s_addr = tmem_base + lane_tmem + half * 64;
+        tmem_ld_32x32b_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&t[0]));
+        tmem_ld_32x32b_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&t[32]));
+        tmem_ld_wait();
+        if (constant) {   // per-row (divergent) from here on: nothing to scale, nothing to compare
+#pragma unroll
+          for (int c = 0; c < 64; ++c) t[c] = __float_as_uint(kMaskedLog2);
+          return kMaskedLog2;
+        }
+        float mx = __uint_as_float(0xff800000u);
+        if (plain) {
+          // unmasked rows keep the RAW accumulators: scale > 0, so the maximum commutes with the
+          // scaling, and write_probs folds the scaling into one FFMA per element
+          float r = __uint_as_float(t[0]);
+#pragma unroll
+          for (int c = 1; c < 64; ++c) r = fmaxf(r, __uint_as_float(t[c]));
+          mx = r * a.scale_log2;
+        } else if (!causal_row && valid == kAttnBK) {   // key-padding bits only
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const uint32_t cc = half * 64 + c;
+            float x = __uint_as_float(t[c]) * a.scale_log2;
+            x = (km[cc >> 5] & (1u << (cc & 31))) ? kMaskedLog2 : x;
+            t[c] = __float_as_uint(x);
+            mx = fmaxf(mx, x);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const uint32_t cc = half * 64 + c;
+            float x = __uint_as_float(t[c]) * a.scale_log2;
+            const bool masked = q_is_pad || ((km[cc >> 5] >> (cc & 31)) & 1u) ||
+                                (a.causal && kb0 + cc > qi);
+            x = masked ? kMaskedLog2 : x;
+            x = (cc < valid) ? x : __uint_as_float(0xff800000u);
+            t[c] = __float_as_uint(x);
+            mx = fmaxf(mx, x);
+          }
+        }
+        return mx;
+      };
+      // exp2(t - m_new) of the 64 live scores -> 16-bit -> P rows in shared memory; returns the sum
+      auto write_probs = [&](auto half_c) -> float {
+        constexpr int half = decltype(half_c)::value;
+        if (constant) {   // one probability value for the whole row of this block
+          const float p = ex2(kMaskedLog2 - m_new);
+          const uint32_t w = pack2<kBf16>(p, p);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(p_row + half * kAttnTileBytes + g * 16) = make_uint4(w, w, w, w);
+          return 64.f * p;
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
           uint32_t w[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            w[i] = pack2<kBf16>(o_acc[g * 8 + 2 * i] * inv_l, o_acc[g * 8 + 2 * i + 1] * inv_l);
-          const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
-          *reinterpret_cast<uint4*>(o_row + phys) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int i = 0; i < 4; ++i) {
+            float p0, p1;
+            if (plain) {
+              p0 = ex2(fmaf(__uint_as_float(t[g * 8 + 2 * i]), a.scale_log2, -m_new));
+              p1 = ex2(fmaf(__uint_as_float(t[g * 8 + 2 * i + 1]), a.scale_log2, -m_new));
+            } else {
+              p0 = ex2(__uint_as_float(t[g * 8 + 2 * i]) - m_new);
+              p1 = ex2(__uint_as_float(t[g * 8 + 2 * i + 1]) - m_new);
+            }
+            sum += p0 + p1;
+            w[i] = pack2<kBf16>(p0, p1);
+          }
+          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+          *reinterpret_cast<uint4*>(p_row + half * kAttnTileBytes + phys) =
+              make_uint4(w[0], w[1], w[2], w[3]);
         }
+        return sum;
+      };
+
+      // O_{j-1} must have landed (and P's buffer be free) before P_j is written; folding it in
+      // first keeps the score registers and the tcgen05.ld staging registers from overlapping
+      if (n > 0) {
+        mbar_wait(smem_u32(&bars->o_full), (n - 1) & 1);
+        tc_fence_after();
+        if (warp_active) accumulate_o(alpha_prev);
+      }
+      if (warp_active) {
+        const float mx0 = load_scores(std::integral_constant<int, 0>{});
+        const float mx1 = load_scores(std::integral_constant<int, 1>{});   // t holds the second half
+        m_new = fmaxf(m_run, fmaxf(mx0, mx1));
+        alpha = ex2(m_run - m_new);
+      }
+      alpha_prev = alpha;
+      if (warp_active) {
+        float sum = write_probs(std::integral_constant<int, 1>{});
+        load_scores(std::integral_constant<int, 0>{});
+        sum += write_probs(std::integral_constant<int, 0>{});
+        l_run = fmaf(l_run, alpha, sum);
+        m_run = m_new;
         fence_proxy_async_smem();
-        if (a.lse && row_active && ch == 0)
-          a.lse[(static_cast<size_t>(b) * a.heads + head) * a.sq + qi] = (m_run + log2f(l_tot)) * kLn2;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bars->s_empty));
+        mbar_arrive(smem_u32(&bars->p_full));
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+
+    mbar_wait(smem_u32(&bars->o_full), (n - 1) & 1);   // n >= 1: the host marks at least one block live
+    tc_fence_after();
+    if (warp_active) {
+      accumulate_o(alpha_prev);
+      const float inv_l = 1.0f / l_run;
+      uint8_t* o_row = smem + off_q + row * 128u;   // Q is dead: every MMA has completed
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          w[i] = pack2<kBf16>(o_acc[g * 8 + 2 * i] * inv_l, o_acc[g * 8 + 2 * i + 1] * inv_l);
+        const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+        *reinterpret_cast<uint4*>(o_row + phys) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      fence_proxy_async_smem();
+      if (a.lse && row_active)
+        a.lse[(static_cast<size_t>(b) * a.heads + head) * a.sq + qi] = (m_run + log2f(l_run)) * kLn2;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     if (warp == 4 && lane == 0) {
-      tma_store_3d(&tmap_o, smem_base + off_q, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b));
+      tma_store_3d(&tmap_o, smem_base + off_q, col_h, static_cast<int32_t>(q0),
+                   static_cast<int32_t>(b));
       tma_store_commit();
       tma_store_wait<0>();
     }
+    }   // !cta_dead
   }
 
   tc_fence_before();
@@ -391,10 +419,10 @@ void launch_attention_fwd(const CUtensorMap& tmap_q, const CUtensorMap& tmap_k,
                           const AttnArgs& args, bool bf16, cudaStream_t stream) {
   dim3 grid((args.sq + kAttnBQ - 1) / kAttnBQ, args.heads, args.batch);
   if (bf16)
-    attention_fwd_kernel<true><<<grid, kAttnFwdThreads, kAttnSmemBytes, stream>>>(tmap_q, tmap_k, tmap_v,
+    attention_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tmap_q, tmap_k, tmap_v,
                                                                               tmap_o, args);
   else
-    attention_fwd_kernel<false><<<grid, kAttnFwdThreads, kAttnSmemBytes, stream>>>(tmap_q, tmap_k, tmap_v,
+    attention_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tmap_q, tmap_k, tmap_v,
                                                                                tmap_o, args);
 }
 

@@ -17,8 +17,7 @@
 //
 // One CTA per (128-query block, head, batch).  Per 128-key block: S = Q·Kᵀ (tcgen05, fp32 in TMEM,
 // double-buffered) -> 4 softmax warps, one thread per query row (online softmax in the log2
-// domain; eight softmax warps, two threads per row, partial maxima/sums exchanged through shared
-// memory) -> P (16-bit) into shared memory in the K-major SW128 operand layout -> O_j = P·V_j
+// domain) -> P (16-bit) into shared memory in the K-major SW128 operand layout -> O_j = P·V_j
 // (V consumed MN-major straight from its TMA tile) -> accumulated in registers with the usual
 // running-max rescale.  K/V stream through a 2-stage TMA ring.  Two CTAs are resident per SM
 // (setmaxnreg moves registers from the TMA/MMA warps to the softmax warps to make that fit).
@@ -33,17 +32,15 @@ constexpr int kAttnHeadDim = 64;
 constexpr int kAttnBQ = 128;      // query rows per CTA
 constexpr int kAttnBK = 128;      // keys per block
 constexpr int kAttnStages = 2;
-constexpr int kAttnThreads = 256;     // (backward prep / legacy) warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, 4 row warps
-constexpr int kAttnFwdThreads = 384;  // forward: the same control warpgroup + 8 softmax warps (2 threads per row)
-constexpr int kAttnXchgBytes = 2 * 128 * 2;       // row-max exchange between the two threads of a row (bf16)
+constexpr int kAttnThreads = 256; // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 softmax
 constexpr int kAttnTileBytes = kAttnBQ * kAttnHeadDim * 2;              // 16 KiB
-// 112 KiB of tiles + 512 B exchange + 256 B of barriers: two CTAs fit one SM (2 x 113 KiB), so one CTA's TMA / MMA /
+// 112 KiB of tiles + 256 B of barriers: two CTAs fit one SM (2 x 113 KiB), so one CTA's TMA / MMA /
 // softmax latencies are hidden behind the other's; TMEM is split 256 + 256 columns.
 constexpr int kAttnBarBytes = 256;
 constexpr int kAttnSmemBytes = kAttnTileBytes                            // Q (reused for O)
                                + kAttnStages * 2 * kAttnTileBytes        // K/V ring
                                + 2 * kAttnTileBytes                      // P (two 64-key K blocks)
-                               + kAttnXchgBytes + kAttnBarBytes;
+                               + kAttnBarBytes;
 constexpr int kAttnTmemCols = 256;                                       // S [0,128) + O [128,192)
 
 struct AttnArgs {

@@ -18,6 +18,11 @@ struct GemmBars {
   uint64_t tmem_empty[2];
   uint64_t res_full[2];    // residual box landed in the staging buffer of column half 0 / 1
   uint32_t tmem_base;
+  uint32_t pad_[3];
+  // Bias slice of the current tile, double-buffered by tile parity: fetched by the epilogue threads
+  // BEFORE they wait for the accumulator, so its global-load latency hides behind that wait (eight
+  // dependent __ldg per chunk used to sit on the epilogue's critical path).
+  alignas(16) uint16_t bias_stage[2][kGemmBN];
 };
 static_assert(sizeof(GemmBars) <= kGemmBarBytes, "barrier block too large");
 
@@ -242,8 +247,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t buf = it & 1;
       const uint32_t m0 = (t / a.tiles_n) * kGemmBM;
       const uint32_t n0 = (t % a.tiles_n) * kGemmBN;
+      if (has_bias) {   // one 16-bit element per epilogue thread: columns n0 .. n0 + 255
+        const uint32_t e = threadIdx.x - 128;
+        bars->bias_stage[buf][e] = n0 + e < a.N ? bias[n0 + e] : static_cast<uint16_t>(0);
+      }
       mbar_wait(smem_u32(&bars->tmem_full[buf]), (it >> 1) & 1);
       tc_fence_after();
+      if (has_bias) named_bar_sync(3, 256);   // slice visible; also keeps warps within one tile of each other
 #pragma unroll 1
       for (uint32_t ch = 0; ch < 2; ++ch) {
         const uint32_t col0 = hh * 128 + ch * 64;
@@ -289,7 +299,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
             if (has_bias && col_ok) {
-              const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + gcol + g * 8));
+              const uint4 bv = *reinterpret_cast<const uint4*>(&bars->bias_stage[buf][col0 + g * 8]);
               const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -326,7 +336,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
           if (has_bias && col_ok) {
-            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + gcol + g * 8));
+            const uint4 bv = *reinterpret_cast<const uint4*>(&bars->bias_stage[buf][col0 + g * 8]);
             const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

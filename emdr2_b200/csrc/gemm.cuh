@@ -36,7 +36,7 @@ constexpr int kGemmStageA = kGemmBM * kGemmBK * 2;            // 16 KiB
 constexpr int kGemmStageB = kGemmBN * kGemmBK * 2;            // 32 KiB
 constexpr int kGemmStageBytes = kGemmStageA + kGemmStageB;    // 48 KiB
 constexpr int kGemmOutBytes = 2 * kGemmBM * 64 * 2;           // two 128x64 staging boxes
-constexpr int kGemmBarBytes = 1024;
+constexpr int kGemmBarBytes = 2048;                              // barriers + the staged bias slice
 constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + kGemmOutBytes + kGemmBarBytes + 1024;
 
 constexpr uint32_t kGemmBias = 1u;
