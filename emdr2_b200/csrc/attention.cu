@@ -317,19 +317,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,
           return 64.f * p;
         }
         float sum = 0.f;
+        const float mul = plain ? a.scale_log2 : 1.0f;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           uint32_t w[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            float p0, p1;
-            if (plain) {
-              p0 = ex2(fmaf(__uint_as_float(t[g * 8 + 2 * i]), a.scale_log2, -m_new));
-              p1 = ex2(fmaf(__uint_as_float(t[g * 8 + 2 * i + 1]), a.scale_log2, -m_new));
-            } else {
-              p0 = ex2(__uint_as_float(t[g * 8 + 2 * i]) - m_new);
-              p1 = ex2(__uint_as_float(t[g * 8 + 2 * i + 1]) - m_new);
-            }
+            // branch-free: unmasked rows hold raw accumulators (mul = scale), masked rows hold
+            // already scaled / replaced values (mul = 1)
+            const float p0 = ex2(fmaf(__uint_as_float(t[g * 8 + 2 * i]), mul, -m_new));
+            const float p1 = ex2(fmaf(__uint_as_float(t[g * 8 + 2 * i + 1]), mul, -m_new));
             sum += p0 + p1;
             w[i] = pack2<kBf16>(p0, p1);
           }

@@ -24,7 +24,7 @@ def timeit(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
-def main():
+def main():  # noqa
     dtype = torch.bfloat16
     out = {"gemm": [], "attention": [], "layernorm": [], "encoder": []}
     g = torch.Generator(device=DEV).manual_seed(0)
