@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from emdr2_b200 import ops
-from tools.gpu_perf_blocks import timeit
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gpu_perf_blocks import timeit
 DEV = "cuda:0"
 g = torch.Generator(device=DEV).manual_seed(0)
 dtype = torch.bfloat16
