@@ -83,6 +83,12 @@ struct AttnBwdMaps {
 cudaError_t launch_attention_bwd(const AttnBwdMaps& maps, const AttnBwdArgs& a, bool bf16, cudaStream_t stream);
 
 cudaError_t attention_prepare();
+// Persistent forward (attention_persist.cu): production path; the one-CTA-per-item kernel of
+// attention.cu is kept behind EMDR2_ATTN_IMPL=legacy for A/B runs.
+cudaError_t attention_persistent_prepare();
+void launch_attention_fwd_persistent(const CUtensorMap& tmap_q, const CUtensorMap& tmap_k,
+                                     const CUtensorMap& tmap_v, const CUtensorMap& tmap_o,
+                                     const AttnArgs& args, bool bf16, int sm_count, cudaStream_t stream);
 void launch_attention_fwd(const CUtensorMap& tmap_q, const CUtensorMap& tmap_k,
                           const CUtensorMap& tmap_v, const CUtensorMap& tmap_o,
                           const AttnArgs& args, bool bf16, cudaStream_t stream);

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -194,8 +196,13 @@ int emdr2_attention_fwd(int dtype, const void* q, int64_t ldq, const void* k, in
   static bool prepared[64] = {};
   if (!prepared[info.device]) {
     CUDA_TRY(emdr2::attention_prepare());
+    CUDA_TRY(emdr2::attention_persistent_prepare());
     prepared[info.device] = true;
   }
+  static const bool legacy = [] {
+    const char* e = getenv("EMDR2_ATTN_IMPL");
+    return e && strcmp(e, "legacy") == 0;
+  }();
   CUtensorMap tq, tk, tv, to;
   if ((rc = make_tmap_3d(&tq, dtype, q, batch, sq, width, ldq, emdr2::kAttnBQ)) != EMDR2_OK) return rc;
   if ((rc = make_tmap_3d(&tk, dtype, k, batch, sk, width, ldk, emdr2::kAttnBK)) != EMDR2_OK) return rc;
@@ -218,7 +225,11 @@ int emdr2_attention_fwd(int dtype, const void* q, int64_t ldq, const void* k, in
   aa.lse = lse;
   ScopedTimer timer(EMDR2_KIND_ATTENTION, static_cast<cudaStream_t>(cuda_stream),
                     4.0 * batch * heads * sq * static_cast<double>(sk) * emdr2::kAttnHeadDim);
-  emdr2::launch_attention_fwd(tq, tk, tv, to, aa, fmt == 1, static_cast<cudaStream_t>(cuda_stream));
+  if (legacy)
+    emdr2::launch_attention_fwd(tq, tk, tv, to, aa, fmt == 1, static_cast<cudaStream_t>(cuda_stream));
+  else
+    emdr2::launch_attention_fwd_persistent(tq, tk, tv, to, aa, fmt == 1, info.sm_count,
+                                           static_cast<cudaStream_t>(cuda_stream));
   CUDA_TRY(cudaGetLastError());
   return EMDR2_OK;
 }

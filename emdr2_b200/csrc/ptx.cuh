@@ -186,6 +186,20 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand is read from tensor memory (row = lane, 16-bit
+// elements packed two per 32-bit column, K-major only); single issuing thread.
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -222,6 +236,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+
+// registers -> TMEM, 32 lanes x 16 consecutive 32-bit columns (same lane mapping as the loads).
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- global memory, relaxed gpu scope

@@ -113,6 +113,9 @@ ATTN_CASES = [
     (1, 2, 200, 333, True, False),       # ragged: neither a multiple of 128
     (1, 1, 1, 1, False, False),
     (2, 2, 130, 130, False, True),
+    (26, 12, 300, 260, True, False),     # 936 work items: every persistent CTA walks several items
+    (40, 8, 130, 130, False, True),      # 640 items, causal, ragged last query block
+    (5, 2, 64, 2000, True, False),       # long key axis: many blocks per item (running-max rescales)
 ]
 
 
@@ -141,6 +144,25 @@ def test_attention_forward(batch, heads, sq, sk, pad, causal, dtype):
     tol = 2 ** -7 if dtype == torch.bfloat16 else 2 ** -10
     err = (got.float() - want).abs().max().item()
     assert torch.allclose(got.float(), want, rtol=tol, atol=tol), err
+    assert torch.allclose(lse, want_lse, rtol=1e-4, atol=1e-3), (lse - want_lse).abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_attention_running_max_rises_across_blocks(dtype):
+    """Keys grow along the key axis, so later blocks beat the running maximum by far more than the
+    lazy-rescale slack (2^8) and O must be rescaled in tensor memory several times per row; a second
+    half with shrinking keys exercises the no-rescale path with large stale-max probabilities."""
+    from emdr2_b200.ops import attention
+    batch, heads, sq, sk = 2, 3, 160, 1024
+    w = heads * 64
+    q = _rand((batch * sq, w), dtype, 61, scale=2.0)
+    ramp = torch.cat([torch.linspace(0.2, 6.0, sk // 2), torch.linspace(6.0, 0.2, sk // 2)]).to(DEV)
+    k = (_rand((batch * sk, w), dtype, 62).float().view(batch, sk, w) * ramp[None, :, None]).to(dtype).view(batch * sk, w)
+    v = _rand((batch * sk, w), dtype, 63)
+    got, lse = attention(q, k, v, batch, heads, sq, sk, return_lse=True)
+    want, want_lse = _ref_attention(q, k, v, batch, heads, sq, sk, None, None, False)
+    tol = 2 ** -6 if dtype == torch.bfloat16 else 2 ** -9
+    assert torch.allclose(got.float(), want, rtol=tol, atol=tol), (got.float() - want).abs().max().item()
     assert torch.allclose(lse, want_lse, rtol=1e-4, atol=1e-3), (lse - want_lse).abs().max().item()
 
 
