@@ -649,7 +649,7 @@ def run_retrieve_read(a):
     attn_tf = attn_fl / max(attn_s, 1e-12) / 1e12
     launches_step = (gemm_n + attn_n + row_n) // a.steps + (2 if world == 1 else 3)
     tokens = a.batch * (a.seq_ret + a.k * a.seq_ret + a.k * a.seq)
-    fmt_h2d = a.batch * a.k * (2 * a.seq_ret + 2 * a.seq) * 8
+    fmt_h2d = a.batch * a.k * (a.seq_ret + 2 * a.seq) * 8      # ids of the three layouts (types are zeros made on the device)
     in_bytes = sum(v.numel() * 8 for v in host.values())
     line = {
         "metric": metric_name(a), "value": a.batch * world / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,

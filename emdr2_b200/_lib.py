@@ -82,6 +82,12 @@ _SIGNATURES = {
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_void_p]),
+    "emdr2_format_passages": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                             ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]),
     "emdr2_ops_timing": (ctypes.c_int, [ctypes.c_int]),
     "emdr2_ops_timing_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
                                              ctypes.POINTER(ctypes.c_int64),

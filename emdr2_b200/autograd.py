@@ -216,6 +216,59 @@ class _CrossAttentionFn(torch.autograd.Function):
         return (dq, dkv) + (None,) * 9
 
 
+class _GroupedSelfAttentionFn(torch.autograd.Function):
+    """Self-attention over a token-packed [T, 3h] projection made of several rectangular groups
+    (emdr2_b200/blocks.py: length-bucketed execution).  `groups` is a list of
+    (row offset, batch, seq, pad uint8 [batch, seq], live uint8 block map or None); one attention
+    launch per group in either direction, all reading / writing slices of the same buffers."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, groups, causal, scale):
+        h = heads * 64
+        out = torch.empty((qkv.shape[0], h), dtype=qkv.dtype, device=qkv.device)
+        lses = []
+        for off, b, s, pad, live in groups:
+            part = qkv[off:off + b * s]
+            _, lse = ops.attention(part[:, :h], part[:, h:2 * h], part[:, 2 * h:], b, heads, s, s, q_pad=pad,
+                                   k_pad=pad, causal=causal, scale=scale, return_lse=True, q_live=live,
+                                   k_live=live, out=out[off:off + b * s])
+            lses.append(lse)
+        ctx.save_for_backward(qkv, out, *lses)
+        ctx.groups, ctx.cfg = groups, (heads, causal, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out = ctx.saved_tensors[:2]
+        lses = ctx.saved_tensors[2:]
+        heads, causal, scale = ctx.cfg
+        h = heads * 64
+        dout = _c(dout)
+        dqkv = torch.empty_like(qkv)
+        for (off, b, s, pad, live), lse in zip(ctx.groups, lses):
+            r = slice(off, off + b * s)
+            q, dq = qkv[r], dqkv[r]
+            _attention_bwd(q[:, :h], q[:, h:2 * h], q[:, 2 * h:], out[r], dout[r], dq[:, :h], dq[:, h:2 * h],
+                           dq[:, 2 * h:], b, heads, s, s, pad, pad, live, live, causal, scale, lse)
+        return dqkv, None, None, None, None
+
+
+def self_attention_grouped(qkv, heads, groups, causal=False, scale=0.125):
+    """ctx [T, h] for a packed projection qkv [T, 3h] whose rows are the concatenation of the groups'
+    [batch*seq] token blocks.  groups: (row offset, batch, seq, pad, live) per group."""
+    groups = [(int(off), int(b), int(s), _u8(pad, qkv.device), _u8(live, qkv.device))
+              for off, b, s, pad, live in groups]
+    if _needs_grad(qkv):
+        return _GroupedSelfAttentionFn.apply(qkv, heads, groups, causal, scale)
+    h = heads * 64
+    out = torch.empty((qkv.shape[0], h), dtype=qkv.dtype, device=qkv.device)
+    for off, b, s, pad, live in groups:
+        part = qkv[off:off + b * s]
+        ops.attention(part[:, :h], part[:, h:2 * h], part[:, 2 * h:], b, heads, s, s, q_pad=pad, k_pad=pad,
+                      causal=causal, scale=scale, q_live=live, k_live=live, out=out[off:off + b * s])
+    return out
+
+
 def self_attention(qkv, batch, heads, seq, pad=None, live=None, causal=False, scale=0.125):
     if _needs_grad(qkv):
         return _SelfAttentionFn.apply(qkv, batch, heads, seq, pad, live, causal, scale)

@@ -112,11 +112,14 @@ class ParallelAttention(nn.Module):
         self.scale = 1.0 / math.sqrt(hidden // heads)
 
     def forward(self, x, batch, sq, q_pad, residual, causal=False, encoder_output=None, sk=None,
-                k_pad=None, q_live=None, k_live=None):
+                k_pad=None, q_live=None, k_live=None, groups=None):
         if self.attention_type == "self":
             qkv = self.query_key_value(x)
-            ctx = ag.self_attention(qkv, batch, self.heads, sq, pad=q_pad, live=q_live, causal=causal,
-                                    scale=self.scale)
+            if groups is not None:      # token-packed rows of several [batch_g, seq_g] rectangles
+                ctx = ag.self_attention_grouped(qkv, self.heads, groups, causal=causal, scale=self.scale)
+            else:
+                ctx = ag.self_attention(qkv, batch, self.heads, sq, pad=q_pad, live=q_live, causal=causal,
+                                        scale=self.scale)
         else:
             q = self.query(x)
             kv = self.key_value(encoder_output)
@@ -149,9 +152,9 @@ class ParallelTransformerLayer(nn.Module):
         self.mlp = ParallelMLP(hidden, ffn, dtype)
 
     def forward(self, x, batch, seq, pad, causal=False, encoder_output=None, enc_seq=None, enc_pad=None,
-                q_live=None, enc_live=None):
+                q_live=None, enc_live=None, groups=None):
         x = self.self_attention(self.input_layernorm(x), batch, seq, pad, residual=x, causal=causal,
-                                q_live=q_live)
+                                q_live=q_live, groups=groups)
         ln = self.post_attention_layernorm(x)
         if self.layer_type == "decoder":
             x = self.inter_attention(ln, batch, seq, pad, residual=x, encoder_output=encoder_output,
@@ -217,20 +220,94 @@ class TransformerLanguageModel(nn.Module):
             return s
         return min(s, max(64, -(-int(max_len) // 64) * 64))
 
-    def encode(self, ids, tokentype_ids=None, max_len=None):
-        """Encoder states [b, s', h]; with max_len (the longest non-padding length, known to the
-        caller on the host) only the first s' = roundup(max_len, 64) columns are computed — every
-        dropped column is padding in every sequence, so the kept positions are unchanged."""
+    #: Length-bucketed execution of large batches (see `encode`): number of buckets, the smallest
+    #: batch it applies to, and the granularity (tokens) a bucket's width is rounded up to.
+    length_buckets = 4
+    bucket_min_rows = 64
+    bucket_granularity = 8
+
+    def _bucket_plan(self, b, s, row_lengths):
+        """None, or [(row indices (host int64 array), width)] covering every row once, sorted by
+        length.  Pure host arithmetic on lengths the caller already has on the host."""
+        import numpy as np
+        if row_lengths is None or self.length_buckets < 2 or b < max(self.bucket_min_rows, 2 * self.length_buckets):
+            return None
+        lengths = np.asarray(row_lengths).reshape(-1)
+        if lengths.shape[0] != b:
+            raise ValueError("row_lengths must hold one length per sequence (%d != %d)" % (lengths.shape[0], b))
+        order = np.argsort(lengths, kind="stable")
+        gran = self.bucket_granularity
+        plan = []
+        for idx in np.array_split(order, self.length_buckets):
+            if idx.size == 0:
+                continue
+            w = int(min(s, max(gran, -(-int(lengths[idx].max()) // gran) * gran)))
+            if plan and plan[-1][1] == w:
+                plan[-1] = (np.concatenate([plan[-1][0], idx]), w)
+            else:
+                plan.append((idx, w))
+        return plan if len(plan) > 1 else None
+
+    def encode(self, ids, tokentype_ids=None, max_len=None, row_lengths=None, cls_only=False):
+        """Encoder states [b, s', h] (or only the position-0 states [b, h] with cls_only).
+
+        max_len (the longest non-padding length, known to the caller on the host): only the first
+        s' = roundup(max_len, 64) columns are computed — every dropped column is padding in every
+        sequence, so the kept positions are unchanged.
+
+        row_lengths (host array, one non-padding length per sequence): large batches additionally
+        run length-bucketed — sequences are sorted by length into `length_buckets` groups, each cut
+        to its own longest member, and the groups' tokens are packed into ONE [T, h] activation
+        matrix: every GEMM / LayerNorm runs once over T rows (T ~ 0.85-0.9 of b*s' on NQ-shaped
+        batches; no wave-quantisation loss from splitting), only attention runs per group on its
+        slice.  Cut columns are padding in every member of the group, so non-padding positions are
+        unchanged; padding positions of the returned states are zero."""
         s_keep = self.trimmed_width(ids.shape[1], max_len)
         if s_keep != ids.shape[1]:
             ids = ids[:, :s_keep].contiguous()
             if tokentype_ids is not None:
                 tokentype_ids = tokentype_ids[:, :s_keep].contiguous()
         b, s = ids.shape
-        pad = ids < 1
+        plan = self._bucket_plan(b, s, row_lengths)
+        if plan is not None:
+            return self._encode_bucketed(ids, tokentype_ids, plan, cls_only)
+        pad = (ids < 1).to(torch.uint8)
         x = self.embedding(ids, tokentype_ids)
         q_live = ops.live_blocks(pad) if self.skip_padding else None
-        return self.encoder(x, b, s, pad, q_live=q_live).view(b, s, self.hidden)
+        y = self.encoder(x, b, s, pad, q_live=q_live).view(b, s, self.hidden)
+        return y[:, 0, :] if cls_only else y
+
+    def _encode_bucketed(self, ids, tokentype_ids, plan, cls_only):
+        import numpy as np
+        b, s = ids.shape
+        dev = ids.device
+        order = np.concatenate([idx for idx, _ in plan])
+        perm = torch.from_numpy(order).pin_memory().to(dev, non_blocking=True)
+        ids_sorted = ids.index_select(0, perm)
+        typ_sorted = tokentype_ids.index_select(0, perm) if tokentype_ids is not None else None
+        xs, groups, spans = [], [], []
+        off = r0 = 0
+        for idx, w in plan:
+            n = int(idx.size)
+            ids_g = ids_sorted[r0:r0 + n, :w].contiguous()
+            typ_g = typ_sorted[r0:r0 + n, :w].contiguous() if typ_sorted is not None else None
+            pad_g = (ids_g < 1).to(torch.uint8)          # converted once, not once per layer
+            xs.append(self.embedding(ids_g, typ_g))
+            groups.append((off, n, w, pad_g, ops.live_blocks(pad_g) if self.skip_padding else None))
+            spans.append((off, r0, n, w))
+            off += n * w
+            r0 += n
+        y = self.encoder(torch.cat(xs, dim=0), None, None, None, groups=groups)      # [T, h]
+        h = self.hidden
+        if cls_only:
+            first = torch.cat([y[o:o + n * w].view(n, w, h)[:, 0, :] for o, _, n, w in spans], dim=0)
+            out = torch.empty_like(first)
+            out[perm] = first                      # back to the caller's row order
+            return out
+        out = y.new_zeros((b, s, h))
+        for o, r, n, w in spans:
+            out[perm[r:r + n], :w] = y[o:o + n * w].view(n, w, h)
+        return out
 
     def decode(self, dec_ids, enc_states, enc_pad):
         """enc_states [b, sk, h] (sk may be K*S: FiD concatenation, emdr2_model.py:159-164)."""
@@ -260,9 +337,10 @@ class BertTower(nn.Module):
         super().__init__()
         self.language_model = TransformerLanguageModel(cfg, num_tokentypes, False, vocab_size)
 
-    def forward(self, input_ids, attention_mask=None, tokentype_ids=None, max_len=None):
+    def forward(self, input_ids, attention_mask=None, tokentype_ids=None, max_len=None, row_lengths=None):
         _require_cuda(input_ids)
-        return self.language_model.encode(input_ids, tokentype_ids, max_len=max_len)[:, 0, :]
+        return self.language_model.encode(input_ids, tokentype_ids, max_len=max_len, row_lengths=row_lengths,
+                                          cls_only=True)
 
     def hidden_states(self, input_ids, tokentype_ids=None):
         return self.language_model.encode(input_ids, tokentype_ids)
@@ -290,12 +368,12 @@ class T5Reader(nn.Module):
     def forward(self, encoder_input_ids, decoder_input_ids, encoder_attn_mask=None,
                 decoder_attn_mask=None, encoder_decoder_attn_mask=None, tokentype_ids=None,
                 lm_labels=None, enc_hidden_states=None, output_enc_hidden=False,
-                enc_ids_for_mask=None, enc_max_len=None):
+                enc_ids_for_mask=None, enc_max_len=None, enc_row_lengths=None):
         _require_cuda(encoder_input_ids)
         lm = self.language_model
         if enc_hidden_states is None:
             # enc_max_len (opt-in): encoder states come back as [b, s', h] with s' = roundup(max_len, 64)
-            enc = lm.encode(encoder_input_ids, tokentype_ids, max_len=enc_max_len)
+            enc = lm.encode(encoder_input_ids, tokentype_ids, max_len=enc_max_len, row_lengths=enc_row_lengths)
             mask_ids = encoder_input_ids[:, :enc.shape[1]]
         else:
             enc = enc_hidden_states.to(lm.embedding.word_embeddings.weight.dtype)

@@ -438,7 +438,25 @@ void launch_attention_fwd_persistent(const CUtensorMap& tmap_q, const CUtensorMa
   const uint32_t nqb = (args.sq + kAttnBQ - 1) / kAttnBQ;
   const uint64_t items = static_cast<uint64_t>(nqb) * args.heads * args.batch;
   const uint64_t slots = 2ull * static_cast<uint64_t>(sm_count);
-  const dim3 grid(static_cast<uint32_t>(items < slots ? items : slots));
+  // Items are numbered query-block fastest and walked with a grid stride.  With padding the query
+  // blocks of a sequence differ in cost (trailing blocks are dead or see fewer live key blocks), so a
+  // stride that is a multiple of nqb would pin every CTA to one query-block index for the whole launch
+  // (296 CTAs, nqb = 4: half of them idle on half-padded batches).  A stride coprime with nqb makes
+  // each CTA rotate through all query-block indices while concurrently running CTAs still cover
+  // neighbouring items (K/V of one sequence stay hot in L2).
+  uint32_t ctas = static_cast<uint32_t>(items < slots ? items : slots);
+  if (items > slots) {
+    auto gcd = [](uint32_t x, uint32_t y) {
+      while (y) {
+        const uint32_t t = x % y;
+        x = y;
+        y = t;
+      }
+      return x;
+    };
+    while (ctas > 1 && gcd(ctas, nqb) != 1) --ctas;
+  }
+  const dim3 grid(ctas);
   if (bf16)
     attention_fwd_persistent_kernel<true><<<grid, kAttnThreads, kPersistSmemBytes, stream>>>(
         tmap_q, tmap_k, tmap_v, tmap_o, args);

@@ -166,32 +166,150 @@ def postprocess_arrays(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_
     return ctx_ids, ctx_types, extended, single
 
 
+class FormatLengths(tuple):
+    """(len_ctx, len_ext, len_one): the longest non-padding prefix of the context, extended and
+    single-context layouts; `.rows` holds the same per row (three int32 host arrays) — known on the
+    host for free, they let the towers trim and length-bucket their batches without a device sync."""
+
+    def __new__(cls, max_len, row_len):
+        self = super().__new__(cls, (int(max_len[0]), int(max_len[1]), int(max_len[2])))
+        self.rows = (row_len[0], row_len[1], row_len[2])
+        return self
+
+
+class _Staging(object):
+    """Two alternating host blocks per output shape (pinned when the target is a CUDA device), each
+    guarded by an event recorded after its upload, so a block is never rewritten while the copy engine
+    may still be reading it."""
+
+    def __init__(self):
+        self.slots = {}
+
+    def acquire(self, n_elems, pinned):
+        key = (n_elems, pinned)
+        ring = self.slots.setdefault(key, {"next": 0, "blocks": [None, None]})
+        i = ring["next"]
+        ring["next"] = 1 - i
+        slot = ring["blocks"][i]
+        if slot is None:
+            slot = {"host": torch.empty(n_elems, dtype=torch.int64, pin_memory=pinned), "event": None}
+            ring["blocks"][i] = slot
+        if slot["event"] is not None:
+            slot["event"].synchronize()
+        return slot
+
+
+_STAGING = _Staging()
+
+
+def flatten_topk(topk_evidence_data):
+    """Nested retriever output -> the flat arrays emdr2_format_passages takes: candidate ranges per
+    question, candidate ids, [title_len, n_docs, main_idx, doc_len*3] per candidate, and one token
+    buffer holding every candidate's title followed by its passages."""
+    cand_begin = np.zeros(len(topk_evidence_data) + 1, dtype=np.int32)
+    ids, meta, pieces = [], [], []
+    for bi, (topkids, text_list) in enumerate(topk_evidence_data):
+        for eid, (doc_list, main_idx, title_ids) in zip(topkids, text_list):
+            nd = len(doc_list)
+            if not 1 <= nd <= 3:
+                raise ValueError("a passage comes with 1..3 paragraphs (itself and its neighbours), got %d" % nd)
+            ids.append(eid)
+            pieces.append(title_ids)
+            pieces.extend(doc_list)
+            meta.append((len(title_ids), nd, main_idx, len(doc_list[0]),
+                         len(doc_list[1]) if nd > 1 else 0, len(doc_list[2]) if nd > 2 else 0))
+        cand_begin[bi + 1] = len(ids)
+    cand_id = np.asarray(ids, dtype=np.int64)
+    cand_meta = np.asarray(meta, dtype=np.int32).reshape(-1, 6)
+    if pieces:
+        tokens = np.concatenate([p if isinstance(p, np.ndarray) else np.asarray(p, dtype=np.int64) for p in pieces])
+        tokens = np.ascontiguousarray(tokens, dtype=np.int64)
+    else:
+        tokens = np.zeros(0, dtype=np.int64)
+    return cand_begin, cand_id, cand_meta, tokens
+
+
+def format_passages_native(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data, topk_retrievals,
+                           seq_length_ret, seq_length, cls_id, sep_id, pad_id, out=None):
+    """`postprocess_arrays` through the library's host entry point emdr2_format_passages (one C call
+    instead of B*K Python iterations).  `out`: optional flat int64 host buffer of
+    rows*(2*seq_length_ret + 2*seq_length) elements to write into (e.g. pinned staging memory).
+    Returns ((ctx_ids, ctx_types, extended, single) as numpy views of the buffer, FormatLengths).
+    Raises ValueError where `postprocess_arrays` does."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    uid = np.ascontiguousarray(np.asarray(query_uid, dtype=np.int64).reshape(-1))
+    bsz = int(uid.shape[0])
+    k_keep = int(topk_retrievals)
+    q = np.ascontiguousarray(np.asarray(query_ids_t5, dtype=np.int64).reshape(bsz, -1))
+    q_len = np.ascontiguousarray(np.asarray(query_ids_t5_len, dtype=np.int64).reshape(-1))
+    if len(topk_evidence_data) != bsz or q_len.shape[0] != bsz:
+        raise ValueError("batch size mismatch between questions and retrieved evidence")
+    cand_begin, cand_id, cand_meta, tokens = flatten_topk(topk_evidence_data)
+    rows = bsz * k_keep
+    n_ret, n_seq = rows * seq_length_ret, rows * seq_length
+    if out is None:
+        out = np.empty(2 * n_ret + 2 * n_seq, dtype=np.int64)
+    assert out.dtype == np.int64 and out.size >= 2 * n_ret + 2 * n_seq and out.flags["C_CONTIGUOUS"]
+    ctx_ids = out[:n_ret].reshape(bsz, k_keep, seq_length_ret)
+    extended = out[n_ret:n_ret + n_seq].reshape(rows, seq_length)
+    single = out[n_ret + n_seq:n_ret + 2 * n_seq].reshape(rows, seq_length)
+    ctx_types = out[n_ret + 2 * n_seq:2 * n_ret + 2 * n_seq].reshape(bsz, k_keep, seq_length_ret)
+    max_len = np.zeros(3, dtype=np.int32)
+    row_len = np.zeros((3, rows), dtype=np.int32)
+    ptr = lambda a: ctypes.c_void_p(a.ctypes.data)   # noqa: E731
+    rc = lib.emdr2_format_passages(bsz, k_keep, ptr(uid), ptr(q), q.shape[1], ptr(q_len), ptr(cand_begin),
+                                   ptr(cand_id), ptr(cand_meta), ptr(tokens), tokens.shape[0],
+                                   int(seq_length_ret), int(seq_length), int(cls_id), int(sep_id), int(pad_id),
+                                   ptr(ctx_ids), ptr(ctx_types), ptr(extended), ptr(single), ptr(max_len),
+                                   ptr(row_len))
+    if rc != 0:
+        msg = lib.emdr2_last_error().decode("utf-8", "replace")
+        raise ValueError(msg)
+    return (ctx_ids, ctx_types, extended, single), FormatLengths(max_len, row_len)
+
+
 def postprocess(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data, topk_retrievals,
                 seq_length_ret, seq_length, cls_id, sep_id, pad_id, device=None, return_lengths=False):
     """Drop-in for emdr2_model.py:250-303 with the tokenizer ids / lengths passed explicitly
     (the reference reads them from get_args()/get_t5_tokenizer()).  Returns four int64 tensors on
-    `device` (default: current CUDA device)."""
+    `device` (default: current CUDA device).  The rows are assembled by the library's host entry
+    point (`format_passages_native`) directly in pinned staging memory and uploaded with ONE
+    asynchronous copy (the all-zero token-type tensor is created on the device)."""
     if torch.is_tensor(query_uid):
         query_uid = query_uid.tolist()
     if torch.is_tensor(query_ids_t5):
         query_ids_t5 = query_ids_t5.cpu().numpy()
     if torch.is_tensor(query_ids_t5_len):
         query_ids_t5_len = query_ids_t5_len.tolist()
-    arrays = postprocess_arrays(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data,
-                                topk_retrievals, seq_length_ret, seq_length, cls_id, sep_id, pad_id)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    out = []
-    for a in arrays:
-        t = torch.from_numpy(a)
-        if torch.device(device).type == "cuda":
-            t = t.pin_memory().to(device, non_blocking=True)
-        out.append(t)
+    device = torch.device(device)
+    on_gpu = device.type == "cuda"
+    bsz, k_keep = len(query_uid), int(topk_retrievals)
+    rows = bsz * k_keep
+    n_ret, n_seq = rows * seq_length_ret, rows * seq_length
+    slot = _STAGING.acquire(2 * n_ret + 2 * n_seq, on_gpu)
+    host = slot["host"]
+    _, lengths = format_passages_native(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data,
+                                        topk_retrievals, seq_length_ret, seq_length, cls_id, sep_id, pad_id,
+                                        out=host.numpy())
+    if on_gpu:
+        with torch.cuda.device(device):
+            dev = host[:n_ret + 2 * n_seq].to(device, non_blocking=True)
+            if slot["event"] is None:
+                slot["event"] = torch.cuda.Event()
+            slot["event"].record()
+        types = torch.zeros((bsz, k_keep, seq_length_ret), dtype=torch.int64, device=device)
+    else:
+        dev = host[:n_ret + 2 * n_seq].clone()
+        types = host[n_ret + 2 * n_seq:2 * n_ret + 2 * n_seq].clone().reshape(bsz, k_keep, seq_length_ret)
+    out = (dev[:n_ret].reshape(bsz, k_keep, seq_length_ret), types,
+           dev[n_ret:n_ret + n_seq].reshape(rows, seq_length),
+           dev[n_ret + n_seq:n_ret + 2 * n_seq].reshape(rows, seq_length))
     if return_lengths:
         # longest non-padding prefix of each tensor, known on the host for free: lets the caller run
         # the towers on [:, :max_len] instead of the padded width without a device sync
-        def longest(a):
-            a2 = a.reshape(-1, a.shape[-1])
-            return int(((a2 != pad_id) * np.arange(1, a2.shape[1] + 1)).max()) if a2.size else 0
-        return tuple(out), (longest(arrays[0]), longest(arrays[2]), longest(arrays[3]))
-    return tuple(out)
+        return out, lengths
+    return out

@@ -43,9 +43,9 @@ class DualEncoder(nn.Module):
             self.context_model = BertTower(cfg, num_tokentypes=2, vocab_size=bert_vocab_size)
 
     @staticmethod
-    def embed_text(model, tokens, attention_mask, token_types, max_len=None):
-        """dualencoder_model.py:76-82."""
-        return model(tokens, attention_mask, token_types, max_len=max_len)
+    def embed_text(model, tokens, attention_mask, token_types, max_len=None, row_lengths=None):
+        """dualencoder_model.py:76-82 (+ the host-known lengths that let the tower trim / bucket)."""
+        return model(tokens, attention_mask, token_types, max_len=max_len, row_lengths=row_lengths)
 
     def forward(self, query_tokens, query_attention_mask, query_types, context_tokens,
                 context_attention_mask, context_types):
@@ -62,7 +62,9 @@ class EMDR2Model(nn.Module):
     topk_retrievals, seq_length, seq_length_ret, retriever_score_scaling, update_retriever,
     cls_id, sep_id, pad_id; trim_padding (default True) runs the towers only on the columns that hold
     a real token in at least one sequence of the batch (lengths are known on the host from the
-    formatter), which leaves every non-padding position unchanged."""
+    formatter), and length_buckets (default True) additionally lets the towers sort the B*K rows by
+    length and run them as a few token-packed buckets (blocks.py: `encode`); both leave every
+    non-padding position unchanged."""
 
     def __init__(self, cfg, evidence_retriever, settings, t5_vocab_size=None, bert_vocab_size=None):
         super().__init__()
@@ -75,12 +77,13 @@ class EMDR2Model(nn.Module):
         self._retriever_model_key = 'retriever/biencoder_model'
         self.evidence_retriever = evidence_retriever
 
-    def retriever_embedder(self, tokens, mask, types, embedder_type, disable_dropout=False, max_len=None):
+    def retriever_embedder(self, tokens, mask, types, embedder_type, disable_dropout=False, max_len=None,
+                           row_lengths=None):
         m = self.retriever_model
         if embedder_type == "query":
-            return m.embed_text(m.query_model, tokens, mask, types, max_len=max_len)
+            return m.embed_text(m.query_model, tokens, mask, types, max_len=max_len, row_lengths=row_lengths)
         if embedder_type == "context":
-            return m.embed_text(m.context_model, tokens, mask, types, max_len=max_len)
+            return m.embed_text(m.context_model, tokens, mask, types, max_len=max_len, row_lengths=row_lengths)
         raise ValueError("Invalid embedder type.")
 
     def forward(self, query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5,
@@ -92,7 +95,7 @@ class EMDR2Model(nn.Module):
         hidden = self.cfg["hidden"]
         seq_length = int(st["seq_length"])
         query_one_context_ids = None
-        len_one = None
+        len_one = rows_one = None
 
         if all_query_context_hidden_states is None:
             query_logits = self.retriever_embedder(query_ids_bert, query_mask_bert, query_types, "query")
@@ -103,17 +106,21 @@ class EMDR2Model(nn.Module):
                 else:
                     topk_evidence_data, _stale = self.evidence_retriever.get_topk(query_logits.clone().detach())
                 (all_context_ids, all_context_types, all_query_extended_context_ids, query_one_context_ids), \
-                    (len_ctx, len_ext, len_one) = \
+                    lengths = \
                     formatter.postprocess(query_uid, query_ids_t5, query_ids_t5_len, topk_evidence_data,
                                           topk, int(st["seq_length_ret"]), seq_length, st["cls_id"],
                                           st["sep_id"], st["pad_id"], device=query_ids_bert.device,
                                           return_lengths=True)
+                len_ctx, len_ext, len_one = lengths
+                rows_ctx, rows_ext, rows_one = lengths.rows
                 if not st.get("trim_padding", True):
-                    len_ctx = len_ext = len_one = None
+                    len_ctx = len_ext = len_one = rows_ctx = rows_ext = rows_one = None
+                elif not st.get("length_buckets", True):
+                    rows_ctx = rows_ext = rows_one = None
             s_ret = all_context_ids.shape[-1]
             all_context_logits = self.retriever_embedder(all_context_ids.reshape(-1, s_ret), None,
                                                          all_context_types.reshape(-1, s_ret), "context",
-                                                         max_len=len_ctx)
+                                                         max_len=len_ctx, row_lengths=rows_ctx)
             all_context_logits = all_context_logits.reshape(bsize, topk, -1).float()
             topk_sim_scores = torch.bmm(query_logits.unsqueeze(1).float(), all_context_logits.transpose(1, 2))
             if st.get("retriever_score_scaling", True):
@@ -123,7 +130,7 @@ class EMDR2Model(nn.Module):
             # Padding columns shared by all B*K rows are not computed (trim_padding): the FiD key axis is
             # then K * s' instead of the reference's K * seq_length, with the ids trimmed alike.
             enc = self.language_model(all_query_extended_context_ids, dec_ids, output_enc_hidden=True,
-                                      enc_max_len=len_ext)
+                                      enc_max_len=len_ext, enc_row_lengths=rows_ext)
             s_enc = enc.shape[1]
             all_query_context_hidden_states = enc.reshape(bsize, topk * s_enc, hidden)
             all_query_context_ids_unflat = all_query_extended_context_ids[:, :s_enc].reshape(bsize, topk * s_enc)
@@ -136,7 +143,8 @@ class EMDR2Model(nn.Module):
             if st.get("update_retriever", False) and query_one_context_ids is not None:
                 with torch.no_grad():       # "SG": no gradient through the one-context pass (:186)
                     dec_ids_repeated = torch.repeat_interleave(dec_ids, topk, dim=0)
-                    flat, _ = self.language_model(query_one_context_ids, dec_ids_repeated, enc_max_len=len_one)
+                    flat, _ = self.language_model(query_one_context_ids, dec_ids_repeated, enc_max_len=len_one,
+                                                  enc_row_lengths=rows_one)
                     lm_logits_one_context = flat.reshape(bsize, topk, flat.shape[1], flat.shape[2])
             return lm_logits, topk_log_probs, lm_logits_one_context
         return lm_logits, topk_log_probs, all_query_context_hidden_states, all_query_context_ids_unflat

@@ -222,6 +222,35 @@ EMDR2_API int emdr2_embedding_bwd(int dtype, const void* dx, const int64_t* ids,
                                   float* dword, float* dpos, float* dtype_emb, int tokens, int seq, int h,
                                   int vocab, int num_types, void* cuda_stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Host-side integer work of the step (no device code, callable without a GPU).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Passage -> model-input formatting for one batch: replaces the B*K Python iterations of
+ * EMDR2Model.postprocess (megatron/model/emdr2_model.py:250-303) and the list builders it calls -
+ * context_bert_format (megatron/data/orqa_wiki_dataset.py:86-120), query_extended_context_t5_format
+ * (emdr2_model.py:306-361) and query_single_context_t5_format (:364-376) - element for element.
+ *   query_uid [bsz], query_ids [bsz, query_stride] with query_len [bsz] valid tokens per row;
+ *   candidates of question b are cand_begin[b] .. cand_begin[b+1]-1 (k or k+1 of them, best first);
+ *   cand_id [n_cand] evidence ids (a candidate whose id equals the question's uid is dropped, as are
+ *   candidates beyond the first k_keep kept ones); cand_meta [n_cand, 6] = title_len, n_docs (1..3:
+ *   the passage and its neighbours, inverted_title_index.py:22-37), main_idx (0, 1 or -1: which of
+ *   them is the passage), doc_len[3]; tokens = every candidate's title followed by its docs, back to
+ *   back (n_tokens in total).
+ * Outputs (host memory, caller-owned, fully overwritten): ctx_ids / ctx_types [bsz, k_keep, seq_ret],
+ * extended / single [bsz*k_keep, seq]; max_len[3] (optional) = longest non-padding prefix in ctx_ids,
+ * extended, single; row_len [3, bsz*k_keep] (optional) = that prefix length for every row of the
+ * three layouts (what lets the towers run length-bucketed without a device sync).  EMDR2_EINVAL when a question keeps fewer than k_keep candidates or
+ * question + title do not fit in seq (the reference would build a ragged tensor / overflow there). */
+EMDR2_API int emdr2_format_passages(int32_t bsz, int32_t k_keep, const int64_t* query_uid,
+                                    const int64_t* query_ids, int64_t query_stride,
+                                    const int64_t* query_len, const int32_t* cand_begin,
+                                    const int64_t* cand_id, const int32_t* cand_meta,
+                                    const int64_t* tokens, int64_t n_tokens, int32_t seq_ret,
+                                    int32_t seq, int64_t cls_id, int64_t sep_id, int64_t pad_id,
+                                    int64_t* ctx_ids, int64_t* ctx_types, int64_t* extended,
+                                    int64_t* single, int32_t* max_len, int32_t* row_len);
+
 /* Measurement aid: with timing enabled every launch of the block operators made by this
  * process is bracketed by CUDA events on its stream (backward passes run on autograd worker threads).  emdr2_ops_timing_read sums the launch
  * durations (ns), launch count and algorithmic FLOPs of one kernel kind since the last read and

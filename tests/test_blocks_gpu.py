@@ -159,3 +159,65 @@ def test_reference_checkpoint_layout_loads():
         assert torch.equal(p.detach().cpu(), flat[n].to(torch.float16))
     with pytest.raises(KeyError):
         load_reference_state_dict(model, {"bogus.weight": torch.zeros(1)})
+
+
+# ------------------------------------------------------------------ length-bucketed execution
+def _ragged_batch(b, s, vocab, seed, lo=3):
+    rng = np.random.RandomState(seed)
+    ids = rng.randint(1, vocab, size=(b, s)).astype(np.int64)
+    lens = rng.randint(lo, s + 1, size=b)
+    lens[rng.randint(0, b)] = s
+    for i, n in enumerate(lens):
+        ids[i, n:] = 0
+    types = (rng.rand(b, s) < 0.5).astype(np.int64) * (ids > 0)
+    return torch.from_numpy(ids), torch.from_numpy(types), lens
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_length_bucketed_encoder_equals_the_rectangular_run_at_every_token(dtype):
+    """Sorting rows by length into token-packed buckets (blocks.py: encode) leaves every non-padding
+    position bit-identical (cut columns are padding in every member of the bucket; GEMM and LayerNorm
+    rows are independent) and stores zeros at padding positions."""
+    from emdr2_b200.blocks import BertTower
+    model = BertTower(_cfg(dtype)).to(DEV)
+    _fill(model, dtype)
+    lm = model.language_model
+    ids, types, lens = _ragged_batch(70, 64, TINY["vocab"], 5)
+    lm.bucket_min_rows = 1 << 30
+    plain = lm.encode(ids.to(DEV), types.to(DEV), max_len=int(lens.max()), row_lengths=lens)
+    lm.bucket_min_rows, lm.length_buckets = 8, 3
+    assert lm._bucket_plan(70, 64, lens) is not None
+    with torch.no_grad():
+        fast = lm.encode(ids.to(DEV), types.to(DEV), max_len=int(lens.max()), row_lengths=lens)
+        cls = model(ids.to(DEV), None, types.to(DEV), max_len=int(lens.max()), row_lengths=lens)
+    live = ids > 0
+    assert fast.shape == plain.shape
+    assert torch.equal(fast.cpu()[live], plain.detach().cpu()[live])
+    assert (fast.cpu()[~live] == 0).all()
+    assert torch.equal(cls, plain.detach()[:, 0, :])
+
+
+def test_length_bucketed_encoder_backward_matches_the_rectangular_run():
+    from emdr2_b200.blocks import BertTower
+    dtype = torch.float16
+    model = BertTower(_cfg(dtype)).to(DEV)
+    _fill(model, dtype)
+    lm = model.language_model
+    ids, types, lens = _ragged_batch(40, 48, TINY["vocab"], 9)
+    weight = torch.randn(40, TINY["hidden"], generator=torch.Generator().manual_seed(1)).to(DEV)
+
+    def grads(bucketed):
+        lm.bucket_min_rows, lm.length_buckets = (8, 4) if bucketed else (1 << 30, 4)
+        for p in model.parameters():
+            p.grad = None
+        out = model(ids.to(DEV), None, types.to(DEV), max_len=int(lens.max()), row_lengths=lens)
+        (out.float() * weight).sum().backward()
+        return out.detach(), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    out_a, g_a = grads(False)
+    out_b, g_b = grads(True)
+    assert torch.equal(out_a, out_b)
+    assert sorted(g_a) == sorted(g_b) and len(g_a) > 10
+    for n in g_a:        # same products, different summation order over the (re-ordered) tokens
+        denom = g_a[n].norm().item() + 1e-6
+        assert (g_a[n] - g_b[n]).norm().item() / denom < 5e-3, n

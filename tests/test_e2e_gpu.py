@@ -165,6 +165,17 @@ def test_retrieve_and_read_forward_tiny(tmp_path, dtype):
     assert full[2].shape == (bsz, TOPK * S, TINY["hidden"])
     assert torch.equal(full[0][live], lm_logits[live]) and torch.equal(full[1], topk_log_probs)
 
+    # length-bucketed towers (blocks.py: encode; forced on for this small batch) do not either
+    towers = (model.language_model.language_model, model.retriever_model.context_model.language_model)
+    for lm in towers:
+        lm.bucket_min_rows, lm.length_buckets = 4, 3
+    bucketed = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV), torch.tensor(q_len).to(DEV),
+                     dec.to(DEV))
+    for lm in towers:
+        del lm.bucket_min_rows, lm.length_buckets
+    assert bucketed[2].shape == ev[2].shape
+    assert torch.equal(bucketed[0][live], lm_logits[live]) and torch.equal(bucketed[1], topk_log_probs)
+
     # ---- losses (a10) on the GPU logits vs fp32 torch on the oracle logits
     lm_loss = losses.reader_cross_entropy(lm_logits, labels.to(DEV), loss_mask.to(DEV))
     want_lm = (torch.nn.functional.cross_entropy(want_logits.view(-1, TINY["vocab"]), labels.view(-1),

@@ -98,6 +98,92 @@ def test_postprocess_shapes_filtering_and_rows():
         formatter.postprocess_arrays(uids, qt5, qlen, [(i[:2], x[:2]) for i, x in topk_data], k, 32, 64, 2, 3, 0)
 
 
+def test_native_formatter_is_identical_to_the_reference_on_every_golden_case():
+    """emdr2_format_passages (C, host) against the fixtures the reference's own functions produced."""
+    n = 0
+    for c in cases():
+        if len(c["query"]) + len(c["title"]) + 2 > c["max_len"]:
+            continue
+        data = [([1], [([np.array(d, dtype=np.int64) for d in c["docs"]], c["main"], np.array(c["title"], dtype=np.int64))])]
+        q = c["query"] + [0] * 4
+        (ctx, typ, ext, one), lens = formatter.format_passages_native([-1], [q], [len(c["query"])], data, 1,
+                                                                      c["max_len"], c["max_len"], 2, 3, 0)
+        assert ext[0].tolist() == c["extended"], c
+        assert one[0].tolist() == c["single"], c
+        assert ctx[0, 0].tolist() == c["bert"][0] and typ[0, 0].tolist() == c["bert"][1], c
+        n += 1
+    assert n > 100
+
+
+def _random_batch(rng, b, k, seq_ret, seq, extra, lists):
+    uids, qt5, qlen, topk_data = [], [], [], []
+    for bi in range(b):
+        n = int(rng.randint(0, 12))
+        q = rng.randint(1, 50, size=n).tolist()
+        qt5.append(q + [0] * (16 - n))
+        qlen.append(n)
+        ids = rng.choice(np.arange(1, 400), size=k + extra, replace=False).tolist()
+        uid = ids[int(rng.randint(0, k + extra))] if (extra and rng.rand() < 0.5) else -(bi + 1)
+        uids.append(uid)
+        texts = []
+        for _ in ids:
+            nd = int(rng.randint(1, 4))
+            # token 0 (= pad id) appears inside passages now and then: exercises the length rule
+            docs = [rng.randint(0, 60, size=int(rng.randint(0, 40))).astype(np.int64) for _ in range(nd)]
+            main = [0, 1, -1][int(rng.randint(0, 3))] if nd > 1 else [0, -1][int(rng.randint(0, 2))]
+            if main == 1 and nd < 2:
+                main = 0
+            title = rng.randint(1, 60, size=int(rng.randint(0, 6))).astype(np.int64)
+            if lists:
+                docs, title = [d.tolist() for d in docs], title.tolist()
+            texts.append((docs, main, title))
+        topk_data.append((ids, texts))
+    return uids, qt5, qlen, topk_data
+
+
+@pytest.mark.parametrize("lists", [False, True])
+def test_native_formatter_matches_the_python_restatement_on_random_batches(lists):
+    rng = np.random.RandomState(7)
+    for trial in range(60):
+        b, k = int(rng.randint(1, 5)), int(rng.randint(1, 6))
+        seq_ret, seq = int(rng.randint(20, 60)), int(rng.randint(32, 120))
+        uids, qt5, qlen, data = _random_batch(rng, b, k, seq_ret, seq, extra=1, lists=lists)
+        want = formatter.postprocess_arrays(uids, qt5, qlen, data, k, seq_ret, seq, 2, 3, 0)
+        got, lens = formatter.format_passages_native(uids, qt5, qlen, data, k, seq_ret, seq, 2, 3, 0)
+        for w, g in zip(want, got):
+            assert w.shape == g.shape and np.array_equal(w, g), trial
+
+        def longest(a):
+            a2 = a.reshape(-1, a.shape[-1])
+            return int(((a2 != 0) * np.arange(1, a2.shape[1] + 1)).max()) if a2.size else 0
+        assert lens == (longest(want[0]), longest(want[2]), longest(want[3]))
+        for per_row, w in zip(lens.rows, (want[0], want[2], want[3])):
+            w2 = w.reshape(-1, w.shape[-1])
+            assert np.array_equal(per_row, ((w2 != 0) * np.arange(1, w2.shape[1] + 1)).max(axis=1))
+
+
+def test_native_formatter_errors_and_staging_reuse():
+    rng = np.random.RandomState(3)
+    uids, qt5, qlen, data = _random_batch(rng, 2, 3, 32, 64, extra=0, lists=False)
+    with pytest.raises(ValueError, match="kept 2 of 3"):
+        formatter.format_passages_native(uids, qt5, qlen, [(i[:2], x[:2]) for i, x in data], 3, 32, 64, 2, 3, 0)
+    long_q = [list(range(1, 17))] * 2
+    with pytest.raises(ValueError, match="do not fit"):
+        formatter.format_passages_native(uids, long_q, [16, 16], data, 3, 32, 18, 2, 3, 0)
+    with pytest.raises(ValueError):
+        formatter.postprocess_arrays(uids, long_q, [16, 16], data, 3, 32, 18, 2, 3, 0)
+    # postprocess() cycles through two staging blocks: results of consecutive calls stay distinct
+    first = formatter.postprocess(uids, qt5, qlen, data, 3, 32, 64, 2, 3, 0, device="cpu")
+    uids2, qt52, qlen2, data2 = _random_batch(rng, 2, 3, 32, 64, extra=0, lists=False)
+    second = formatter.postprocess(uids2, qt52, qlen2, data2, 3, 32, 64, 2, 3, 0, device="cpu")
+    third, lens = formatter.postprocess(uids, qt5, qlen, data, 3, 32, 64, 2, 3, 0, device="cpu", return_lengths=True)
+    want = formatter.postprocess_arrays(uids, qt5, qlen, data, 3, 32, 64, 2, 3, 0)
+    for a, b_, w in zip(first, third, want):
+        assert torch.equal(a, b_) and np.array_equal(a.numpy(), w)
+    assert not torch.equal(first[2], second[2])
+    assert len(lens) == 3
+
+
 def _loss_golden():
     with np.load(os.path.join(GOLDEN, "losses_ref.npz")) as z:
         return {k: torch.from_numpy(z[k]) if z[k].ndim else z[k] for k in z.files}

@@ -163,3 +163,17 @@ def test_sharded_search_world2_gloo_equals_unsharded_oracle(tmp_path, n):
     for rank in range(world):
         assert np.array_equal(r[rank]["mine"], i[3 * rank:3 * rank + 3].astype(np.int32))
         assert r[rank]["dist"].dtype == np.float16
+
+
+def test_bucket_plan_is_a_partition_sorted_by_length():
+    from emdr2_b200.blocks import TransformerLanguageModel
+    lm = TransformerLanguageModel.__new__(TransformerLanguageModel)      # plan is pure host arithmetic
+    lens = np.random.RandomState(0).randint(1, 200, size=333)
+    plan = lm._bucket_plan(333, 256, lens)
+    rows = np.concatenate([idx for idx, _ in plan])
+    assert sorted(rows.tolist()) == list(range(333))
+    assert all(w % 8 == 0 and w <= 256 and lens[idx].max() <= w for idx, w in plan)
+    assert [w for _, w in plan] == sorted(w for _, w in plan) and 1 < len(plan) <= lm.length_buckets
+    assert lm._bucket_plan(32, 256, lens[:32]) is None                   # small batches run as one rectangle
+    assert lm._bucket_plan(333, 256, None) is None
+    assert lm._bucket_plan(100, 256, np.full(100, 77)) is None           # equal lengths: nothing to bucket
