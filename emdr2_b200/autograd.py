@@ -277,10 +277,58 @@ def self_attention(qkv, batch, heads, seq, pad=None, live=None, causal=False, sc
                          causal=causal, scale=scale, q_live=live, k_live=live)
 
 
+#: Key-split ("flash-decoding") of long cross-attention in the no-grad path: with few (batch, head)
+#: pairs and a very long key axis (FiD: 8 questions x 12 heads over 50 x 512 = 25 600 keys) one CTA per
+#: pair would walk 200 key blocks while two thirds of the GPU idle.  The key axis is cut into
+#: `splits` contiguous ranges that run as extra batch entries of the same kernel; the partial outputs
+#: are merged with their log-sum-exp weights.  Applies when sk >= CROSS_SPLIT_MIN_KEYS.
+CROSS_SPLIT_MIN_KEYS = 4096
+CROSS_SPLIT_TARGET_ITEMS = 888        # ~3 work items per resident CTA (2 x 148)
+
+
+def _cross_splits(batch, heads, sk):
+    """Number of key ranges (a divisor of the 128-key block count), 1 = do not split."""
+    if sk < CROSS_SPLIT_MIN_KEYS or sk % 128 or batch * heads * 2 > CROSS_SPLIT_TARGET_ITEMS:
+        return 1
+    nblk = sk // 128
+    want = max(1, CROSS_SPLIT_TARGET_ITEMS // (batch * heads))
+    best = 1
+    for s in range(2, min(nblk // 4, 64) + 1):          # keep at least 4 key blocks per range
+        if nblk % s == 0 and abs(s - want) < abs(best - want):
+            best = s
+    return best
+
+
+def _cross_attention_split(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, splits):
+    h = heads * 64
+    dev = q.device
+    sk_s = sk // splits
+    q_rep = q.reshape(batch, 1, sq, h).expand(batch, splits, sq, h).reshape(batch * splits * sq, h)
+
+    def rep(m):          # per-query masks are shared by the ranges of a question
+        return None if m is None else _u8(m, dev).repeat_interleave(splits, dim=0)
+
+    k_pad_s = None if k_pad is None else _u8(k_pad, dev).reshape(batch * splits, sk_s)
+    k_live_s = None
+    if k_live is not None:
+        k_live_s = _u8(k_live, dev).reshape(batch * splits, sk_s // 128).clone()
+        k_live_s[:, 0] = 1                         # the kernel wants one live block per entry; an
+        #                                            all-padding range then weighs exp(-10000) = 0
+    out, lse = ops.attention(q_rep, kv[:, :h], kv[:, h:], batch * splits, heads, sq, sk_s, q_pad=rep(q_pad),
+                             k_pad=k_pad_s, scale=scale, return_lse=True, q_live=rep(q_live), k_live=k_live_s)
+    w = torch.softmax(lse.view(batch, splits, heads, sq), dim=1)              # fp32 [B, splits, heads, sq]
+    w = w.permute(0, 1, 3, 2).unsqueeze(-1)                                    # [B, splits, sq, heads, 1]
+    merged = (out.view(batch, splits, sq, heads, 64).float() * w).sum(dim=1)
+    return merged.to(q.dtype).view(batch * sq, h)
+
+
 def cross_attention(q, kv, batch, heads, sq, sk, q_pad=None, k_pad=None, q_live=None, k_live=None, scale=0.125):
     if _needs_grad(q, kv):
         return _CrossAttentionFn.apply(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale)
     h = heads * 64
+    splits = _cross_splits(batch, heads, sk)
+    if splits > 1:
+        return _cross_attention_split(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, splits)
     return ops.attention(q, kv[:, :h], kv[:, h:], batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad, scale=scale,
                          q_live=q_live, k_live=k_live)
 

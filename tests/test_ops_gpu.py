@@ -272,3 +272,34 @@ def test_gemm_ex_preactivation_and_gelu_backward(dtype):
     uu = pre.float().requires_grad_(True)
     torch.nn.functional.gelu(uu).backward(dy.float() @ w2.float())
     assert torch.allclose(got, uu.grad, rtol=2 * tol, atol=2 * tol), (got - uu.grad).abs().max().item()
+
+
+# ---------------------------------------------------------------- key-split cross-attention
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_key_split_cross_attention_matches_the_single_pass(dtype):
+    """FiD-shaped cross-attention (few questions, very long key axis) runs as several key ranges merged
+    by their log-sum-exp weights (autograd.py: _cross_attention_split); one whole range is padding."""
+    from emdr2_b200 import autograd as ag
+    from emdr2_b200 import ops
+    batch, heads, sq, sk = 3, 2, 20, 40 * 128
+    w = heads * 64
+    q = _rand((batch * sq, w), dtype, 71, scale=1.5)
+    kv = _rand((batch * sk, 2 * w), dtype, 72)
+    k_pad = torch.zeros(batch, sk, dtype=torch.bool, device=DEV)
+    k_pad[0, 3000:] = True                     # question 0: the last ranges are padding only
+    k_pad[1, 100:1500] = True                  # question 1: a hole early on
+    q_pad = torch.zeros(batch, sq, dtype=torch.bool, device=DEV)
+    q_pad[2, 15:] = True
+    splits = ag._cross_splits(batch, heads, sk)
+    assert splits > 1 and (sk // 128) % splits == 0
+    for live in (False, True):
+        k_live = ops.live_blocks(k_pad) if live else None
+        q_live = ops.live_blocks(q_pad) if live else None
+        got = ag.cross_attention(q, kv, batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad, q_live=q_live, k_live=k_live)
+        want = ops.attention(q, kv[:, :w], kv[:, w:], batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad,
+                             q_live=q_live, k_live=k_live)
+        ref, _ = _ref_attention(q, kv[:, :w].contiguous(), kv[:, w:].contiguous(), batch, heads, sq, sk, q_pad, k_pad, False)
+        keep = ~q_pad.reshape(-1)
+        tol = 2 ** -6 if dtype == torch.bfloat16 else 2 ** -9
+        assert torch.allclose(got.float()[keep], want.float()[keep], rtol=tol, atol=tol)
+        assert torch.allclose(got.float()[keep], ref[keep], rtol=tol, atol=tol)
