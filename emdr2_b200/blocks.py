@@ -261,7 +261,8 @@ class TransformerLanguageModel(nn.Module):
         matrix: every GEMM / LayerNorm runs once over T rows (T ~ 0.85-0.9 of b*s' on NQ-shaped
         batches; no wave-quantisation loss from splitting), only attention runs per group on its
         slice.  Cut columns are padding in every member of the group, so non-padding positions are
-        unchanged; padding positions of the returned states are zero."""
+        unchanged; the cut columns of the returned states are zero (no consumer reads padding
+        positions: the decoder masks them through the ids)."""
         s_keep = self.trimmed_width(ids.shape[1], max_len)
         if s_keep != ids.shape[1]:
             ids = ids[:, :s_keep].contiguous()
