@@ -77,7 +77,31 @@ struct ScopedTimer {
 
 }  // namespace
 
+// 1: large forward products use the CTA-pair kernel (gemm_pair.cu); 0: always the one-CTA kernel.
+static std::atomic<int> g_gemm_pair{[] {
+  const char* e = getenv("EMDR2_GEMM_PAIR");
+  return (e && e[0] == '1') ? 1 : 0;
+}()};
+
 extern "C" {
+
+int emdr2_ops_set_option(const char* name, int64_t value) {
+  if (!name) return fail(EMDR2_EINVAL, "NULL option name");
+  if (strcmp(name, "gemm_pair") == 0) {
+    g_gemm_pair.store(value != 0 ? 1 : 0, std::memory_order_relaxed);
+    return EMDR2_OK;
+  }
+  return fail(EMDR2_EINVAL, "unknown option '%s'", name);
+}
+
+int emdr2_ops_get_option(const char* name, int64_t* out_value) {
+  if (!name || !out_value) return fail(EMDR2_EINVAL, "NULL argument");
+  if (strcmp(name, "gemm_pair") == 0) {
+    *out_value = g_gemm_pair.load(std::memory_order_relaxed);
+    return EMDR2_OK;
+  }
+  return fail(EMDR2_EINVAL, "unknown option '%s'", name);
+}
 
 int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn,
                   void* d, int64_t ldd, const void* bias, const void* aux, int64_t ld_aux, void* preact,
@@ -118,13 +142,20 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
   static bool prepared[64] = {};
   if (!prepared[info.device]) {
     CUDA_TRY(emdr2::gemm_prepare());
+    CUDA_TRY(emdr2::gemm_pair_prepare());
     prepared[info.device] = true;
   }
   CUtensorMap ta, tb, td, tr, tp;
+  // Large K-major products with a 16-bit output run on CTA pairs (gemm_pair.cu): 256 x 256 tiles, at
+  // least two per pair so the persistent pipeline has something to overlap.
+  const int64_t pair_tiles = static_cast<int64_t>((m + 255) / 256) * ((n + emdr2::kGemmBN - 1) / emdr2::kGemmBN);
+  const bool use_pair = g_gemm_pair.load(std::memory_order_relaxed) != 0 && !a_mn && !b_mn && !accum &&
+                        splits == 1 && info.sm_count >= 2 && pair_tiles >= 2 * (info.sm_count / 2);
   // K-major operand: [rows, k] with box rows x 64; MN-major: [k, rows] with 64 x 64 boxes
   rc = a_mn ? make_tmap_2d(&ta, dtype, a, k, m, lda, 64) : make_tmap_2d(&ta, dtype, a, m, k, lda, emdr2::kGemmBM);
   if (rc != EMDR2_OK) return rc;
-  rc = b_mn ? make_tmap_2d(&tb, dtype, b, k, n, ldb, 64) : make_tmap_2d(&tb, dtype, b, n, k, ldb, emdr2::kGemmBN);
+  rc = b_mn ? make_tmap_2d(&tb, dtype, b, k, n, ldb, 64)
+            : make_tmap_2d(&tb, dtype, b, n, k, ldb, use_pair ? emdr2::kGemmBN / 2 : emdr2::kGemmBN);
   if (rc != EMDR2_OK) return rc;
   if (accum) {
     td = tb;   // no 16-bit output map needed; any valid descriptor fills the unused slots
@@ -156,6 +187,13 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
   const uint32_t work = ga.tiles_m * ga.tiles_n * ga.splits;
   const int grid = static_cast<int>(work < static_cast<uint32_t>(info.sm_count) ? work : info.sm_count);
   ScopedTimer timer(EMDR2_KIND_GEMM, static_cast<cudaStream_t>(cuda_stream), 2.0 * m * n * k);
+  if (use_pair) {
+    ga.idesc = emdr2::ptx::instr_desc_f16(dtype == EMDR2_DTYPE_BF16 ? 1 : 0, 2 * emdr2::kGemmBM, emdr2::kGemmBN);
+    const int pairs = info.sm_count / 2;
+    CUDA_TRY(emdr2::launch_gemm_pair(ta, tb, td, tr, tp, ga, dtype == EMDR2_DTYPE_BF16, 2 * pairs,
+                                     static_cast<cudaStream_t>(cuda_stream)));
+    return EMDR2_OK;
+  }
   CUDA_TRY(emdr2::launch_gemm(ta, tb, td, tr, tp, ga, dtype == EMDR2_DTYPE_BF16, a_mn != 0, b_mn != 0, grid,
                               static_cast<cudaStream_t>(cuda_stream)));
   return EMDR2_OK;

@@ -66,4 +66,12 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, co
                         const CUtensorMap& tmap_r, const CUtensorMap& tmap_p, const GemmArgs& args,
                         bool bf16, bool a_mn, bool b_mn, int grid, cudaStream_t stream);
 
+// CTA-pair variant (gemm_pair.cu): K-major operands, 16-bit output, no split-K; 256 x 256 tiles shared by
+// two CTAs (tcgen05.mma.cta_group::2).  tmap_b_half: B [N, K] with a 128 x 64 box (each CTA stages half
+// of the tile's B rows).  grid must be even (whole pairs).
+cudaError_t gemm_pair_prepare();
+cudaError_t launch_gemm_pair(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b_half, const CUtensorMap& tmap_d,
+                             const CUtensorMap& tmap_r, const CUtensorMap& tmap_p, const GemmArgs& args,
+                             bool bf16, int grid, cudaStream_t stream);
+
 }  // namespace emdr2

@@ -193,6 +193,18 @@ def token_logprob(logits, labels):
 KIND_GEMM, KIND_ATTENTION, KIND_ROWOP = 0, 1, 2
 
 
+def set_option(name, value):
+    """Process-wide switch of the block operators (include/emdr2_b200.h: emdr2_ops_set_option),
+    e.g. set_option("gemm_pair", 1)."""
+    _lib.check(_lib.load().emdr2_ops_set_option(name.encode(), int(value)), "emdr2_ops_set_option")
+
+
+def get_option(name):
+    v = ctypes.c_int64()
+    _lib.check(_lib.load().emdr2_ops_get_option(name.encode(), ctypes.byref(v)), "emdr2_ops_get_option")
+    return v.value
+
+
 def timing(enable):
     """Bracket every block-operator launch of this thread with CUDA events (measurement aid)."""
     _lib.check(_lib.load().emdr2_ops_timing(1 if enable else 0), "emdr2_ops_timing")
