@@ -239,7 +239,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                   static_cast<int32_t>((t % a.tiles_n) * kGemmBN + hh * 128 + ch * 64),
                   static_cast<int32_t>((t / a.tiles_n) * kGemmBM), kEvictNormal);
     };
-    if (has_res && !out_f32 && issuer && chunk_live(blockIdx.x, 0)) load_residual(blockIdx.x, 0);
+    // First live chunk at or after (w, ch) in this column half's processing order (ragged N: the
+    // chunks of the last column tile may be past the end for one half); w >= num_work if none.
+    auto next_live_chunk = [&](uint32_t& w, uint32_t& ch) {
+      while (w < num_work) {
+        if (ch == 2) {
+          w += gridDim.x;
+          ch = 0;
+          continue;
+        }
+        if (chunk_live(w, ch)) return;
+        ++ch;
+      }
+    };
+    if (has_res && !out_f32 && issuer) {
+      uint32_t fw = blockIdx.x, fch = 0;
+      next_live_chunk(fw, fch);
+      if (fw < num_work) load_residual(fw, fch);
+    }
 
     uint32_t it = 0;
     for (uint32_t w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
@@ -375,11 +392,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tma_store_commit();
           if (has_res) {   // prefetch the residual of this group's next live chunk
             uint32_t nt = w, nch = ch + 1;
-            if (nch == 2 || !chunk_live(nt, nch)) {
-              nt = w + gridDim.x;
-              nch = 0;
-            }
-            if (chunk_live(nt, nch)) {
+            next_live_chunk(nt, nch);
+            if (nt < num_work) {
               tma_store_wait_read<0>();
               load_residual(nt, nch);
             }

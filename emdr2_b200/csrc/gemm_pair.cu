@@ -234,7 +234,24 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   static_cast<int32_t>((w % a.tiles_n) * kGemmBN + hh * 128 + ch * 64),
                   static_cast<int32_t>(tile_m0(w)), kEvictNormal);
     };
-    if (has_res && issuer && chunk_live(pair, 0)) load_residual(pair, 0);
+    // First live chunk at or after (w, ch) in this column half's processing order (ragged N: the
+    // chunks of the last column tile may be past the end for one half); w >= num_work if none.
+    auto next_live_chunk = [&](uint32_t& w, uint32_t& ch) {
+      while (w < num_work) {
+        if (ch == 2) {
+          w += num_pairs;
+          ch = 0;
+          continue;
+        }
+        if (chunk_live(w, ch)) return;
+        ++ch;
+      }
+    };
+    if (has_res && issuer) {
+      uint32_t fw = pair, fch = 0;
+      next_live_chunk(fw, fch);
+      if (fw < num_work) load_residual(fw, fch);
+    }
 
     uint32_t it = 0;
     for (uint32_t w = pair; w < num_work; w += num_pairs, ++it) {
@@ -353,11 +370,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tma_store_commit();
           if (has_res) {
             uint32_t nt = w, nch = ch + 1;
-            if (nch == 2 || !chunk_live(nt, nch)) {
-              nt = w + num_pairs;
-              nch = 0;
-            }
-            if (chunk_live(nt, nch)) {
+            next_live_chunk(nt, nch);
+            if (nt < num_work) {
               tma_store_wait_read<0>();
               load_residual(nt, nch);
             }
