@@ -80,7 +80,7 @@ struct ScopedTimer {
 // 1: large forward products use the CTA-pair kernel (gemm_pair.cu); 0: always the one-CTA kernel.
 static std::atomic<int> g_gemm_pair{[] {
   const char* e = getenv("EMDR2_GEMM_PAIR");
-  return (e && e[0] == '1') ? 1 : 0;
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
 }()};
 
 extern "C" {
@@ -88,7 +88,8 @@ extern "C" {
 int emdr2_ops_set_option(const char* name, int64_t value) {
   if (!name) return fail(EMDR2_EINVAL, "NULL option name");
   if (strcmp(name, "gemm_pair") == 0) {
-    g_gemm_pair.store(value != 0 ? 1 : 0, std::memory_order_relaxed);
+    if (value < 0 || value > 2) return fail(EMDR2_EINVAL, "gemm_pair takes 0 (off), 1 (on) or 2 (auto)");
+    g_gemm_pair.store(static_cast<int>(value), std::memory_order_relaxed);
     return EMDR2_OK;
   }
   return fail(EMDR2_EINVAL, "unknown option '%s'", name);
@@ -149,7 +150,9 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
   // Large K-major products with a 16-bit output run on CTA pairs (gemm_pair.cu): 256 x 256 tiles, at
   // least two per pair so the persistent pipeline has something to overlap.
   const int64_t pair_tiles = static_cast<int64_t>((m + 255) / 256) * ((n + emdr2::kGemmBN - 1) / emdr2::kGemmBN);
-  const bool use_pair = g_gemm_pair.load(std::memory_order_relaxed) != 0 && !a_mn && !b_mn && !accum &&
+  const int pair_mode = g_gemm_pair.load(std::memory_order_relaxed);   // 0 never, 1 whenever eligible, 2 auto
+  const bool pair_wins = has_aux || (flags & EMDR2_GEMM_GELU);          // measured: profiles/README.md
+  const bool use_pair = (pair_mode == 1 || (pair_mode == 2 && pair_wins)) && !a_mn && !b_mn && !accum &&
                         splits == 1 && info.sm_count >= 2 && pair_tiles >= 2 * (info.sm_count / 2);
   // K-major operand: [rows, k] with box rows x 64; MN-major: [k, rows] with 64 x 64 boxes
   rc = a_mn ? make_tmap_2d(&ta, dtype, a, k, m, lda, 64) : make_tmap_2d(&ta, dtype, a, m, k, lda, emdr2::kGemmBM);

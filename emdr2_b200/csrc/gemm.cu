@@ -339,16 +339,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (has_res) {
           mbar_wait(res_bar, res_phase);   // residual box is in the staging buffer
           res_phase ^= 1;
-        } else {
-          // staging buffer must be free: the previous TMA store has finished reading it
-          if (issuer) tma_store_wait_read<0>();
-          named_bar_sync(bar_id, 128);
         }
+        // The arithmetic runs BEFORE the wait for the staging buffer, so the previous chunk's TMA store
+        // drains shared memory underneath it (it used to sit on the critical path of every chunk and
+        // made the GeLU epilogue longer than the tile's MMAs).
+        uint32_t packed[32];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {  // 8 columns per group == one 16-byte chunk
           const bool col_ok = gcol + g * 8 < a.N;
           const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
-          uint4* slot = reinterpret_cast<uint4*>(stage_ptr + row * 128u + phys);
           float x[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
@@ -367,7 +366,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
           }
           if (has_res) {   // out-of-range rows / columns were zero-filled by the TMA load
-            const uint4 rv = *slot;
+            const uint4 rv = *reinterpret_cast<const uint4*>(stage_ptr + row * 128u + phys);
             const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -381,8 +380,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               }
             }
           }
-          *slot = make_uint4(pack2<kBf16>(x[0], x[1]), pack2<kBf16>(x[2], x[3]),
-                             pack2<kBf16>(x[4], x[5]), pack2<kBf16>(x[6], x[7]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) packed[g * 4 + j] = pack2<kBf16>(x[2 * j], x[2 * j + 1]);
+        }
+        if (!has_res) {
+          // staging buffer must be free: the previous TMA store has finished reading it.  (With a
+          // residual the buffer already is this chunk's: the residual box was loaded into it, and every
+          // thread overwrites exactly the slots it has just read.)
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, 128);
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+          *reinterpret_cast<uint4*>(stage_ptr + row * 128u + phys) =
+              make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);

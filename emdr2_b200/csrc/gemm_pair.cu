@@ -6,7 +6,7 @@
 // (85 flop per byte fetched from L2) and only 4 such stages fit beside the output staging — ncu shows
 // the tensor pipe 52-78 % busy with L2->SM traffic at 13-17 TB/s.  Here two CTAs on the two SMs of a
 // TPC share one 256x256 tile: each stages its own 128 rows of A and HALF of the B tile (32 KiB per
-// k block, 128 flop per byte), six stages deep, and CTA rank 0 issues tcgen05.mma.cta_group::2 with
+// k block, 128 flop per byte), five stages deep, and CTA rank 0 issues tcgen05.mma.cta_group::2 with
 // M = 256, which reads both halves of B from the two shared memories.  Each CTA's 128 accumulator
 // rows live in its own TMEM and are drained by its own epilogue warps, exactly as in gemm.cu.
 //
@@ -29,12 +29,14 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kPairStages = 6;
+constexpr int kPairStages = 5;
 constexpr int kPairBM = 2 * kGemmBM;                              // rows of the pair's tile
 constexpr int kPairStageA = kGemmBM * kGemmBK * 2;                // 16 KiB: this CTA's 128 rows of A
 constexpr int kPairStageB = (kGemmBN / 2) * kGemmBK * 2;          // 16 KiB: this CTA's half of B
 constexpr int kPairStageBytes = kPairStageA + kPairStageB;        // 32 KiB
-constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kGemmOutBytes + kGemmBarBytes + 1024;
+constexpr int kPairResBytes = 2 * kGemmBM * 64 * 2;               // residual boxes, one per column half
+constexpr int kPairSmemBytes =
+    kPairStages * kPairStageBytes + kGemmOutBytes + kPairResBytes + kGemmBarBytes + 1024;
 static_assert(kPairSmemBytes <= 227 * 1024, "shared memory budget");
 
 struct PairBars {
@@ -112,7 +114,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   constexpr uint32_t off_out = kPairStages * kPairStageBytes;
-  constexpr uint32_t off_bar = off_out + kGemmOutBytes;
+  constexpr uint32_t off_res = off_out + kGemmOutBytes;
+  constexpr uint32_t off_bar = off_res + kPairResBytes;
   PairBars* bars = reinterpret_cast<PairBars*>(smem + off_bar);
   const uint32_t smem_base = smem_u32(smem);
 
@@ -212,6 +215,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t row = quad * 32 + lane;
     const uint32_t stage_off = off_out + hh * (kGemmBM * 64 * 2);
     uint8_t* stage_ptr = smem + stage_off;
+    // The residual (or GeLU-backward aux) box of a chunk lands in its OWN buffer, so its TMA load for
+    // chunk c+1 flies while chunk c is still being stored (in gemm.cu it shares the output staging
+    // buffer and each chunk pays store-drain + load latency back to back).
+    const uint32_t res_off = off_res + hh * (kGemmBM * 64 * 2);
+    const uint8_t* res_ptr = smem + res_off;
     const bool issuer = (warp - 4) % 4 == 0 && lane == 0;
     const uint32_t bar_id = 1 + hh;
     const bool has_bias = (a.flags & kGemmBias) != 0;
@@ -230,7 +238,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     };
     auto load_residual = [&](uint32_t w, uint32_t ch) {
       mbar_arrive_expect_tx(res_bar, kGemmBM * 64 * 2);
-      tma_load_2d(smem_base + stage_off, &tmap_r, res_bar,
+      tma_load_2d(smem_base + res_off, &tmap_r, res_bar,
                   static_cast<int32_t>((w % a.tiles_n) * kGemmBN + hh * 128 + ch * 64),
                   static_cast<int32_t>(tile_m0(w)), kEvictNormal);
     };
@@ -316,17 +324,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         if (has_res) {
-          mbar_wait(res_bar, res_phase);
+          mbar_wait(res_bar, res_phase);   // this chunk's residual box has landed
           res_phase ^= 1;
-        } else {
-          if (issuer) tma_store_wait_read<0>();
-          named_bar_sync(bar_id, 128);
         }
+        // arithmetic first: the previous chunk's TMA store drains the staging buffer underneath it
+        uint32_t packed[32];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const bool col_ok = gcol + g * 8 < a.N;
           const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
-          uint4* slot = reinterpret_cast<uint4*>(stage_ptr + row * 128u + phys);
           float x[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
@@ -344,8 +350,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
           }
-          if (has_res) {
-            const uint4 rv = *slot;
+          if (has_res) {   // out-of-range rows / columns were zero-filled by the TMA load
+            const uint4 rv = *reinterpret_cast<const uint4*>(res_ptr + row * 128u + phys);
             const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -359,8 +365,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
-          *slot = make_uint4(pack2<kBf16>(x[0], x[1]), pack2<kBf16>(x[2], x[3]),
-                             pack2<kBf16>(x[4], x[5]), pack2<kBf16>(x[6], x[7]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) packed[g * 4 + j] = pack2<kBf16>(x[2 * j], x[2 * j + 1]);
+        }
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(bar_id, 128);   // staging buffer free; every thread has read the residual box
+        if (has_res && issuer) {       // fetch the residual of this half's next live chunk
+          uint32_t nt = w, nch = ch + 1;
+          next_live_chunk(nt, nch);
+          if (nt < num_work) load_residual(nt, nch);
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+          *reinterpret_cast<uint4*>(stage_ptr + row * 128u + phys) =
+              make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
@@ -368,14 +387,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tma_store_2d(&tmap_d, smem_base + stage_off, static_cast<int32_t>(gcol),
                        static_cast<int32_t>(m0));
           tma_store_commit();
-          if (has_res) {
-            uint32_t nt = w, nch = ch + 1;
-            next_live_chunk(nt, nch);
-            if (nt < num_work) {
-              tma_store_wait_read<0>();
-              load_residual(nt, nch);
-            }
-          }
         }
       }
     }

@@ -177,3 +177,33 @@ def test_bucket_plan_is_a_partition_sorted_by_length():
     assert lm._bucket_plan(32, 256, lens[:32]) is None                   # small batches run as one rectangle
     assert lm._bucket_plan(333, 256, None) is None
     assert lm._bucket_plan(100, 256, np.full(100, 77)) is None           # equal lengths: nothing to bucket
+
+
+@pytest.mark.parametrize("clustered", [False, True])
+def test_k_above_the_kernel_limit_is_exact_by_range_refinement(clustered):
+    """k = 100 (the recall evaluator's setting) on the oracle-backed double: the answer equals the
+    oracle's top-100 even when most of it sits in one row range (forces the refinement loop)."""
+    rng = np.random.RandomState(5)
+    n, d, nq, k = 3000, 16, 5, 100
+    rows = (rng.randint(-127, 128, size=(n, d)) / 64).astype(np.float16)
+    queries = (rng.randint(-127, 128, size=(nq, d)) / 64).astype(np.float16)
+    if clustered:
+        rows[100:400] = (queries[0].astype(np.float32) * 1.5).astype(np.float16) + rows[100:400] / 16
+    ids = rng.permutation(np.arange(1, n + 1)).astype(np.int64)
+    index = CpuDoubleIndex(d, device="cpu")
+    calls = []
+    orig = index._search_range
+    index._search_range = lambda q, lo, hi, kk: (calls.append((lo, hi)), orig(q, lo, hi, kk))[1]
+    index.add_arrays(ids, rows)
+    got_s, got_i = index.search(torch.from_numpy(queries), k)
+    want_s, want_i, ties = oracle.mips_topk(rows, queries, k, ids=ids, want_ties=True)
+    assert np.array_equal(got_s.numpy(), want_s)
+    free = ties == 0
+    assert np.array_equal(got_i.numpy()[free], want_i[free])
+    for qi in range(nq):                                     # tie groups: same id sets
+        assert sorted(got_i.numpy()[qi].tolist()) == sorted(want_i[qi].tolist())
+    assert len(calls) >= 4 and (len(calls) > 4) == clustered
+    dist16, idx32 = index.search_mips_index(torch.from_numpy(queries), k)
+    assert dist16.dtype == torch.float16 and idx32.dtype == torch.int32 and idx32.shape == (nq, k)
+    small_s, small_i = index.search(torch.from_numpy(queries), 7)
+    assert np.array_equal(small_i.numpy(), got_i.numpy()[:, :7]) or not free[:, :7].all()
