@@ -80,7 +80,7 @@ struct ScopedTimer {
 // 1: large forward products use the CTA-pair kernel (gemm_pair.cu); 0: always the one-CTA kernel.
 static std::atomic<int> g_gemm_pair{[] {
   const char* e = getenv("EMDR2_GEMM_PAIR");
-  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
 }()};
 
 extern "C" {
@@ -151,7 +151,9 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
   // least two per pair so the persistent pipeline has something to overlap.
   const int64_t pair_tiles = static_cast<int64_t>((m + 255) / 256) * ((n + emdr2::kGemmBN - 1) / emdr2::kGemmBN);
   const int pair_mode = g_gemm_pair.load(std::memory_order_relaxed);   // 0 never, 1 whenever eligible, 2 auto
-  const bool pair_wins = has_aux || (flags & EMDR2_GEMM_GELU);          // measured: profiles/README.md
+  // auto: where the pair kernel is measured to win (profiles/README.md, r1g): residual / aux epilogues
+  // over >= 100 k rows (+3.5 % at K = 3072, +8 % at K = 768); elsewhere the one-CTA kernel is as fast or faster
+  const bool pair_wins = has_aux && m >= 100000;
   const bool use_pair = (pair_mode == 1 || (pair_mode == 2 && pair_wins)) && !a_mn && !b_mn && !accum &&
                         splits == 1 && info.sm_count >= 2 && pair_tiles >= 2 * (info.sm_count / 2);
   // K-major operand: [rows, k] with box rows x 64; MN-major: [k, rows] with 64 x 64 boxes

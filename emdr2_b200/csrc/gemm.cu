@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "gelu.cuh"
 #include "ptx.cuh"
 
 namespace emdr2 {
@@ -45,23 +46,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
-// GeLU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7,
-// far below the 16-bit output rounding): 2 MUFU + ~12 FP32 ops instead of erff's two-branch
-// polynomial, which made the h -> 4h GEMM epilogue-bound.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-  const float q = 0.5f * poly * e;          // 0.5 * (1 - erf(|x| / sqrt 2))
-  return x >= 0.f ? fmaf(-x, q, x) : x * q;
-}
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -363,7 +347,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           if (has_gelu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+            for (int j = 0; j < 8; j += 2) gelu_erf_pair(x[j], x[j + 1]);
           }
           if (has_res) {   // out-of-range rows / columns were zero-filled by the TMA load
             const uint4 rv = *reinterpret_cast<const uint4*>(stage_ptr + row * 128u + phys);

@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "gelu.cuh"
 #include "ptx.cuh"
 
 namespace emdr2 {
@@ -70,21 +71,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
-// Same arithmetic as gemm.cu (A&S 7.1.26 erf): the two kernels must round identically.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-  const float q = 0.5f * poly * e;
-  return x >= 0.f ? fmaf(-x, q, x) : x * q;
-}
+
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
   float t;
@@ -348,7 +335,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           if (has_gelu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+            for (int j = 0; j < 8; j += 2) gelu_erf_pair(x[j], x[j + 1]);
           }
           if (has_res) {   // out-of-range rows / columns were zero-filled by the TMA load
             const uint4 rv = *reinterpret_cast<const uint4*>(res_ptr + row * 128u + phys);

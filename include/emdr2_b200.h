@@ -254,8 +254,8 @@ EMDR2_API int emdr2_format_passages(int32_t bsz, int32_t k_keep, const int64_t* 
 /* Process-wide switches of the block operators.  "gemm_pair" (initial value from the environment
  * variable EMDR2_GEMM_PAIR): 1 = large K-major products with a 16-bit output run on CTA pairs
  * (tcgen05.mma.cta_group::2, 256 x 256 tiles, residual box in its own staging buffer) instead of one
- * CTA per 128 x 256 tile; 2 = only where that is measured to win (GeLU / residual / aux epilogues);
- * 0 = never.  Results are bit-identical between the two kernels (same products, same fp32
+ * CTA per 128 x 256 tile; 2 (default) = only where that is measured to win (residual / aux epilogues
+ * over >= 100 k rows); 0 = never.  Results are bit-identical between the two kernels (same products, same fp32
  * accumulation order per element). */
 EMDR2_API int emdr2_ops_set_option(const char* name, int64_t value);
 EMDR2_API int emdr2_ops_get_option(const char* name, int64_t* out_value);
