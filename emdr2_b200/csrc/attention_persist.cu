@@ -284,8 +284,6 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint32_t valid = min(static_cast<uint32_t>(kAttnBK), a.sk - kb0);
             const bool causal_row = a.causal && (kb0 + kAttnBK - 1 > qi);
             const bool plain = !q_is_pad && !causal_row && valid == kAttnBK && (km[0] | km[1] | km[2] | km[3]) == 0u;
-            const bool constant = valid == kAttnBK && (q_is_pad || (km[0] & km[1] & km[2] & km[3]) == 0xffffffffu ||
-                                                       (a.causal && kb0 > qi));
             uint32_t t[kAttnBK];   // scores as raw fp32 bits (tcgen05.ld output registers)
             const uint32_t s_addr = tmem_base + lane_tmem;
             tmem_ld_32x32b_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&t[0]));
@@ -293,35 +291,64 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q,
             tmem_ld_32x32b_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&t[64]));
             tmem_ld_32x32b_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&t[96]));
             tmem_ld_wait();
-            // ---- maximum of the masked log2-domain scores.  Fast path (every row of the warp is either
-            // unmasked in this block or sees one constant value): the accumulators stay raw and the
-            // exp FFMA applies p = exp2(t * mul + bias).  Slow path (block crossed by a padding
-            // boundary, the causal diagonal or the end of the keys): t is rewritten in place.
-            float mx, mul, bias = 0.f;
-            if (__any_sync(kFull, !(plain || constant))) {
-              mx = kNegInf;
-              mul = 1.0f;
-#pragma unroll
-              for (int c = 0; c < kAttnBK; ++c) {
-                float x = __uint_as_float(t[c]) * a.scale_log2;
-                const bool masked = q_is_pad || ((km[c >> 5] >> (c & 31)) & 1u) ||
-                                    (a.causal && kb0 + c > qi);
-                x = masked ? kMaskedLog2 : x;
-                x = (static_cast<uint32_t>(c) < valid) ? x : kNegInf;
-                t[c] = __float_as_uint(x);
-                mx = fmaxf(mx, x);
-              }
-            } else {
+            // ---- maximum of the masked log2-domain scores; p = exp2(t * mul + bias - m) per 32-key chunk.
+            // Whole block unmasked for every row of the warp (the common case): raw maximum, one scale.
+            // Otherwise each 32-key chunk is classified per row — unmasked, all masked (one constant),
+            // past the end of the keys (-inf) — and keeps its raw accumulators; only a chunk that a padding
+            // boundary, the causal diagonal or the end of the keys actually CROSSES for some row of the
+            // warp is rewritten element by element (it used to be the whole 128-key block).
+            float mx;
+            float mul_c[4], bias_c[4];
+            if (__all_sync(kFull, plain)) {
               float r0 = __uint_as_float(t[0]), r1 = __uint_as_float(t[1]);
 #pragma unroll
               for (int c = 2; c < kAttnBK; c += 2) {
                 r0 = fmaxf(r0, __uint_as_float(t[c]));
                 r1 = fmaxf(r1, __uint_as_float(t[c + 1]));
               }
-              // scale > 0: the maximum commutes with the scaling; a constant row ignores its scores
-              mx = constant ? kMaskedLog2 : fmaxf(r0, r1) * a.scale_log2;
-              mul = constant ? 0.0f : a.scale_log2;
-              bias = constant ? kMaskedLog2 : 0.0f;
+              mx = fmaxf(r0, r1) * a.scale_log2;   // scale > 0: the maximum commutes with the scaling
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                mul_c[c] = a.scale_log2;
+                bias_c[c] = 0.f;
+              }
+            } else {
+              mx = kNegInf;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t c0 = kb0 + c * 32;
+                const bool past_end = c0 >= a.sk;
+                const bool all_masked = q_is_pad || km[c] == 0xffffffffu || (a.causal && c0 > qi);
+                const bool none_masked = !q_is_pad && km[c] == 0u && !(a.causal && c0 + 31 > qi);
+                const bool uniform = past_end || (c0 + 32 <= a.sk && (all_masked || none_masked));
+                float m;
+                if (__any_sync(kFull, !uniform)) {
+                  m = kNegInf;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    float x = __uint_as_float(t[c * 32 + i]) * a.scale_log2;
+                    const bool masked = q_is_pad || ((km[c] >> i) & 1u) || (a.causal && c0 + i > qi);
+                    x = masked ? kMaskedLog2 : x;
+                    x = (c0 + i < a.sk) ? x : kNegInf;
+                    t[c * 32 + i] = __float_as_uint(x);
+                    m = fmaxf(m, x);
+                  }
+                  mul_c[c] = 1.0f;
+                  bias_c[c] = 0.f;
+                } else {
+                  float r0 = __uint_as_float(t[c * 32]), r1 = __uint_as_float(t[c * 32 + 1]);
+#pragma unroll
+                  for (int i = 2; i < 32; i += 2) {
+                    r0 = fmaxf(r0, __uint_as_float(t[c * 32 + i]));
+                    r1 = fmaxf(r1, __uint_as_float(t[c * 32 + i + 1]));
+                  }
+                  const bool constant = all_masked && !past_end;
+                  m = past_end ? kNegInf : (constant ? kMaskedLog2 : fmaxf(r0, r1) * a.scale_log2);
+                  mul_c[c] = (past_end || constant) ? 0.0f : a.scale_log2;
+                  bias_c[c] = past_end ? kNegInf : (constant ? kMaskedLog2 : 0.0f);
+                }
+                mx = fmaxf(mx, m);
+              }
             }
             // ---- running maximum: raised only when the block exceeds it by more than 2^8
             const bool raise = first || mx > m_run + kLazyRescale;
@@ -345,10 +372,11 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q,
               }
             }
             // ---- uniform part: P = exp2(t * mul - m_run) -> 16-bit pairs -> TMEM columns [0, 64)
-            const float negm = bias - m_run;
             float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
             for (int c = 0; c < kAttnBK / 32; ++c) {
+              const float mul = mul_c[c];
+              const float negm = bias_c[c] - m_run;
               uint32_t w[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
