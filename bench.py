@@ -12,7 +12,9 @@ all-gather of the queries -> brute-force top-50 MIPS over the 21 000 000 x 768 f
 row-sharded over the N ranks (one all-gather of [nq,k] pairs + merge) -> passage lookup + formatting
 on the host -> context tower over 50 passages per question (S=256) -> fresh scores -> T5-base encoder
 over the 50 (question, passage) pairs (S=512) -> FiD decoder (L=32, cross-attention over 25 600
-keys) + LM head.  Forward only: the backward pass is not in the timed region (not built yet).
+keys) + LM head.  The default run times the forward path (what BASELINE's retrieve+read metric names);
+`--train` times the whole training step (forward incl. the no-grad one-context pass, both losses, backward,
+gradient all-reduce, optimizer).
 Synthetic NQ-shaped data: random-init weights N(0, 0.02), question length
 U[8,24], passages U[100,180] tokens, titles U[2,8], answers U[2,6].
 
@@ -89,6 +91,16 @@ def measured_peak(key="hbm_gbs"):
     except Exception:
         fallback = {"hbm_gbs": FALLBACK_HBM_GBS, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}[key]
         return fallback, "fallback (B200_PROFILING.md)"
+
+
+def recorded_gemm_traffic():
+    """Mean DRAM bytes per launch of emdr2::gemm_kernel over the layer's four projections, from the
+    committed `ncu --set full` capture (profiles/roofline_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get("gemm_kernel", {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def recorded_traffic(rows_per_gpu, dim):
@@ -673,7 +685,11 @@ def run_retrieve_read(a):
                        "; includes the host-side passage lookup/formatting"},
         "gpu_launches": int(launches_step * a.steps),
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_t, "unit": "TFLOP/s", "frac": gemm_tf / peak_t,
-                     "traffic": None, "kernel": "emdr2::gemm_kernel", "algorithmic_flops_per_step": gemm_fl / a.steps,
+                     "traffic": recorded_gemm_traffic(),
+                     "traffic_note": "mean DRAM bytes/launch of the layer's four projections at 102400 tokens (ncu --set full, "
+                                     "profiles/roofline_traffic.json); the bound is the tensor pipe, not DRAM",
+                     "kernel": "emdr2::gemm_kernel (+ emdr2::gemm_pair_kernel for residual epilogues over >=100k rows)",
+                     "algorithmic_flops_per_step": gemm_fl / a.steps,
                      "kernel_ms_per_step": gemm_s / a.steps * 1e3, "launches_timed": gemm_n, "peak_source": peak_t_src},
         "roofline_mips": roof_mips,
         "kernel_time_ms_per_step": {"gemm": gemm_s / a.steps * 1e3, "attention": attn_s / a.steps * 1e3,
