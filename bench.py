@@ -169,22 +169,31 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------- synthetic corpus
-class SyntheticTokens(object):
-    """passages_map / title_map stand-in: x[doc_id - 1] -> np.int64 token array.  A pool of
-    pre-generated passages indexed modulo its size (21 M real passages would be 25 GB of tokens)."""
+def synthetic_token_store(lo, hi, seed, pool=65536):
+    """passages_map / title_map stand-in as a flat token store (emdr2_b200/tokens.py — the layout of the
+    reference's memory-mapped indexed datasets): x[doc_id - 1] -> int64 token array.  A pool of
+    pre-generated documents indexed modulo its size (21 M real passages would be 25 GB of tokens)."""
+    import numpy as np
+    from emdr2_b200.tokens import FlatTokenStore
 
-    def __init__(self, lo, hi, seed, pool=65536):
-        import numpy as np
-        rng = np.random.RandomState(seed)
-        lens = rng.randint(lo, hi + 1, size=pool)
-        self.items = [rng.randint(1000, 30000, size=int(n)).astype(np.int64) for n in lens]
+    class ModuloTokenStore(FlatTokenStore):
+        def __getitem__(self, i):
+            return FlatTokenStore.__getitem__(self, i % len(self))
 
-    def __getitem__(self, i):
-        return self.items[i % len(self.items)]
+        def spans(self, index):
+            index = np.asarray(index, dtype=np.int64)
+            return FlatTokenStore.spans(self, np.where(index >= 0, index % len(self), -1))
+
+    rng = np.random.RandomState(seed)
+    lens = rng.randint(lo, hi + 1, size=pool)
+    offsets = np.zeros(pool + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    return ModuloTokenStore(rng.randint(1000, 30000, size=int(offsets[-1])).astype(np.int64), offsets)
 
 
 class SyntheticTitleMap(object):
-    """Articles of 4 consecutive passages (tools/inverted_title_index.py:22-37 semantics)."""
+    """Articles of 4 consecutive passages (tools/inverted_title_index.py:22-37 semantics), answering one
+    doc id (`get_neighbour_paragraphs`) or a whole batch (`lookup`, like titlemap.NeighbourTable)."""
 
     def __init__(self, num_docs, per_article=4):
         self.n, self.per = num_docs, per_article
@@ -198,6 +207,23 @@ class SyntheticTitleMap(object):
         if i == len(docs) - 1:
             return docs[i - 2:i + 1], -1
         return docs[i - 1:i + 2], 1
+
+    def lookup(self, doc_ids):
+        import numpy as np
+        ids = np.asarray(doc_ids, dtype=np.int64).reshape(-1)
+        first = ((ids - 1) // self.per) * self.per + 1
+        length = np.minimum(self.n, first + self.per - 1) - first + 1
+        i = ids - first
+        is_first = i == 0
+        is_last = (~is_first) & (i == length - 1)
+        alone = is_last & (i < 2)
+        start = np.where(is_first, 0, np.where(is_last, np.maximum(i - 2, 0), i - 1))
+        start = np.where(alone, i, start)
+        count = np.where(is_first, np.minimum(length, 3), np.where(alone, 1, 3))
+        cols = np.arange(3)[None, :]
+        docs = np.where(cols < count[:, None], first[:, None] + start[:, None] + cols, -1)
+        main = np.where(is_first, 0, np.where(is_last, -1, 1)).astype(np.int32)
+        return docs, count.astype(np.int32), main
 
 
 def synthetic_questions(a, rank):
@@ -553,7 +579,7 @@ def run_retrieve_read(a):
     lo, hi = chunk_range(a.rows, world, rank)
     rows = make_shard(torch, hi - lo, a.dim, edtype, 1234 + rank, device)
     retriever = B200EvidenceRetriever(a.k, a.dim, allow_trivial_doc=True, group=d.group, dtype=edtype,
-                                      passages_map=SyntheticTokens(100, 180, 1), title_map=SyntheticTokens(2, 8, 2),
+                                      passages_map=synthetic_token_store(100, 180, 1), title_map=synthetic_token_store(2, 8, 2),
                                       wikititledocmap=SyntheticTitleMap(a.rows))
     retriever.mips_index.add_local_shard(None, rows, num_rows=a.rows, row_lo=lo)
     searcher = retriever.mips_index._searcher

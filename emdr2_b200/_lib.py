@@ -88,6 +88,13 @@ _SIGNATURES = {
                                              ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]),
+    "emdr2_format_passages_flat": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                                  ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_void_p]),
     "emdr2_ops_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "emdr2_ops_get_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)]),
     "emdr2_ops_timing": (ctypes.c_int, [ctypes.c_int]),

@@ -177,6 +177,40 @@ class FormatLengths(tuple):
         return self
 
 
+class PackedTopk(object):
+    """Retrieved evidence of a batch in the flat form `emdr2_format_passages_flat` reads: no token has
+    been touched yet.  cand_begin int32 [B + 1], cand_id int64 [n], cand_meta int32 [n, 6] (title_len,
+    n_docs, main_idx, doc_len x 3), piece_offset int64 [n, 4] (title | passages) into the two stores."""
+
+    def __init__(self, cand_begin, cand_id, cand_meta, piece_offset, title_store, passage_store):
+        if title_store.token_bytes != passage_store.token_bytes:
+            raise TypeError("title and passage stores must share one token width")
+        self.cand_begin = np.ascontiguousarray(cand_begin, dtype=np.int32)
+        self.cand_id = np.ascontiguousarray(cand_id, dtype=np.int64)
+        self.cand_meta = np.ascontiguousarray(cand_meta, dtype=np.int32).reshape(-1, 6)
+        self.piece_offset = np.ascontiguousarray(piece_offset, dtype=np.int64).reshape(-1, 4)
+        self.title_store, self.passage_store = title_store, passage_store
+
+    def __len__(self):
+        return self.cand_begin.shape[0] - 1
+
+    def to_nested(self):
+        """The reference's nested form (emdr2_model.py:457-468): [(ids, [(doc_list, main_idx, title)])]."""
+        out = []
+        for b in range(len(self)):
+            ids, texts = [], []
+            for c in range(self.cand_begin[b], self.cand_begin[b + 1]):
+                tl, nd, main = (int(x) for x in self.cand_meta[c, :3])
+                off = self.piece_offset[c]
+                title = np.asarray(self.title_store.tokens[off[0]:off[0] + tl], dtype=np.int64)
+                docs = [np.asarray(self.passage_store.tokens[off[1 + i]:off[1 + i] + int(self.cand_meta[c, 3 + i])],
+                                   dtype=np.int64) for i in range(nd)]
+                ids.append(int(self.cand_id[c]))
+                texts.append((docs, main, title))
+            out.append((ids, texts))
+        return out
+
+
 class _Staging(object):
     """Two alternating host blocks per output shape (pinned when the target is a CUDA device), each
     guarded by an event recorded after its upload, so a block is never rewritten while the copy engine
@@ -246,7 +280,9 @@ def format_passages_native(query_uid, query_ids_t5, query_ids_t5_len, topk_evide
     q_len = np.ascontiguousarray(np.asarray(query_ids_t5_len, dtype=np.int64).reshape(-1))
     if len(topk_evidence_data) != bsz or q_len.shape[0] != bsz:
         raise ValueError("batch size mismatch between questions and retrieved evidence")
-    cand_begin, cand_id, cand_meta, tokens = flatten_topk(topk_evidence_data)
+    packed = topk_evidence_data if isinstance(topk_evidence_data, PackedTopk) else None
+    if packed is None:
+        cand_begin, cand_id, cand_meta, tokens = flatten_topk(topk_evidence_data)
     rows = bsz * k_keep
     n_ret, n_seq = rows * seq_length_ret, rows * seq_length
     if out is None:
@@ -259,11 +295,20 @@ def format_passages_native(query_uid, query_ids_t5, query_ids_t5_len, topk_evide
     max_len = np.zeros(3, dtype=np.int32)
     row_len = np.zeros((3, rows), dtype=np.int32)
     ptr = lambda a: ctypes.c_void_p(a.ctypes.data)   # noqa: E731
-    rc = lib.emdr2_format_passages(bsz, k_keep, ptr(uid), ptr(q), q.shape[1], ptr(q_len), ptr(cand_begin),
-                                   ptr(cand_id), ptr(cand_meta), ptr(tokens), tokens.shape[0],
-                                   int(seq_length_ret), int(seq_length), int(cls_id), int(sep_id), int(pad_id),
-                                   ptr(ctx_ids), ptr(ctx_types), ptr(extended), ptr(single), ptr(max_len),
-                                   ptr(row_len))
+    if packed is not None:
+        # tokens are read in place from the flat stores (possibly memory-mapped files)
+        tt, dt = packed.title_store.tokens, packed.passage_store.tokens
+        rc = lib.emdr2_format_passages_flat(
+            bsz, k_keep, ptr(uid), ptr(q), q.shape[1], ptr(q_len), ptr(packed.cand_begin), ptr(packed.cand_id),
+            ptr(packed.cand_meta), ptr(packed.piece_offset), ptr(tt), tt.shape[0], ptr(dt), dt.shape[0],
+            packed.passage_store.token_bytes, int(seq_length_ret), int(seq_length), int(cls_id), int(sep_id),
+            int(pad_id), ptr(ctx_ids), ptr(ctx_types), ptr(extended), ptr(single), ptr(max_len), ptr(row_len))
+    else:
+        rc = lib.emdr2_format_passages(bsz, k_keep, ptr(uid), ptr(q), q.shape[1], ptr(q_len), ptr(cand_begin),
+                                       ptr(cand_id), ptr(cand_meta), ptr(tokens), tokens.shape[0],
+                                       int(seq_length_ret), int(seq_length), int(cls_id), int(sep_id), int(pad_id),
+                                       ptr(ctx_ids), ptr(ctx_types), ptr(extended), ptr(single), ptr(max_len),
+                                       ptr(row_len))
     if rc != 0:
         msg = lib.emdr2_last_error().decode("utf-8", "replace")
         raise ValueError(msg)

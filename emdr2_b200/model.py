@@ -100,7 +100,10 @@ class EMDR2Model(nn.Module):
         if all_query_context_hidden_states is None:
             query_logits = self.retriever_embedder(query_ids_bert, query_mask_bert, query_types, "query")
             with torch.no_grad():
-                if getattr(self.evidence_retriever, "supports_arrays", False):
+                if getattr(self.evidence_retriever, "supports_packed", False):
+                    topk_evidence_data, _stale = self.evidence_retriever.get_topk(query_logits.detach(),
+                                                                                  as_packed=True)
+                elif getattr(self.evidence_retriever, "supports_arrays", False):
                     topk_evidence_data, _stale = self.evidence_retriever.get_topk(query_logits.detach(),
                                                                                   as_arrays=True)
                 else:

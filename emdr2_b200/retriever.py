@@ -74,10 +74,46 @@ class B200EvidenceRetriever(object):
     #: EMDR2Model passes as_arrays=True when the retriever advertises it (skips ~B*K*4 .tolist() calls)
     supports_arrays = True
 
-    def get_topk(self, query_tensor, as_arrays=False):
+    @property
+    def supports_packed(self):
+        """True when the token maps are flat stores and the title map answers whole batches
+        (emdr2_b200/tokens.py:FlatTokenStore, titlemap.py:NeighbourTable or anything with `lookup`):
+        `get_topk(..., as_packed=True)` then does the tail of emdr2_model.py:457-468 with a handful of
+        numpy gathers and hands the formatter offsets instead of token arrays."""
+        from .tokens import FlatTokenStore
+        return isinstance(self.passages_map, FlatTokenStore) and isinstance(self.title_map, FlatTokenStore) \
+            and hasattr(self.wikititledocmap, "lookup")
+
+    def get_topk_packed(self, query_tensor):
+        """(PackedTopk, distance): the retrieval tail without touching a token."""
+        import numpy as np
+        from .formatter import PackedTopk
+        local_bsize = query_tensor.shape[0]
+        scores, ids = self.search_all(query_tensor)
+        rank = self.mips_index.rank
+        mine = slice(rank * local_bsize, (rank + 1) * local_bsize)
+        distance = scores[mine].to(torch.float16)
+        topk = ids[mine].to(torch.int32).cpu().numpy().astype(np.int64)       # ONE device->host copy
+        bsz, k = topk.shape
+        flat_ids = topk.reshape(-1)
+        docs, n_docs, main_idx = self.wikititledocmap.lookup(flat_ids)          # [n, 3], [n], [n]
+        t_off, t_len = self.title_map.spans(flat_ids - 1)
+        d_off, d_len = self.passages_map.spans(np.where(docs >= 0, docs - 1, -1))
+        meta = np.empty((flat_ids.shape[0], 6), dtype=np.int32)
+        meta[:, 0], meta[:, 1], meta[:, 2] = t_len, n_docs, main_idx
+        meta[:, 3:] = d_len
+        piece = np.empty((flat_ids.shape[0], 4), dtype=np.int64)
+        piece[:, 0] = t_off
+        piece[:, 1:] = d_off
+        cand_begin = np.arange(bsz + 1, dtype=np.int32) * k
+        return PackedTopk(cand_begin, flat_ids, meta, piece, self.title_map, self.passages_map), distance
+
+    def get_topk(self, query_tensor, as_arrays=False, as_packed=False):
         """(topk_data, distance) like the reference.  as_arrays=True keeps the passage / title tokens
         as the int64 arrays the token store returns instead of converting them to Python lists
         (emdr2_model.py:464-466 calls .tolist() on each); formatter.postprocess takes either."""
+        if as_packed:
+            return self.get_topk_packed(query_tensor)
         local_bsize = query_tensor.shape[0]
         scores, ids = self.search_all(query_tensor)
         rank = self.mips_index.rank

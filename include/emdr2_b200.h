@@ -251,6 +251,22 @@ EMDR2_API int emdr2_format_passages(int32_t bsz, int32_t k_keep, const int64_t* 
                                     int64_t* ctx_ids, int64_t* ctx_types, int64_t* extended,
                                     int64_t* single, int32_t* max_len, int32_t* row_len);
 
+/* Same formatting with the tokens read IN PLACE from flat token stores (what the reference's memory-mapped
+ * indexed datasets are: one token buffer + per-document offsets, megatron/data/indexed_dataset.py): no
+ * per-passage array objects, no concatenation.  piece_offset [n_cand, 4] = element offset of the
+ * candidate's title in title_tokens and of its up to three passages in doc_tokens (lengths in cand_meta);
+ * token_bytes = 2 (uint16), 4 (int32) or 8 (int64) - the element type of both stores. */
+EMDR2_API int emdr2_format_passages_flat(int32_t bsz, int32_t k_keep, const int64_t* query_uid,
+                                         const int64_t* query_ids, int64_t query_stride,
+                                         const int64_t* query_len, const int32_t* cand_begin,
+                                         const int64_t* cand_id, const int32_t* cand_meta,
+                                         const int64_t* piece_offset, const void* title_tokens,
+                                         int64_t n_title_tokens, const void* doc_tokens,
+                                         int64_t n_doc_tokens, int32_t token_bytes, int32_t seq_ret,
+                                         int32_t seq, int64_t cls_id, int64_t sep_id, int64_t pad_id,
+                                         int64_t* ctx_ids, int64_t* ctx_types, int64_t* extended,
+                                         int64_t* single, int32_t* max_len, int32_t* row_len);
+
 /* Process-wide switches of the block operators.  "gemm_pair" (initial value from the environment
  * variable EMDR2_GEMM_PAIR): 1 = large K-major products with a 16-bit output run on CTA pairs
  * (tcgen05.mma.cta_group::2, 256 x 256 tiles, residual box in its own staging buffer) instead of one

@@ -184,6 +184,92 @@ def test_native_formatter_errors_and_staging_reuse():
     assert len(lens) == 3
 
 
+def _flat_corpus(rng, n_articles=120):
+    from emdr2_b200.titlemap import TitleDocMap
+    pairs, passages, titles, did = [], [], [], 1
+    for a in range(n_articles):
+        title = rng.randint(1, 60, size=int(rng.randint(0, 6))).astype(np.int64)
+        for _ in range(int(rng.randint(1, 6))):
+            pairs.append((did, "t%d" % a))
+            passages.append(rng.randint(0, 60, size=int(rng.randint(1, 40))).astype(np.int64))
+            titles.append(title)
+            did += 1
+    return TitleDocMap(pairs=pairs), passages, titles
+
+
+class _FixedSearchRetriever(object):
+    """B200EvidenceRetriever with the GPU search replaced by fixed ids (host-tail tests on CPU)."""
+
+    def __new__(cls, topk_ids, passages_map, title_map, titlemap):
+        from emdr2_b200.retriever import B200EvidenceRetriever
+
+        class R(B200EvidenceRetriever):
+            def __init__(self):                      # no index: only the tail is under test
+                self.topk = topk_ids.shape[1]
+                self.passages_map, self.title_map, self.wikititledocmap = passages_map, title_map, titlemap
+                self.mips_index = type("I", (), {"rank": 0, "world": 1})()
+
+            def search_all(self, query_tensor):
+                ids = torch.from_numpy(topk_ids)
+                return torch.zeros(ids.shape, dtype=torch.float32), ids
+
+        return R()
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.int32, np.uint16])
+def test_packed_retrieval_tail_and_flat_formatter_equal_the_nested_path(dtype):
+    """FlatTokenStore + NeighbourTable + emdr2_format_passages_flat (tokens read in place, any width)
+    against the per-passage Python tail + postprocess_arrays, on a corpus with 1..5-passage articles."""
+    from emdr2_b200.titlemap import NeighbourTable
+    from emdr2_b200.tokens import FlatTokenStore
+    rng = np.random.RandomState(21)
+    titlemap, passages, titles = _flat_corpus(rng)
+    n = len(passages)
+    flat_p, flat_t = FlatTokenStore.from_arrays(passages, dtype=dtype), FlatTokenStore.from_arrays(titles, dtype=dtype)
+    assert len(flat_p) == n and np.array_equal(flat_p[7], passages[7]) and np.array_equal(flat_t[-1], titles[-1])
+    b, k = 4, 6
+    topk_ids = np.stack([rng.choice(np.arange(1, n + 1), size=k + 1, replace=False) for _ in range(b)]).astype(np.int64)
+    uids = [-1, int(topk_ids[1, 2]), -3, int(topk_ids[3, 0])]          # two questions drop their own passage
+    qt5 = [rng.randint(1, 50, size=8).tolist() + [0] * 8 for _ in range(b)]
+    qlen = [8, 5, 0, 3]
+    q = torch.zeros(b, 4)
+    slow = _FixedSearchRetriever(topk_ids, passages, titles, titlemap)
+    assert not slow.supports_packed
+    nested, _ = slow.get_topk(q, as_arrays=True)
+    fast = _FixedSearchRetriever(topk_ids, flat_p, flat_t, NeighbourTable(titlemap))
+    assert fast.supports_packed
+    packed, dist = fast.get_topk(q, as_packed=True)
+    assert dist.dtype == torch.float16 and len(packed) == b
+    # the packed form describes exactly the nested one
+    for (ids_a, texts_a), (ids_b, texts_b) in zip(nested, packed.to_nested()):
+        assert list(ids_a) == list(ids_b)
+        for (docs_a, main_a, title_a), (docs_b, main_b, title_b) in zip(texts_a, texts_b):
+            assert main_a == main_b and np.array_equal(title_a, title_b) and len(docs_a) == len(docs_b)
+            assert all(np.array_equal(x, y) for x, y in zip(docs_a, docs_b))
+    want = formatter.postprocess_arrays(uids, qt5, qlen, nested, k, 40, 96, 2, 3, 0)
+    got, lens = formatter.format_passages_native(uids, qt5, qlen, packed, k, 40, 96, 2, 3, 0)
+    for w, g in zip(want, got):
+        assert np.array_equal(w, g)
+    via_nested, lens2 = formatter.format_passages_native(uids, qt5, qlen, nested, k, 40, 96, 2, 3, 0)
+    assert lens == lens2 and all(np.array_equal(x, y) for x, y in zip(lens.rows, lens2.rows))
+    t = formatter.postprocess(uids, qt5, qlen, packed, k, 40, 96, 2, 3, 0, device="cpu")
+    assert torch.equal(t[2], torch.from_numpy(want[2])) and torch.equal(t[0], torch.from_numpy(want[0]))
+
+
+def test_flat_store_checks():
+    from emdr2_b200.tokens import FlatTokenStore
+    with pytest.raises(TypeError):
+        FlatTokenStore(np.zeros(4, dtype=np.float32), [0, 4])
+    with pytest.raises(ValueError):
+        FlatTokenStore(np.zeros(4, dtype=np.int64), [0, 5])
+    st = FlatTokenStore(np.arange(10, dtype=np.int32), [0, 3, 3, 10])
+    assert [len(st[i]) for i in range(3)] == [3, 0, 7] and st.token_bytes == 4
+    off, ln = st.spans(np.array([[2, -1], [0, 1]]))
+    assert off.tolist() == [[3, 0], [0, 3]] and ln.tolist() == [[7, 0], [3, 0]]
+    with pytest.raises(IndexError):
+        st.spans([3])
+
+
 def _loss_golden():
     with np.load(os.path.join(GOLDEN, "losses_ref.npz")) as z:
         return {k: torch.from_numpy(z[k]) if z[k].ndim else z[k] for k in z.files}
