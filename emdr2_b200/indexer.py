@@ -14,6 +14,7 @@ The batch source is any iterable of (row_id int64 [b], context_tokens int64 [b, 
 context_types int64 [b, s]) — `get_open_retrieval_batch` (megatron/data/orqa_wiki_dataset.py) with
 the dense mask dropped, since the kernels derive it from the token ids.
 """
+import numpy as np
 import torch
 
 from .store import EvidenceStore
@@ -40,6 +41,14 @@ class IndexBuilder(object):
             m = m.module
         return m.context_model if hasattr(m, "context_model") else m
 
+    @staticmethod
+    def _tower_takes_lengths(tower):
+        import inspect
+        try:
+            return "row_lengths" in inspect.signature(tower.forward).parameters
+        except (TypeError, ValueError):
+            return False
+
     def track_and_report_progress(self, batch_size):
         self.iteration += 1
         self.total_processed += batch_size * self.num_total_builders
@@ -56,8 +65,15 @@ class IndexBuilder(object):
         tower = self._context_tower()
         for row_id, tokens, types in self.batches:
             dev = next(tower.parameters()).device
+            kw = {}
+            if not tokens.is_cuda and self._tower_takes_lengths(tower):
+                # lengths are free on the host: the tower then skips all-padding columns and runs the
+                # batch length-bucketed (blocks.py: encode); CLS embeddings are unchanged
+                t = tokens.numpy()
+                lens = ((t != 0) * np.arange(1, t.shape[1] + 1)).max(axis=1)
+                kw = dict(max_len=int(lens.max()) if lens.size else 0, row_lengths=lens)
             with torch.no_grad():
-                emb = tower(tokens.to(dev, non_blocking=True), None, types.to(dev, non_blocking=True))
+                emb = tower(tokens.to(dev, non_blocking=True), None, types.to(dev, non_blocking=True), **kw)
             self.track_and_report_progress(batch_size=len(row_id))
             yield row_id, emb
 

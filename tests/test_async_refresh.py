@@ -32,7 +32,7 @@ class StubTower(torch.nn.Module):
         super().__init__()
         self.version = torch.nn.Parameter(torch.zeros(1))
 
-    def forward(self, tokens, mask, types):
+    def forward(self, tokens, mask, types, max_len=None, row_lengths=None):
         base = tokens[:, :1].float() * torch.arange(1, DIM + 1).float()[None]
         return (base + 1000.0 * self.version.detach()).to(torch.float16)
 

@@ -176,6 +176,28 @@ def test_retrieve_and_read_forward_tiny(tmp_path, dtype):
     assert bucketed[2].shape == ev[2].shape
     assert torch.equal(bucketed[0][live], lm_logits[live]) and torch.equal(bucketed[1], topk_log_probs)
 
+    # ---- evaluation decoding (search_strategy.py) through the real model: greedy tokens equal a greedy
+    # decode of the oracle reader wherever the oracle's top-2 logit margin exceeds the 16-bit tolerance
+    from emdr2_b200 import search_strategy as ss
+    bos, eos = 3, TINY["vocab"] - 1
+    inputs = (uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV), torch.tensor(q_len).to(DEV))
+    greedy = ss.reader_generate(model, inputs, max_decode_len=4, bos_id=bos, eos_id=eos, beam_size=1,
+                                topk_evidence=TOPK)
+    beam = ss.reader_generate(model, inputs, max_decode_len=4, bos_id=bos, eos_id=eos, beam_size=3,
+                              topk_evidence=TOPK)
+    assert len(greedy) == bsz == len(beam) and all(1 <= len(g) <= 4 for g in greedy)
+    enc_flat, ids_flat = enc.reshape(bsz, TOPK * S, -1), ext_t.reshape(bsz, TOPK * S)
+    y = torch.full((bsz, 1), bos, dtype=torch.int64)
+    for step in range(4):
+        ologits = ob.t5_decode(y, enc_flat, ids_flat, wt5, TINY["heads"], TINY["layers"])[:, -1, :]
+        top2 = ologits.topk(2, dim=1)
+        for i in range(bsz):
+            done = eos in greedy[i][:step] or step >= len(greedy[i])
+            if not done and float(top2.values[i, 0] - top2.values[i, 1]) > 5e-2:
+                assert greedy[i][step] == int(top2.indices[i, 0]), (i, step)
+        nxt = torch.tensor([[g[step] if step < len(g) else eos] for g in greedy])
+        y = torch.cat([y, nxt], dim=1)
+
     # ---- losses (a10) on the GPU logits vs fp32 torch on the oracle logits
     lm_loss = losses.reader_cross_entropy(lm_logits, labels.to(DEV), loss_mask.to(DEV))
     want_lm = (torch.nn.functional.cross_entropy(want_logits.view(-1, TINY["vocab"]), labels.view(-1),
