@@ -2,6 +2,7 @@
 cases produced by the reference's own functions (tests/golden/make_formatter_golden.py)."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -333,3 +334,29 @@ def test_token_logprob_large_vocab():
     want[5] = 0
     assert torch.allclose(lse, want_lse, rtol=1e-5, atol=1e-4)
     assert torch.allclose(lp, want, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/megatron"), reason="reference not mounted")
+@pytest.mark.parametrize("dtype", [np.uint16, np.int32])
+def test_flat_store_wraps_the_reference_indexed_dataset_without_copying(tmp_path, dtype):
+    """FlatTokenStore.from_indexed_dataset over a real MMapIndexedDataset written by the reference's own
+    builder (megatron/data/indexed_dataset.py): same documents, token buffer shared with the mmap."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_mips_golden
+    make_mips_golden.install_shims()
+    from megatron.data import indexed_dataset as ref
+    from emdr2_b200.tokens import FlatTokenStore
+    rng = np.random.RandomState(3)
+    docs = [rng.randint(1, 30000, size=int(rng.randint(1, 50))) for _ in range(40)]
+    prefix = str(tmp_path / "evidence_text")
+    builder = ref.MMapIndexedDatasetBuilder(ref.data_file_path(prefix), dtype=dtype)
+    for d in docs:
+        builder.add_item(torch.from_numpy(d.astype(np.int64)))
+        builder.end_document()
+    builder.finalize(ref.index_file_path(prefix))
+    ds = ref.MMapIndexedDataset(prefix)
+    store = FlatTokenStore.from_indexed_dataset(ds)
+    assert len(store) == len(docs) == len(ds) and store.token_bytes == np.dtype(dtype).itemsize
+    for i, d in enumerate(docs):
+        assert np.array_equal(store[i], d) and np.array_equal(ds[i], store[i])
+    assert np.shares_memory(store.tokens, np.frombuffer(ds._bin_buffer, dtype=dtype))
