@@ -84,6 +84,22 @@ def finish_beam(outs, total_score, batchsize, eos_id):
     return id_list, score_list
 
 
+class _ReaderState(object):
+    """What `EMDR2Model.forward` returns beside the logits and takes back on the next call: the encoder
+    states of the retrieved passages, their ids (for the cross-attention mask) and the retriever's
+    log-probabilities.  None before the first call, which retrieves and encodes."""
+
+    def __init__(self):
+        self.hidden = self.ids_unflat = self.topk_log_probs = None
+
+    def step(self, model, question, decoder_ids):
+        """Next-token logits [rows, vocab] (fp32) for the hypotheses in decoder_ids [rows, t]."""
+        logits, self.topk_log_probs, self.hidden, self.ids_unflat = model(
+            *question, decoder_ids, all_query_context_hidden_states=self.hidden,
+            all_query_context_ids_unflat=self.ids_unflat, topk_log_probs=self.topk_log_probs)
+        return logits[:, -1, :].float()
+
+
 class BeamSearch(object):
     def __init__(self, max_decode_len, bos_id, eos_id, beam_size=5, alpha=0.6, topk_evidence=-1):
         self.max_decode_length = max_decode_len
@@ -95,21 +111,18 @@ class BeamSearch(object):
 
     def generate_output(self, model, query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5,
                         query_ids_t5_len):
-        batch = query_ids_bert.shape[0]
-        dev = query_ids_bert.device
+        question = (query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5, query_ids_t5_len)
+        batch, dev = query_ids_bert.shape[0], query_ids_bert.device
+        state = _ReaderState()
         y_block = torch.full((batch, 1), self.bos_id, dtype=torch.int64, device=dev)
         outs = torch.full((batch * self.k, 1), self.bos_id, dtype=torch.int64, device=dev)
         total_score = None
-        hidden = ids_unflat = topk_log_probs = None
         for _ in range(self.max_decode_length):
-            logits, topk_log_probs, hidden, ids_unflat = model(
-                query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5, query_ids_t5_len, y_block,
-                all_query_context_hidden_states=hidden, all_query_context_ids_unflat=ids_unflat,
-                topk_log_probs=topk_log_probs)
-            topk_score, topk = torch.topk(F.log_softmax(logits[:, -1, :].float(), dim=1), self.k)
+            topk_score, topk = torch.topk(F.log_softmax(state.step(model, question, y_block), dim=1), self.k)
             assert float(topk_score.max()) <= 0.0
-            outs, total_score, ids_unflat, hidden, topk_log_probs = update_beam_state(
-                outs, total_score, topk, topk_score, self.eos_id, self.alpha, ids_unflat, hidden, topk_log_probs)
+            outs, total_score, state.ids_unflat, state.hidden, state.topk_log_probs = update_beam_state(
+                outs, total_score, topk, topk_score, self.eos_id, self.alpha, state.ids_unflat, state.hidden,
+                state.topk_log_probs)
             y_block = outs
             if bool((outs == self.eos_id).any(dim=1).all()):
                 break                    # every hypothesis has produced EOS
@@ -127,17 +140,13 @@ class SampleOrGreedySearch(object):
 
     def generate_output(self, model, query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5,
                         query_ids_t5_len):
-        batch = query_ids_bert.shape[0]
-        dev = query_ids_bert.device
+        question = (query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5, query_ids_t5_len)
+        batch, dev = query_ids_bert.shape[0], query_ids_bert.device
+        state = _ReaderState()
         y_block = torch.full((batch, 1), self.bos_id, dtype=torch.int64, device=dev)
         eos_seen = torch.zeros(batch, dtype=torch.bool, device=dev)
-        hidden = ids_unflat = topk_log_probs = None
         for _ in range(self.max_decode_length):
-            logits, topk_log_probs, hidden, ids_unflat = model(
-                query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5, query_ids_t5_len, y_block,
-                all_query_context_hidden_states=hidden, all_query_context_ids_unflat=ids_unflat,
-                topk_log_probs=topk_log_probs)
-            last = logits[:, -1, :].float()
+            last = state.step(model, question, y_block)
             if self.sample:
                 ys = torch.multinomial(F.softmax(last, dim=1), num_samples=1).reshape(-1)
             else:
