@@ -133,6 +133,23 @@ def _run(rank, world, n_train, port, tmp, mode, rounds, interval):
     dist.destroy_process_group()
 
 
+def _spawn(world, n_train, tmp, mode, rounds, interval, attempts=2):
+    """mp.spawn with one retry on a fresh port: the rendezvous port is picked by bind-and-release, which
+    another process on the machine can win in between."""
+    import torch.multiprocessing as mp
+    for attempt in range(attempts):
+        try:
+            mp.spawn(_run, args=(world, n_train, _free_port(), tmp, mode, rounds, interval), nprocs=world, join=True)
+            return
+        except Exception:
+            if attempt + 1 == attempts:
+                raise
+            for name in os.listdir(tmp):          # leave no half-written state behind
+                path = os.path.join(tmp, name)
+                if os.path.isfile(path):
+                    os.remove(path)
+
+
 def _logs(tmp, world):
     out = []
     for r in range(world):
@@ -144,9 +161,8 @@ def _logs(tmp, world):
 def test_store_handover_world3_gloo(tmp_path):
     """1 trainer + 2 indexers, the reference's pickle hand-over: every published index holds every
     document once, built with the weights of the checkpoint saved at the previous hand-over."""
-    import torch.multiprocessing as mp
     world, n_train, rounds = 3, 1, 3
-    mp.spawn(_run, args=(world, n_train, _free_port(), str(tmp_path), "store", rounds, 2), nprocs=world, join=True)
+    _spawn(world, n_train, str(tmp_path), "store", rounds, 2)
     logs = _logs(str(tmp_path), world)
     reloads = [e for e in logs[0] if e[0] == "reload"]
     handovers = [e for e in logs[0] if e[0] == "handover"]
@@ -164,9 +180,8 @@ def test_store_handover_world3_gloo(tmp_path):
 def test_direct_handover_world4_gloo(tmp_path):
     """2 trainers + 2 indexers, direct hand-over: each trainer ends up with exactly its torch.chunk
     row range, ids attached, without any file."""
-    import torch.multiprocessing as mp
     world, n_train, rounds = 4, 2, 2
-    mp.spawn(_run, args=(world, n_train, _free_port(), str(tmp_path), "direct", rounds, 1), nprocs=world, join=True)
+    _spawn(world, n_train, str(tmp_path), "direct", rounds, 1)
     logs = _logs(str(tmp_path), world)
     assert not os.path.exists(str(tmp_path / "evidence.pkl"))
     for t in range(n_train):

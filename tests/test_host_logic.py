@@ -152,7 +152,13 @@ def _worker(rank, world, port, n, out_dir):
 def test_sharded_search_world2_gloo_equals_unsharded_oracle(tmp_path, n):
     import torch.multiprocessing as mp
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    for attempt in range(2):          # one retry on a fresh port (bind-and-release can lose the port)
+        try:
+            mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+            break
+        except Exception:
+            if attempt:
+                raise
     r = [np.load(str(tmp_path / ("r%d.npz" % i))) for i in range(world)]
     assert np.array_equal(r[0]["scores"], r[1]["scores"]) and np.array_equal(r[0]["ids"], r[1]["ids"])
     rng = np.random.RandomState(11)
