@@ -23,8 +23,9 @@ emdr2_b200/indexer.py:IndexBuilder.  Two hand-over modes:
             reloads that file (emdr2_model.py:426-432).  Byte-compatible with a reference trainer.
   "direct"  B200-native: indexer i sends its (ids, rows) blocks straight to the
             trainer rank that owns those rows under the `torch.chunk` split; the trainer receives them
-            into a STANDBY shard buffer in HBM while it keeps searching the live one, and swaps the two
-            at the hand-over point.  No pickle, no host copy of the 32 GB matrix.  `ShardReceiver` /
+            into a STANDBY shard buffer in HBM at the hand-over point (the live shard stays valid and
+            searchable until the swap) and then swaps the two.  No pickle, no host copy of the 32 GB
+            matrix; the indexers keep their rows in their own HBM until the trainers are ready for them.  `ShardReceiver` /
             `send_rows_to_owners` implement the exchange over any torch.distributed backend (NCCL
             between GPUs; Gloo in the CPU tests).
 """
