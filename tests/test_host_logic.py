@@ -213,3 +213,38 @@ def test_k_above_the_kernel_limit_is_exact_by_range_refinement(clustered):
     assert dist16.dtype == torch.float16 and idx32.dtype == torch.int32 and idx32.shape == (nq, k)
     small_s, small_i = index.search(torch.from_numpy(queries), 7)
     assert np.array_equal(small_i.numpy(), got_i.numpy()[:, :7]) or not free[:, :7].all()
+
+
+def _worker_large_k(rank, world, port, out_dir):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rng = np.random.RandomState(31)
+    n, d, k = 1100, 16, 100
+    rows = (rng.randint(-127, 128, size=(n, d)) / 64).astype(np.float16)
+    queries = torch.from_numpy((rng.randint(-127, 128, size=(4, d)) / 64).astype(np.float16))
+    index = CpuDoubleIndex(d, device="cpu", group=dist.group.WORLD)
+    index.add_arrays(np.arange(1, n + 1, dtype=np.int64), rows)
+    scores, ids = index.search(queries, k)
+    np.savez(os.path.join(out_dir, "k%d.npz" % rank), scores=scores.numpy(), ids=ids.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_k_above_the_kernel_limit_row_sharded_world2_gloo(tmp_path):
+    """k = 100 on two ranks: each rank refines its own row range, one all-gather of [nq, 100] pairs, merge."""
+    import torch.multiprocessing as mp
+    for attempt in range(2):
+        try:
+            mp.spawn(_worker_large_k, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+            break
+        except Exception:
+            if attempt:
+                raise
+    rng = np.random.RandomState(31)
+    rows = (rng.randint(-127, 128, size=(1100, 16)) / 64).astype(np.float16)
+    queries = (rng.randint(-127, 128, size=(4, 16)) / 64).astype(np.float16)
+    want_s, want_i, ties = oracle.mips_topk(rows, queries, 100, id_base=1, want_ties=True)
+    for rank in range(2):
+        r = np.load(str(tmp_path / ("k%d.npz" % rank)))
+        assert np.array_equal(r["scores"], want_s)
+        assert np.array_equal(r["ids"][ties == 0], want_i[ties == 0])
