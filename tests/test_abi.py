@@ -82,3 +82,23 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), fn
                 assert "liboracle" not in text, fn
+
+
+def test_the_abi_is_usable_from_plain_c(tmp_path):
+    """tests/c/abi_smoke.c compiled with gcc against include/emdr2_b200.h and linked to the library:
+    version string, the host-side formatter on a tiny batch, the error convention."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lib = build_mod.build()
+    exe = str(tmp_path / "abi_smoke")
+    src = os.path.join(ROOT, "tests", "c", "abi_smoke.c")
+    libdir = os.path.dirname(lib)
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                          "-L", libdir, "-lemdr2_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stderr)
+    assert run.stdout.startswith("emdr2_b200")
