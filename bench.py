@@ -366,14 +366,14 @@ def run_reference_arm(a):
     for _ in range(max(1, a.steps)):             # bounded: stop early rather than run for hours
         t = mips_step() * mips_scale
         if read:
-            t += read[0]() * read[2]
+            t += read[0]() * read[2] * a.gpus        # the step reads batch * gpus questions (weak scaling)
         times.append(t)
         if time.perf_counter() - wall0 > budget_s:
             break
     sec = statistics.mean(times)
     queries_per_step = nq if a.retrieve_only else a.batch * a.gpus
     value = queries_per_step / sec
-    full_sample = sample + ("" if not read else "; " + read[1])
+    full_sample = sample + ("" if not read else "; " + read[1] + (", x%d ranks' questions" % a.gpus if a.gpus > 1 else ""))
     line = {
         "impl": "reference", "metric": metric_name(a), "value": value, "unit": "queries/s", "n_gpus": a.gpus,
         "steps": len(times), "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
