@@ -426,6 +426,8 @@ class Dist(object):
         torch.cuda.set_device(self.local_rank)
         self.device = torch.device("cuda", self.local_rank)
         if self.world > 1:
+            # NCCL prints its version banner to stdout when NCCL_DEBUG is set; stdout carries the JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.device)
         self.group = dist.group.WORLD if self.world > 1 else None
 
