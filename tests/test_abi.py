@@ -58,6 +58,9 @@ def test_sass_contains_tcgen05_and_tma():
     sass = subprocess.run([cuobjdump, "-sass", build_mod.build()], capture_output=True, text=True).stdout
     for mnemonic in ["UTCHMMA", "LDTM", "UTMALDG"]:
         assert mnemonic in sass, mnemonic
+    # the CTA-pair GEMM (cta_group::2 MMA, pair TMA loads, multicast commits) and the packed-fp32 GeLU
+    for mnemonic in ["UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "FFMA2", "FMUL2", "STTM"]:
+        assert mnemonic in sass, mnemonic
 
 
 def test_no_cpu_fallback_without_a_device():
