@@ -443,6 +443,13 @@ class Dist(object):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
     def timed(self, step_fn, steps):
         torch = self.torch
         self.barrier()
@@ -460,6 +467,63 @@ class Dist(object):
         if self.world > 1:
             self.dist.barrier()
             self.dist.destroy_process_group()
+
+
+def retrieval_parity(d, index, rows, row_lo, queries, k, chunk=1 << 18):
+    """Outside the timed region: the ids `index.search` returns for `queries` (the same collective call
+    the step makes) against an INDEPENDENT exact search of the same resident rows — fp64 chunked
+    torch.matmul over this rank's shard, exact local top-k, all-gather of the per-rank lists over NCCL
+    and a (score desc, id asc) sort: the oracle's ranking definition (oracle/mips_oracle.c) evaluated
+    with library calls only, none of this repo's kernels.  Tie-aware like
+    tests/helpers.assert_ids_equal_outside_ties: ranks whose neighbouring exact scores are within
+    2^-20 relative may swap (fp32 tensor-core accumulation order) and are compared as sets."""
+    torch = d.torch
+    got_s, got_i = index.search(queries, k)                   # [nq, k] on every rank
+    q64 = queries.double()
+    nq = q64.shape[0]
+    n_local = rows.shape[0]
+    kk = k + 1                                                # one extra rank: shows a tie at the cut
+    dev = rows.device
+    best_s = torch.zeros((nq, 0), dtype=torch.float64, device=dev)
+    best_i = torch.zeros((nq, 0), dtype=torch.int64, device=dev)
+    for r0 in range(0, n_local, chunk):
+        r1 = min(n_local, r0 + chunk)
+        s = q64 @ rows[r0:r1].double().T                      # exact products, fp64 accumulation
+        ids = torch.arange(row_lo + r0 + 1, row_lo + r1 + 1, device=dev).expand(nq, -1)
+        s, ids = torch.cat([best_s, s], 1), torch.cat([best_i, ids], 1)
+        top = torch.topk(s, min(kk, s.shape[1]), dim=1)
+        best_s, best_i = top.values, torch.gather(ids, 1, top.indices)
+    if best_s.shape[1] < kk:                                  # short / empty shard: pad like the kernel
+        pad = kk - best_s.shape[1]
+        best_s = torch.cat([best_s, torch.full((nq, pad), float("-inf"), dtype=torch.float64, device=dev)], 1)
+        best_i = torch.cat([best_i, torch.full((nq, pad), -1, dtype=torch.int64, device=dev)], 1)
+    if d.world > 1:
+        all_s = [torch.empty_like(best_s) for _ in range(d.world)]
+        all_i = [torch.empty_like(best_i) for _ in range(d.world)]
+        d.dist.all_gather(all_s, best_s.contiguous())
+        d.dist.all_gather(all_i, best_i.contiguous())
+        best_s, best_i = torch.cat(all_s, 1), torch.cat(all_i, 1)
+    order = torch.argsort(best_i, dim=1, stable=True)         # id asc, then score desc (stable)
+    best_s, best_i = torch.gather(best_s, 1, order), torch.gather(best_i, 1, order)
+    order = torch.argsort(best_s, dim=1, descending=True, stable=True)[:, :kk]
+    want_s, want_i = torch.gather(best_s, 1, order), torch.gather(best_i, 1, order)
+    w32 = want_s.float()
+    gap = (w32[:, :-1] - w32[:, 1:]).abs() <= w32[:, :-1].abs() * 2.0 ** -20      # [nq, k]
+    tie = torch.zeros((nq, kk), dtype=torch.bool, device=dev)
+    tie[:, :-1] |= gap
+    tie[:, 1:] |= gap
+    cut_tie = gap[:, -1]                                      # rank k ties with rank k+1
+    tie, want_s, want_i = tie[:, :k], want_s[:, :k], want_i[:, :k]
+    differ = (got_i != want_i) & ~tie
+    sets_equal = (torch.sort(got_i, 1).values == torch.sort(want_i, 1).values).all(dim=1) | cut_tie
+    scores_ok = bool(torch.allclose(got_s.double(), want_s, rtol=1e-5, atol=1e-6))
+    n_differ = int(differ.sum().item())
+    ok = n_differ == 0 and scores_ok and bool(sets_equal.all().item())
+    return {"ids": "identical" if ok else "DIFFERENT", "checked_rows": int(d.sum_over_ranks(n_local)),
+            "checked_queries": nq, "k": k, "ranks": d.world, "ids_differing_outside_ties": n_differ,
+            "ranks_in_numerical_ties": int(tie.sum().item()), "scores_within_1e-5": scores_ok,
+            "against": "independent fp64 chunked torch.matmul + exact top-k over the same resident rows, "
+                       "(score desc, id asc), gathered over all ranks; tie-aware (2^-20 relative)"}
 
 
 def mips_roofline(a, d, searcher, n_local, nq):
@@ -532,6 +596,7 @@ def run_retrieve_only(a):
         "gpu_launches": (2 if world == 1 else 3) * (-(-a.nq // 64)) * a.steps,
         "roofline": roof, "clocks": clocks.summary(),
     }
+    line["parity"] = retrieval_parity(d, index, rows, lo, q_dev[0], a.k)
     if world == 1 and not a.no_gpu_reference:
         line["gpu_reference"] = gpu_reference_leg(torch, rows, q_dev, a)
     line["cpu_baseline"] = cpu_baseline(a) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
@@ -725,6 +790,16 @@ def run_retrieve_read(a):
                                     "attention_tflops": attn_tf},
         "clocks": clocks.summary(),
     }
+    # parity of THIS step's retrieval (outside the timed region): the question embeddings the query tower
+    # produces for the batch, gathered over the ranks exactly as get_topk does, searched by the index
+    with torch.no_grad():
+        q_emb = model.retriever_embedder(dev["q_bert"], None, dev["q_types"], "query").to(edtype).contiguous()
+        if world > 1:
+            all_q = torch.empty((world * q_emb.shape[0], q_emb.shape[1]), dtype=q_emb.dtype, device=device)
+            d.dist.all_gather_into_tensor(all_q, q_emb)
+        else:
+            all_q = q_emb
+        line["parity"] = retrieval_parity(d, retriever.mips_index, rows, lo, all_q, retriever.topk)
     line["cpu_baseline"] = cpu_baseline(a) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
     if rank == 0:
         print(json.dumps(line), flush=True)

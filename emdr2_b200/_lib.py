@@ -118,9 +118,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
-    if not os.path.exists(path):
-        path = _build.build()
+    path = _build.build()        # no-op when the stamp matches the sources; never loads a stale library
     lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch: fail loudly

@@ -346,6 +346,17 @@ class BertTower(nn.Module):
     def hidden_states(self, input_ids, tokentype_ids=None):
         return self.language_model.encode(input_ids, tokentype_ids)
 
+    def state_dict_for_save_checkpoint(self, destination=None, prefix='', keep_vars=False):
+        """{'language_model': {...}} exactly as PretrainedBertModel writes it (dualencoder_model.py:183-189),
+        so the reference's load_state_dict (:191-194) reads checkpoints saved here."""
+        return {"language_model": language_model_checkpoint(self.language_model, keep_vars)}
+
+    def load_state_dict(self, state_dict, strict=True):
+        if "language_model" in state_dict and isinstance(state_dict["language_model"], dict):
+            load_reference_state_dict(self, state_dict, strict)
+            return
+        return super().load_state_dict(state_dict, strict)
+
 
 class _LMHead(nn.Module):
     def __init__(self, vocab, dtype):
@@ -390,6 +401,17 @@ class T5Reader(nn.Module):
         loss = -ag.token_logprob(logits, lm_labels)          # vocab_parallel_cross_entropy (t5_model.py:139-146)
         return loss, enc
 
+    def state_dict_for_save_checkpoint(self, destination=None, prefix='', keep_vars=False):
+        """{'language_model': {...}, 'lm_head': {'bias': ..}} as T5Model writes it (t5_model.py:156-168)."""
+        return {"language_model": language_model_checkpoint(self.language_model, keep_vars),
+                "lm_head": _module_state(self.lm_head, keep_vars)}
+
+    def load_state_dict(self, state_dict, strict=True):
+        if "language_model" in state_dict and isinstance(state_dict["language_model"], dict):
+            load_reference_state_dict(self, state_dict, strict)
+            return
+        return super().load_state_dict(state_dict, strict)
+
 
 # ---------------------------------------------------------------------- checkpoint compatibility
 def _flatten(nested, prefix=""):
@@ -401,6 +423,24 @@ def _flatten(nested, prefix=""):
         else:
             flat[key] = v
     return flat
+
+
+def _module_state(module, keep_vars=False):
+    return {k: (v if keep_vars else v.detach()) for k, v in module.state_dict(keep_vars=True).items()}
+
+
+def language_model_checkpoint(lm, keep_vars=False):
+    """The nested dict TransformerLanguageModel.state_dict_for_save_checkpoint writes
+    (language_model.py:367-387, :183-198): 'embedding' -> one flat state dict per table,
+    'encoder' / 'decoder' -> the flat state dict of the stack ('layers.0.input_layernorm.weight', ...)."""
+    emb = {"word_embeddings": _module_state(lm.embedding.word_embeddings, keep_vars),
+           "position_embeddings": _module_state(lm.embedding.position_embeddings, keep_vars)}
+    if lm.embedding.tokentype_embeddings is not None:
+        emb["tokentype_embeddings"] = _module_state(lm.embedding.tokentype_embeddings, keep_vars)
+    out = {"embedding": emb, "encoder": _module_state(lm.encoder, keep_vars)}
+    if lm.add_decoder:
+        out["decoder"] = _module_state(lm.decoder, keep_vars)
+    return out
 
 
 def load_reference_state_dict(module, state_dict, strict=True):

@@ -55,6 +55,24 @@ class DualEncoder(nn.Module):
             if self.use_context_model else None
         return q, c
 
+    def state_dict_for_save_checkpoint(self, destination=None, prefix='', keep_vars=False):
+        """{'query_model': {'language_model': ..}, 'context_model': ..} (dualencoder_model.py:84-98)."""
+        out = {}
+        if self.use_query_model:
+            out["query_model"] = self.query_model.state_dict_for_save_checkpoint(destination, prefix, keep_vars)
+        if self.use_context_model:
+            out["context_model"] = self.context_model.state_dict_for_save_checkpoint(destination, prefix, keep_vars)
+        return out
+
+    def load_state_dict(self, state_dict, strict=True):
+        if any(isinstance(v, dict) for v in state_dict.values()):      # the reference's nested layout (:100-109)
+            if self.use_query_model:
+                self.query_model.load_state_dict(state_dict["query_model"], strict)
+            if self.use_context_model:
+                self.context_model.load_state_dict(state_dict["context_model"], strict)
+            return
+        return super().load_state_dict(state_dict, strict)
+
 
 class EMDR2Model(nn.Module):
     """cfg: dict(hidden, heads, layers, ffn, vocab, max_pos, dtype).  `settings` carries what the
@@ -153,8 +171,10 @@ class EMDR2Model(nn.Module):
         return lm_logits, topk_log_probs, all_query_context_hidden_states, all_query_context_ids_unflat
 
     def state_dict_for_save_checkpoint(self, destination=None, prefix='', keep_vars=False):
-        return {self._language_model_key: self.language_model.state_dict(),
-                self._retriever_model_key: self.retriever_model.state_dict()}
+        """The reference's nested layout (emdr2_model.py:217-226): what its T5Model / DualEncoderModel
+        load_state_dict index into, so a reference indexer or trainer reads checkpoints saved here."""
+        return {self._language_model_key: self.language_model.state_dict_for_save_checkpoint(destination, prefix, keep_vars),
+                self._retriever_model_key: self.retriever_model.state_dict_for_save_checkpoint(destination, prefix, keep_vars)}
 
     def load_state_dict(self, state_dict, strict=True):
         if self._language_model_key in state_dict:

@@ -107,7 +107,11 @@ def attention(q, k, v, batch, heads, sq, sk, q_pad=None, k_pad=None, causal=Fals
             if tuple(m.shape) != (batch, n):
                 raise ValueError("%s must be [batch, %d]" % (name, n))
         masks.append(m)
-    lse = torch.empty((batch, heads, sq), dtype=torch.float32, device=device) if return_lse else None
+    # all-padding query blocks (q_live == 0) are stored as zeros and never write their lse: define it (0)
+    # so that consumers that combine partial results by lse (autograd._cross_attention_split) stay finite
+    lse = None
+    if return_lse:
+        lse = (torch.zeros if q_live is not None else torch.empty)((batch, heads, sq), dtype=torch.float32, device=device)
     if scale is None:
         scale = 1.0 / 8.0
     lib = _lib.load()
