@@ -84,7 +84,9 @@ def test_k100_row_range_refinement_on_the_gpu_vs_oracle(clustered):
     rows = (rng.randint(-127, 128, size=(n, d)) / 64).astype(np.float16)
     queries = (rng.randint(-127, 128, size=(nq, d)) / 64).astype(np.float16)
     if clustered:
-        rows[1000:1400] = (queries[0].astype(np.float32) * 1.5).astype(np.float16) + rows[1000:1400] / 16
+        # (k/64) * (3k'/128 + k''/256): every product is an integer / 2^14 and the 128-term sums stay below 2^24 of
+        # those units, so fp32 accumulation is exact in any order
+        rows[1000:1400] = (queries[0].astype(np.float32) * 1.5).astype(np.float16) + rows[1000:1400] / 4
     ids = np.arange(1, n + 1, dtype=np.int64)          # ascending ids: row order == id order
     index = B200BruteForceIndex(d, device=DEV)
     calls = []
