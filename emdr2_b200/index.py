@@ -104,15 +104,40 @@ class B200BruteForceIndex(object):
         if self.embed_data is not None:
             path = self.embed_data.embedding_path
             cls = type(self.embed_data)
-            self.embed_data = cls(path)
+            try:
+                fresh = cls(path, load_from_path=False)
+            except TypeError:            # a store class without that switch: let it load itself
+                self.embed_data = cls(path)
+            else:
+                if hasattr(self.embed_data, "format"):
+                    fresh.format = self.embed_data.format
+                self.embed_data = fresh
+                self._load_store(fresh)
         self._set_mips_index()
 
     def update_index(self):
-        """Reload the store from disk and rebuild (:232-239); called after each index refresh."""
+        """Reload the store from disk and rebuild (:232-239); called after each index refresh.  A store
+        that can load a row range (emdr2_b200/store.py: flat files, memory-mapped) is asked for this
+        rank's torch.chunk range only — no rank reads or holds the other ranks' rows."""
         self._release()
         if self.embed_data is not None:
-            self.embed_data.load_from_file()
+            self._load_store(self.embed_data)
         self._set_mips_index()
+
+    def _load_store(self, store):
+        import inspect
+        try:
+            ranged = "row_range" in inspect.signature(store.load_from_file).parameters
+        except (TypeError, ValueError):
+            ranged = False
+        if ranged and self.world > 1:
+            from .store import flat_exists, flat_shape
+            path = getattr(store, "embedding_path", None)
+            if path is not None and flat_exists(path):
+                n = flat_shape(path)[0]
+                store.load_from_file(row_range=chunk_range(n, self.world, self.rank))
+                return
+        store.load_from_file()
 
     def _release(self):
         if self._searcher is not None:
@@ -124,9 +149,23 @@ class B200BruteForceIndex(object):
         self.local_ids = None
 
     def add_embed_data(self, all_embed_data):
-        """Dict store -> this rank's resident shard + id map (:241-266)."""
-        ids, rows = dict_to_arrays(all_embed_data.embed_data)
+        """Store -> this rank's resident shard + id map (:241-266).  An array-backed store hands its
+        blocks over as they are (`to_arrays`); a reference-style dict store is converted once."""
+        if hasattr(all_embed_data, "to_arrays"):
+            ids, rows = all_embed_data.to_arrays()
+        else:
+            ids, rows = dict_to_arrays(all_embed_data.embed_data)
+        loaded = getattr(all_embed_data, "loaded_range", None)
         all_embed_data.clear()           # the index owns the data now (:263)
+        if loaded is not None:           # the store held only this rank's slice [lo, hi) of N rows
+            lo, hi, n = loaded
+            want = chunk_range(n, self.world, self.rank)
+            if (lo, hi) != want:
+                raise ValueError("store slice [%d, %d) is not this rank's row range %s" % (lo, hi, want))
+            self.indices_arr = None
+            self.add_local_shard(torch.from_numpy(np.ascontiguousarray(ids)),
+                                 torch.from_numpy(np.ascontiguousarray(rows)), num_rows=n, row_lo=lo)
+            return
         self.add_arrays(ids, rows)
 
     def add_arrays(self, ids, rows):

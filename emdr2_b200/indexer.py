@@ -87,7 +87,7 @@ class IndexBuilder(object):
         if self.is_main_builder:
             self.evidence_embedder_obj.merge_shards_and_save()
             if expected_total is not None:      # "every single piece of data was embedded" (:110)
-                assert len(self.evidence_embedder_obj.embed_data) == expected_total
+                assert len(self.evidence_embedder_obj) == expected_total
         self.evidence_embedder_obj.clear()
         self._barrier()
 

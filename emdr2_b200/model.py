@@ -78,7 +78,8 @@ class EMDR2Model(nn.Module):
     """cfg: dict(hidden, heads, layers, ffn, vocab, max_pos, dtype).  `settings` carries what the
     reference reads from get_args()/tokenizers on every call (emdr2_model.py:92,250-303):
     topk_retrievals, seq_length, seq_length_ret, retriever_score_scaling, update_retriever,
-    cls_id, sep_id, pad_id; trim_padding (default True) runs the towers only on the columns that hold
+    no_query_embedder_training / no_context_embedder_training (detach that tower's embeddings, :103-104,
+    :130-131), disable_retriever_dropout (:69-77), cls_id, sep_id, pad_id; trim_padding (default True) runs the towers only on the columns that hold
     a real token in at least one sequence of the batch (lengths are known on the host from the
     formatter), and length_buckets (default True) additionally lets the towers sort the B*K rows by
     length and run them as a few token-packed buckets (blocks.py: `encode`); both leave every
@@ -98,11 +99,12 @@ class EMDR2Model(nn.Module):
     def retriever_embedder(self, tokens, mask, types, embedder_type, disable_dropout=False, max_len=None,
                            row_lengths=None):
         m = self.retriever_model
-        if embedder_type == "query":
-            return m.embed_text(m.query_model, tokens, mask, types, max_len=max_len, row_lengths=row_lengths)
-        if embedder_type == "context":
-            return m.embed_text(m.context_model, tokens, mask, types, max_len=max_len, row_lengths=row_lengths)
-        raise ValueError("Invalid embedder type.")
+        if embedder_type not in ("query", "context"):
+            raise ValueError("Invalid embedder type.")
+        tower = m.query_model if embedder_type == "query" else m.context_model
+        if disable_dropout:          # --disable-retriever-dropout: the reference puts the tower in eval mode (:69-77)
+            tower.eval()
+        return m.embed_text(tower, tokens, mask, types, max_len=max_len, row_lengths=row_lengths)
 
     def forward(self, query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5,
                 query_ids_t5_len, dec_ids, all_query_context_hidden_states=None,
@@ -116,7 +118,11 @@ class EMDR2Model(nn.Module):
         len_one = rows_one = None
 
         if all_query_context_hidden_states is None:
-            query_logits = self.retriever_embedder(query_ids_bert, query_mask_bert, query_types, "query")
+            no_ret_dropout = bool(st.get("disable_retriever_dropout", False))
+            query_logits = self.retriever_embedder(query_ids_bert, query_mask_bert, query_types, "query",
+                                                   disable_dropout=no_ret_dropout)
+            if st.get("no_query_embedder_training", False):        # emdr2_model.py:103-104
+                query_logits = query_logits.detach()
             with torch.no_grad():
                 if getattr(self.evidence_retriever, "supports_packed", False):
                     topk_evidence_data, _stale = self.evidence_retriever.get_topk(query_logits.detach(),
@@ -141,7 +147,10 @@ class EMDR2Model(nn.Module):
             s_ret = all_context_ids.shape[-1]
             all_context_logits = self.retriever_embedder(all_context_ids.reshape(-1, s_ret), None,
                                                          all_context_types.reshape(-1, s_ret), "context",
+                                                         disable_dropout=no_ret_dropout,
                                                          max_len=len_ctx, row_lengths=rows_ctx)
+            if st.get("no_context_embedder_training", False):      # emdr2_model.py:130-131
+                all_context_logits = all_context_logits.detach()
             all_context_logits = all_context_logits.reshape(bsize, topk, -1).float()
             topk_sim_scores = torch.bmm(query_logits.unsqueeze(1).float(), all_context_logits.transpose(1, 2))
             if st.get("retriever_score_scaling", True):

@@ -1,0 +1,136 @@
+"""The second consumers of the MIPS index and the BERT towers, driven through the sm_100a kernels
+(SURVEY §8 f-2 / f-4): the recall evaluator over B200FaissMIPSIndex at k = 100, the in-batch-negative
+retriever step over the DualEncoder towers (forward + backward), and an index refresh from the flat
+evidence store.  CPU-side logic of the same modules is covered in test_recall.py, test_dense_retriever.py
+and test_host_logic.py; here the engine underneath is the real one."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import TINY, assert_ids_equal_outside_ties, seeded_weights
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_recall_evaluator_top100_on_the_gpu_index():
+    """tasks/openqa/dense_retriever/evaluation/evaluate.py:123-168 on B200FaissMIPSIndex: k = 100 goes
+    through the exact row-range refinement over the real scan kernel; the rank at which each question's
+    answer-bearing passage appears, and hence every top-k accuracy, must equal the oracle's."""
+    from emdr2_b200 import recall
+    from emdr2_b200.index import B200FaissMIPSIndex
+    from oracle import mips as oracle
+    rng = np.random.RandomState(2)
+    n, d, nq, k = 20000, 64, 12, 100
+    rows = (rng.randint(-127, 128, size=(n, d)) / 64).astype(np.float16)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    gold = rng.choice(n, size=nq, replace=False)
+    # half of the questions sit near their passage, half are only weakly related (answer deep in the list)
+    pull = np.where(np.arange(nq) % 2 == 0, 2.0, 0.35)[:, None]
+    queries = (rows[gold].astype(np.float32) * pull + rng.randint(-64, 65, size=(nq, d)) / 64).astype(np.float16)
+    id2text = {int(i): ("filler text number %d" % i, "title") for i in ids}
+    answers = []
+    for qi, row in enumerate(gold):
+        id2text[int(ids[row])] = ("the answer is Zürich-%d indeed" % qi, "title")
+        answers.append(["zürich-%d" % qi])
+    index = B200FaissMIPSIndex(d, device=DEV)
+    index.add_arrays(ids, rows)
+    ev = recall.RecallEvaluator(index, id2text, topk_retrievals=k)
+    acc, stats, closest = ev.evaluate(torch.from_numpy(queries), answers)
+    want_s, want_i, ties = oracle.mips_topk(rows, queries, k, ids=ids, want_ties=True)
+    got_i = np.array([c[0] for c in closest])
+    assert_ids_equal_outside_ties(got_i, want_i, ties)
+    assert np.array_equal(np.array([c[1] for c in closest], dtype=np.float32), want_s)
+    for kk in (1, 5, 10, 20, 50, 100):
+        want = sum(bool((want_i[qi, :kk] == ids[gold[qi]]).any()) for qi in range(nq)) / nq
+        assert acc[kk] == want, (kk, acc[kk], want)
+    assert 0 < acc[1] <= acc[100]
+
+
+@pytest.mark.parametrize("with_neg", [False, True])
+def test_in_batch_negative_step_through_the_towers(with_neg):
+    """train_dense_retriever.py:89-196 with both BERT towers on the library kernels: loss, hit count and
+    parameter gradients against fp32 autograd of the block oracle on the same fp16-rounded weights.
+    Tolerance: loss 2e-3 absolute; gradients 4e-2 relative Frobenius (fp16 activations, two towers)."""
+    from emdr2_b200 import dense_retriever as dr
+    from emdr2_b200.model import DualEncoder
+    from oracle import blocks as ob
+    dtype = torch.float16
+    model = DualEncoder(dict(TINY, dtype=dtype)).to(DEV)
+    w32 = {}
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            w = seeded_weights(name, tuple(p.shape)).to(dtype)
+            p.copy_(w)
+            w32[name] = w.float().requires_grad_(True)
+    rng = np.random.RandomState(8)
+    b, s, neg = 4, 32, 3
+
+    def batch(rows):
+        ids = rng.randint(1, TINY["vocab"], size=(rows, s)).astype(np.int64)
+        for i, n in enumerate(rng.randint(6, s + 1, size=rows)):
+            ids[i, n:] = 0
+        return torch.from_numpy(ids), torch.from_numpy((rng.rand(rows, s) < 0.5).astype(np.int64) * (ids > 0))
+
+    q, qt = batch(b)
+    c, ct = batch(b)
+    ng, ngt = batch(neg) if with_neg else (None, None)
+    loss, stats = dr.forward_step(model, q.to(DEV), qt.to(DEV), c.to(DEV), ct.to(DEV),
+                                  None if ng is None else ng.to(DEV), None if ngt is None else ngt.to(DEV),
+                                  hidden_size=TINY["hidden"])
+    loss.backward()
+
+    def sub(prefix):
+        return {k[len(prefix):]: v for k, v in w32.items() if k.startswith(prefix)}
+
+    call = torch.cat([c, ng]) if with_neg else c
+    callt = torch.cat([ct, ngt]) if with_neg else ct
+    oq = ob.bert_pooled(q, qt, sub("query_model."), TINY["heads"], TINY["layers"])
+    oc = ob.bert_pooled(call, callt, sub("context_model."), TINY["heads"], TINY["layers"])
+    scores = oq @ oc.T / math.sqrt(TINY["hidden"])
+    lp = torch.log_softmax(scores, dim=1)
+    want = torch.nn.functional.nll_loss(lp, torch.arange(b))
+    want.backward()
+    assert abs(loss.item() - want.item()) < 2e-3
+    assert int(stats["correct_prediction_count"].item()) == int((lp.argmax(1) == torch.arange(b)).sum())
+    worst = 0.0
+    for name, p in model.named_parameters():
+        g = w32[name].grad
+        if g is None or float(g.norm()) == 0.0:
+            continue
+        worst = max(worst, ((p.grad.float().cpu() - g).norm() / g.norm()).item())
+    assert worst < 4e-2, worst
+
+
+def test_index_refresh_from_the_flat_store_on_the_gpu(tmp_path):
+    """emdr2_index.py:232-239 (`update_index`) over the flat evidence store: rows are memory-mapped and go
+    straight to HBM; results equal the oracle before and after the refresh."""
+    from emdr2_b200.index import B200BruteForceIndex
+    from emdr2_b200.store import EvidenceStore
+    from oracle import mips as oracle
+    path = str(tmp_path / "ev.pkl")
+    rng = np.random.RandomState(4)
+    n, d = 5000, 128
+    rows = (rng.randint(-127, 128, size=(n, d)) / 64).astype(np.float16)
+    queries = (rng.randint(-127, 128, size=(8, d)) / 64).astype(np.float16)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    st = EvidenceStore(path, load_from_path=False, rank=0, format="flat")
+    st.add_block_data(ids, rows)
+    st.save_shard()
+    st.merge_shards_and_save()
+    index = B200BruteForceIndex(d, EvidenceStore(path), device=DEV)
+    s0, i0 = index.search(torch.from_numpy(queries).to(DEV), 20)
+    w0 = oracle.mips_topk(rows, queries, 20, ids=ids)
+    assert np.array_equal(i0.cpu().numpy(), w0[1]) and np.array_equal(s0.cpu().numpy(), w0[0])
+    st2 = EvidenceStore(path, load_from_path=False, rank=0, format="flat")      # the refreshed embeddings
+    st2.add_block_data(ids, rows[::-1])
+    st2.save_shard()
+    st2.merge_shards_and_save()
+    index.update_index()
+    s1, i1 = index.search(torch.from_numpy(queries).to(DEV), 20)
+    w1 = oracle.mips_topk(np.ascontiguousarray(rows[::-1]), queries, 20, ids=ids)
+    assert np.array_equal(i1.cpu().numpy(), w1[1]) and np.array_equal(s1.cpu().numpy(), w1[0])
+    index.reset_index()
+    assert torch.equal(index.search(torch.from_numpy(queries).to(DEV), 20)[1], i1)

@@ -80,6 +80,43 @@ def test_store_is_interchangeable_with_the_reference_class(tmp_path):
     assert list(again.embed_data) == [5, 3, 9, 11]
 
 
+def test_store_blocks_flat_format_and_overwrite_semantics(tmp_path):
+    """The array-backed store: blocks are appended without per-row work, `embed_data` is the reference's
+    dict on demand, overwrites follow dict semantics, and format='flat' shards merge into flat files."""
+    path = str(tmp_path / "ev.pkl")
+    rng = np.random.RandomState(3)
+    rows = rng.randn(12, 8).astype(np.float16)
+    for rank, sl in enumerate([slice(0, 5), slice(5, 12)]):
+        st = EvidenceStore(path, load_from_path=False, rank=rank, format="flat")
+        st.add_block_data(np.arange(1 + sl.start, 1 + sl.stop), rows[sl])
+        assert len(st) == sl.stop - sl.start and len(st._id_blocks) == 1
+        st.save_shard()
+    main = EvidenceStore(path, load_from_path=False, rank=0, format="flat")
+    main.add_block_data(np.arange(1, 6), rows[:5])
+    main.merge_shards_and_save()
+    assert not os.path.exists(path) and os.path.exists(str(tmp_path / "ev.rows.f16"))
+    whole = EvidenceStore(path)                               # finds the flat files
+    ids, arr = whole.to_arrays()
+    assert ids.tolist() == list(range(1, 13)) and np.array_equal(np.asarray(arr), rows)
+    part = EvidenceStore(path, load_from_path=False)
+    part.load_from_file(row_range=(4, 9))
+    assert part.loaded_range == (4, 9, 12) and part.to_arrays()[0].tolist() == [5, 6, 7, 8, 9]
+    assert list(whole.embed_data) == list(range(1, 13)) and whole.embed_data[7].dtype == np.float16
+    with pytest.raises(ValueError):
+        whole.add_block_data([3], rows[:1])                   # the reference's overwrite guard (:59-60)
+    whole.add_block_data([3, 40], rows[:2] * 0 + 1, allow_overwrite=True)
+    assert list(whole.embed_data)[2] == 3 and list(whole.embed_data)[-1] == 40 and len(whole) == 13
+    assert np.all(np.asarray(whole.embed_data[3]) == 1)
+    overlap = EvidenceStore(path, load_from_path=False, rank=1, format="flat")
+    overlap.add_block_data([1], rows[:1])
+    overlap.save_shard()
+    clash = EvidenceStore(path, load_from_path=False, rank=0, format="flat")
+    clash.add_block_data([1, 2], rows[:2])
+    clash.save_shard()
+    with pytest.raises(AssertionError):
+        clash.merge_shards_and_save()                         # :88-90
+
+
 # ---------------------------------------------------------------- world_size-2 exchange on gloo
 class OracleSearcher(object):
     """CPU test double with ShardSearcher's surface, backed by the oracle (tests only)."""
@@ -213,6 +250,52 @@ def test_k_above_the_kernel_limit_is_exact_by_range_refinement(clustered):
     assert dist16.dtype == torch.float16 and idx32.dtype == torch.int32 and idx32.shape == (nq, k)
     small_s, small_i = index.search(torch.from_numpy(queries), 7)
     assert np.array_equal(small_i.numpy(), got_i.numpy()[:, :7]) or not free[:, :7].all()
+
+
+def _worker_flat_refresh(rank, world, port, out_dir):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    path = os.path.join(out_dir, "ev.pkl")
+    index = CpuDoubleIndex(16, EvidenceStore(path, load_from_path=False), device="cpu", group=dist.group.WORLD)
+    loads = []
+    orig = EvidenceStore.load_from_file
+    EvidenceStore.load_from_file = lambda self, row_range=None: (loads.append(row_range), orig(self, row_range))[1]
+    index.update_index()                                   # each rank maps ONLY its torch.chunk range
+    rng = np.random.RandomState(77)
+    queries = torch.from_numpy((rng.randint(-127, 128, size=(4, 16)) / 64).astype(np.float16))
+    s1, i1 = index.search(queries, 7)
+    index.reset_index()
+    s2, i2 = index.search(queries, 7)
+    np.savez(os.path.join(out_dir, "f%d.npz" % rank), s=s1.numpy(), i=i1.numpy(), s2=s2.numpy(), i2=i2.numpy(),
+             lo=index.row_lo, hi=index.row_hi, loads=np.array([list(r) for r in loads]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_index_refresh_from_the_flat_store_loads_only_the_local_row_range(tmp_path):
+    """f-2: B200BruteForceIndex.update_index / reset_index over the flat store — every rank memory-maps
+    just its own row range (emdr2_index.py:232-266 reloads the whole 32 GB pickle on the index owner)."""
+    import torch.multiprocessing as mp
+    rng = np.random.RandomState(21)
+    n, d = 1001, 16
+    rows = (rng.randint(-127, 128, size=(n, d)) / 64).astype(np.float16)
+    ids = rng.permutation(np.arange(1, n + 1)).astype(np.int64)
+    save_flat(str(tmp_path / "ev.pkl"), ids, rows)
+    for attempt in range(2):
+        try:
+            mp.spawn(_worker_flat_refresh, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+            break
+        except Exception:
+            if attempt:
+                raise
+    queries = (np.random.RandomState(77).randint(-127, 128, size=(4, d)) / 64).astype(np.float16)
+    want_s, want_i, ties = oracle.mips_topk(rows, queries, 7, ids=ids, want_ties=True)
+    for rank in range(2):
+        r = np.load(str(tmp_path / ("f%d.npz" % rank)))
+        assert (int(r["lo"]), int(r["hi"])) == chunk_range(n, 2, rank)
+        assert r["loads"].tolist() == [list(chunk_range(n, 2, rank))] * 2
+        for s, i in ((r["s"], r["i"]), (r["s2"], r["i2"])):
+            assert np.array_equal(s, want_s) and np.array_equal(i[ties == 0], want_i[ties == 0])
 
 
 def _worker_large_k(rank, world, port, out_dir):
