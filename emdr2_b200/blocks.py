@@ -310,6 +310,57 @@ class TransformerLanguageModel(nn.Module):
             out[perm[r:r + n], :w] = y[o:o + n * w].view(n, w, h)
         return out
 
+    def decode_incremental(self, dec_ids, enc_states, enc_pad, cache):
+        """Decoder states [rows, n_new, h] of the positions not yet in `cache` (dec_ids [rows, t_total];
+        rows = b * r, see DecoderCache).  Position-for-position the same arithmetic as `decode` — GEMM and
+        LayerNorm rows are independent, a query's softmax runs over the same keys in the same order — but
+        each token passes through the stack once and the encoder states are projected once per layer."""
+        rows, t_total = dec_ids.shape
+        b, sk = enc_states.shape[0], enc_states.shape[1]
+        if rows % b:
+            raise ValueError("decoder rows (%d) must be a multiple of the question batch (%d)" % (rows, b))
+        r = rows // b
+        t0 = cache.t
+        n_new = t_total - t0
+        if n_new < 1 or t_total > cache.max_len:
+            raise ValueError("nothing new to decode, or past the cache's %d positions" % cache.max_len)
+        if n_new > 1 and t0 > 0:
+            raise ValueError("several new tokens are only supported on the first call (prefix)")
+        h, heads, dev = self.hidden, self.decoder.layers[0].self_attention.heads, dec_ids.device
+        dtype = self.embedding.word_embeddings.weight.dtype
+        if cache.cross_kv is None:
+            enc2d = enc_states.reshape(b * sk, h)
+            cache.cross_kv = [layer.inter_attention.key_value(enc2d) for layer in self.decoder.layers]
+            cache.enc_pad = enc_pad.to(torch.uint8).contiguous()
+            cache.enc_live = ops.live_blocks(enc_pad) if self.skip_padding else None
+        if cache.self_kv is None or cache.self_kv[0].shape[0] != rows:
+            if cache.self_kv is not None:
+                raise ValueError("hypothesis rows changed without DecoderCache.reorder")
+            cache.self_kv = [torch.zeros((rows, cache.max_len, 2 * h), dtype=dtype, device=dev)
+                             for _ in self.decoder.layers]
+        new_ids = dec_ids[:, t0:].contiguous()
+        emb = self.embedding
+        x = ops.embedding(new_ids, emb.word_embeddings.weight, emb.position_embeddings.weight[t0:])
+        key_pad = (torch.arange(cache.max_len, device=dev) >= t_total).to(torch.uint8)[None].expand(rows, -1).contiguous()
+        for li, layer in enumerate(self.decoder.layers):
+            att = layer.self_attention
+            qkv = att.query_key_value(layer.input_layernorm(x))                    # [rows*n_new, 3h]
+            kv = cache.self_kv[li]
+            kv[:, t0:t_total] = qkv[:, h:].view(rows, n_new, 2 * h)
+            kv2d = kv.view(rows * cache.max_len, 2 * h)
+            ctx = ops.attention(qkv[:, :h], kv2d[:, :h], kv2d[:, h:], rows, heads, n_new, cache.max_len,
+                                k_pad=key_pad, causal=n_new > 1, scale=att.scale)
+            x = att.dense(ctx, residual=x)
+            ln = layer.post_attention_layernorm(x)
+            cross = layer.inter_attention
+            q = cross.query(ln)                                                     # [b * (r*n_new), h]
+            ctx = ag.cross_attention(q, cache.cross_kv[li], b, heads, r * n_new, sk, k_pad=cache.enc_pad,
+                                     k_live=cache.enc_live, scale=cross.scale)
+            x = cross.dense(ctx, residual=x)
+            x = layer.mlp(layer.post_inter_attention_layernorm(x), residual=x)
+        cache.t = t_total
+        return self.decoder.final_layernorm(x).view(rows, n_new, h)
+
     def decode(self, dec_ids, enc_states, enc_pad):
         """enc_states [b, sk, h] (sk may be K*S: FiD concatenation, emdr2_model.py:159-164)."""
         b, sq = dec_ids.shape
@@ -322,6 +373,30 @@ class TransformerLanguageModel(nn.Module):
         y = self.decoder(x, b, sq, dec_pad, causal=True, encoder_output=enc2d, enc_seq=sk,
                          enc_pad=enc_pad, q_live=q_live, enc_live=enc_live)
         return y.view(b, sq, self.hidden)
+
+
+class DecoderCache(object):
+    """Incremental decoding state of one question batch (evaluation decode loop, reference
+    megatron/model/search_strategy.py:189-240 re-runs the whole decoder — including the cross-attention
+    K/V projection of all K*S encoder positions in every layer — for every generated token).
+
+    cross_kv[l]  [b*sk, 2h]       layer l's key/value projection of the encoder states: computed ONCE
+    self_kv[l]   [rows, T, 2h]    keys/values of the tokens decoded so far, per hypothesis row
+    t            tokens consumed; rows = b * r hypotheses (r = 1 greedy, beam size in beam search; the r
+                 hypotheses of a question are consecutive rows and share its encoder states)."""
+
+    def __init__(self, max_len):
+        self.max_len = int(max_len)
+        self.cross_kv = None
+        self.self_kv = None
+        self.enc_pad = self.enc_live = None
+        self.t = 0
+
+    def reorder(self, source):
+        """Hypothesis rows after a beam step: new row i continues old row source[i] (rows may grow from b
+        to b*k on the first step)."""
+        if self.self_kv is not None:
+            self.self_kv = [kv.index_select(0, source) for kv in self.self_kv]
 
 
 def _require_cuda(t):
@@ -380,7 +455,7 @@ class T5Reader(nn.Module):
     def forward(self, encoder_input_ids, decoder_input_ids, encoder_attn_mask=None,
                 decoder_attn_mask=None, encoder_decoder_attn_mask=None, tokentype_ids=None,
                 lm_labels=None, enc_hidden_states=None, output_enc_hidden=False,
-                enc_ids_for_mask=None, enc_max_len=None, enc_row_lengths=None):
+                enc_ids_for_mask=None, enc_max_len=None, enc_row_lengths=None, decoder_cache=None):
         _require_cuda(encoder_input_ids)
         lm = self.language_model
         if enc_hidden_states is None:
@@ -392,7 +467,11 @@ class T5Reader(nn.Module):
             mask_ids = enc_ids_for_mask if enc_ids_for_mask is not None else encoder_input_ids
         if output_enc_hidden:
             return enc
-        dec = lm.decode(decoder_input_ids, enc, mask_ids < 1)
+        if decoder_cache is not None:          # evaluation decode loop: only the not-yet-decoded positions
+            with torch.no_grad():
+                dec = lm.decode_incremental(decoder_input_ids, enc, mask_ids < 1, decoder_cache)
+        else:
+            dec = lm.decode(decoder_input_ids, enc, mask_ids < 1)
         b, sq, h = dec.shape
         word = lm.embedding.word_embeddings.weight
         logits = ag.linear(dec.reshape(b * sq, h), word, self.lm_head.bias).view(b, sq, word.shape[0])

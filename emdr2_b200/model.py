@@ -85,6 +85,9 @@ class EMDR2Model(nn.Module):
     length and run them as a few token-packed buckets (blocks.py: `encode`); both leave every
     non-padding position unchanged."""
 
+    #: the decode loops (search_strategy.py) may pass `decoder_cache=` to forward
+    supports_decoder_cache = True
+
     def __init__(self, cfg, evidence_retriever, settings, t5_vocab_size=None, bert_vocab_size=None):
         super().__init__()
         self.cfg = cfg
@@ -108,7 +111,7 @@ class EMDR2Model(nn.Module):
 
     def forward(self, query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5,
                 query_ids_t5_len, dec_ids, all_query_context_hidden_states=None,
-                all_query_context_ids_unflat=None, topk_log_probs=None):
+                all_query_context_ids_unflat=None, topk_log_probs=None, decoder_cache=None):
         st = self.settings
         topk = self.topk
         bsize = query_ids_bert.shape[0]
@@ -165,9 +168,12 @@ class EMDR2Model(nn.Module):
             all_query_context_hidden_states = enc.reshape(bsize, topk * s_enc, hidden)
             all_query_context_ids_unflat = all_query_extended_context_ids[:, :s_enc].reshape(bsize, topk * s_enc)
 
+        # decoder_cache (blocks.DecoderCache, evaluation decoding only): logits come back for the positions
+        # not decoded yet; the decode loops read [:, -1, :] either way
+        extra = {} if decoder_cache is None else {"decoder_cache": decoder_cache}
         lm_logits, _ = self.language_model(all_query_context_ids_unflat[:, :1], dec_ids,
                                            enc_hidden_states=all_query_context_hidden_states,
-                                           enc_ids_for_mask=all_query_context_ids_unflat)
+                                           enc_ids_for_mask=all_query_context_ids_unflat, **extra)
         if self.training:
             lm_logits_one_context = None
             if st.get("update_retriever", False) and query_one_context_ids is not None:

@@ -87,16 +87,29 @@ def finish_beam(outs, total_score, batchsize, eos_id):
 class _ReaderState(object):
     """What `EMDR2Model.forward` returns beside the logits and takes back on the next call: the encoder
     states of the retrieved passages, their ids (for the cross-attention mask) and the retriever's
-    log-probabilities.  None before the first call, which retrieves and encodes."""
+    log-probabilities.  None before the first call, which retrieves and encodes.
 
-    def __init__(self):
+    With a model that advertises `supports_decoder_cache` (emdr2_b200.model.EMDR2Model) the state also owns
+    a `blocks.DecoderCache`: every token then passes through the decoder once and the K*S encoder positions
+    are projected to keys/values once per layer, instead of once per generated token; the encoder states
+    stay one copy per QUESTION (beam hypotheses are rows of the cache, not copies of the states)."""
+
+    def __init__(self, max_len=None):
         self.hidden = self.ids_unflat = self.topk_log_probs = None
+        self.max_len = max_len
+        self.cache = None
 
     def step(self, model, question, decoder_ids):
         """Next-token logits [rows, vocab] (fp32) for the hypotheses in decoder_ids [rows, t]."""
+        extra = {}
+        if self.max_len is not None and getattr(model, "supports_decoder_cache", False):
+            if self.cache is None:
+                from .blocks import DecoderCache
+                self.cache = DecoderCache(self.max_len)
+            extra["decoder_cache"] = self.cache
         logits, self.topk_log_probs, self.hidden, self.ids_unflat = model(
             *question, decoder_ids, all_query_context_hidden_states=self.hidden,
-            all_query_context_ids_unflat=self.ids_unflat, topk_log_probs=self.topk_log_probs)
+            all_query_context_ids_unflat=self.ids_unflat, topk_log_probs=self.topk_log_probs, **extra)
         return logits[:, -1, :].float()
 
 
@@ -113,16 +126,24 @@ class BeamSearch(object):
                         query_ids_t5_len):
         question = (query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5, query_ids_t5_len)
         batch, dev = query_ids_bert.shape[0], query_ids_bert.device
-        state = _ReaderState()
+        state = _ReaderState(self.max_decode_length + 1)
         y_block = torch.full((batch, 1), self.bos_id, dtype=torch.int64, device=dev)
         outs = torch.full((batch * self.k, 1), self.bos_id, dtype=torch.int64, device=dev)
         total_score = None
         for _ in range(self.max_decode_length):
             topk_score, topk = torch.topk(F.log_softmax(state.step(model, question, y_block), dim=1), self.k)
             assert float(topk_score.max()) <= 0.0
-            outs, total_score, state.ids_unflat, state.hidden, state.topk_log_probs = update_beam_state(
-                outs, total_score, topk, topk_score, self.eos_id, self.alpha, state.ids_unflat, state.hidden,
-                state.topk_log_probs)
+            if state.cache is not None:
+                # cached decoding: the per-question state is shared by a question's hypotheses; only the
+                # cache rows follow the survivors (`source` comes back through a row-index stand-in)
+                rows = torch.arange(topk.shape[0], device=dev)
+                outs, total_score, source, _, _ = update_beam_state(
+                    outs, total_score, topk, topk_score, self.eos_id, self.alpha, rows, rows, rows)
+                state.cache.reorder(source)
+            else:
+                outs, total_score, state.ids_unflat, state.hidden, state.topk_log_probs = update_beam_state(
+                    outs, total_score, topk, topk_score, self.eos_id, self.alpha, state.ids_unflat, state.hidden,
+                    state.topk_log_probs)
             y_block = outs
             if bool((outs == self.eos_id).any(dim=1).all()):
                 break                    # every hypothesis has produced EOS
@@ -142,7 +163,7 @@ class SampleOrGreedySearch(object):
                         query_ids_t5_len):
         question = (query_uid, query_ids_bert, query_types, query_mask_bert, query_ids_t5, query_ids_t5_len)
         batch, dev = query_ids_bert.shape[0], query_ids_bert.device
-        state = _ReaderState()
+        state = _ReaderState(self.max_decode_length + 1)
         y_block = torch.full((batch, 1), self.bos_id, dtype=torch.int64, device=dev)
         eos_seen = torch.zeros(batch, dtype=torch.bool, device=dev)
         for _ in range(self.max_decode_length):

@@ -42,7 +42,7 @@ def test_recall_evaluator_top100_on_the_gpu_index():
     want_s, want_i, ties = oracle.mips_topk(rows, queries, k, ids=ids, want_ties=True)
     got_i = np.array([c[0] for c in closest])
     assert_ids_equal_outside_ties(got_i, want_i, ties)
-    assert np.array_equal(np.array([c[1] for c in closest], dtype=np.float32), want_s)
+    assert np.allclose(np.array([c[1] for c in closest], dtype=np.float32), want_s, rtol=1e-5, atol=1e-6)   # fp32 accumulation order
     for kk in (1, 5, 10, 20, 50, 100):
         want = sum(bool((want_i[qi, :kk] == ids[gold[qi]]).any()) for qi in range(nq)) / nq
         assert acc[kk] == want, (kk, acc[kk], want)
@@ -95,13 +95,15 @@ def test_in_batch_negative_step_through_the_towers(with_neg):
     want.backward()
     assert abs(loss.item() - want.item()) < 2e-3
     assert int(stats["correct_prediction_count"].item()) == int((lp.argmax(1) == torch.arange(b)).sum())
-    worst = 0.0
+    errs = []
     for name, p in model.named_parameters():
         g = w32[name].grad
-        if g is None or float(g.norm()) == 0.0:
-            continue
-        worst = max(worst, ((p.grad.float().cpu() - g).norm() / g.norm()).item())
-    assert worst < 4e-2, worst
+        if g is None or float(g.norm()) < 1e-5:     # e.g. the context tower's last bias: the softmax over the
+            continue                                 # contexts is invariant to it, its gradient is rounding noise
+        errs.append((((p.grad.float().cpu() - g).norm() / g.norm()).item(), name, float(g.norm()),
+                     float(p.grad.float().norm())))
+    errs.sort(reverse=True)
+    assert errs[0][0] < 4e-2, errs[:6]
 
 
 def test_index_refresh_from_the_flat_store_on_the_gpu(tmp_path):

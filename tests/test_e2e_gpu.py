@@ -186,6 +186,27 @@ def test_retrieve_and_read_forward_tiny(tmp_path, dtype):
     beam = ss.reader_generate(model, inputs, max_decode_len=4, bos_id=bos, eos_id=eos, beam_size=3,
                               topk_evidence=TOPK)
     assert len(greedy) == bsz == len(beam) and all(1 <= len(g) <= 4 for g in greedy)
+    # the decode loops above ran on the decoder cache (blocks.DecoderCache: each token through the stack
+    # once, encoder states projected once per layer); the reference's way — the whole decoder for every
+    # token — must produce the same tokens, and the same last-position logits
+    model.supports_decoder_cache = False
+    assert ss.reader_generate(model, inputs, max_decode_len=4, bos_id=bos, eos_id=eos, beam_size=1,
+                              topk_evidence=TOPK) == greedy
+    assert ss.reader_generate(model, inputs, max_decode_len=4, bos_id=bos, eos_id=eos, beam_size=3,
+                              topk_evidence=TOPK) == beam
+    del model.supports_decoder_cache
+    from emdr2_b200.blocks import DecoderCache
+    with torch.no_grad():
+        first = model(*inputs, torch.full((bsz, 1), bos, dtype=torch.int64, device=DEV))
+        prefix = torch.tensor([[bos] + (g + [eos] * 4)[:3] for g in greedy], device=DEV)
+        full = model(*inputs, prefix, all_query_context_hidden_states=first[2], all_query_context_ids_unflat=first[3],
+                     topk_log_probs=first[1])[0]
+        cache = DecoderCache(8)
+        for t in range(1, 5):
+            step = model(*inputs, prefix[:, :t], all_query_context_hidden_states=first[2],
+                         all_query_context_ids_unflat=first[3], topk_log_probs=first[1], decoder_cache=cache)[0]
+            assert step.shape[1] == 1 and torch.allclose(step[:, -1].float(), full[:, t - 1].float(), atol=2e-2, rtol=0)
+        assert cache.t == 4 and len(cache.cross_kv) == TINY["layers"]
     enc_flat, ids_flat = enc.reshape(bsz, TOPK * S, -1), ext_t.reshape(bsz, TOPK * S)
     y = torch.full((bsz, 1), bos, dtype=torch.int64)
     for step in range(4):
