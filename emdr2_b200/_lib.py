@@ -95,6 +95,26 @@ _SIGNATURES = {
                                                   ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_void_p]),
+    "emdr2_dropout_colhash": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "emdr2_dropout_mask": (ctypes.c_int, [ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
+    "emdr2_dropout_add": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                         ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p,
+                                         ctypes.c_void_p]),
+    "emdr2_attention_fwd_dropout": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                                   ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                                   ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
+                                                   ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64,
+                                                   ctypes.c_void_p, ctypes.c_void_p]),
+    "emdr2_attention_bwd_dropout": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p, ctypes.c_int64] * 8 +
+                                    [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 +
+                                    [ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p,
+                                     ctypes.c_void_p]),
     "emdr2_ops_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "emdr2_ops_get_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)]),
     "emdr2_ops_timing": (ctypes.c_int, [ctypes.c_int]),

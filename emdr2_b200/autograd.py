@@ -116,6 +116,36 @@ def mlp(x, w1, b1, w2, b2, residual=None):
     return ops.linear(ops.linear(x, w1, b1, gelu=True), w2, b2, residual=residual)
 
 
+# ---------------------------------------------------------------------------------- dropout-add
+class _DropoutAddFn(torch.autograd.Function):
+    """out = residual + dropout(y) (bias_dropout_add once the bias is in y, transformer.py:397-419; with
+    residual None the embedding dropout of language_model.py:181).  Backward regenerates the mask."""
+
+    @staticmethod
+    def forward(ctx, y, residual, spec):
+        ctx.spec, ctx.has_res = spec, residual is not None
+        return ops.dropout_add(y, residual, spec)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _c(dout)
+        dy = ops.dropout_add(dout, None, ctx.spec) if ctx.needs_input_grad[0] else None
+        dres = dout if (ctx.has_res and ctx.needs_input_grad[1]) else None
+        return dy, dres, None
+
+
+def dropout_add(y, residual, p, spec=None):
+    """residual + dropout_p(y); p == 0 degenerates to the plain sum (or y)."""
+    if spec is None:
+        if not p:
+            return y if residual is None else y + residual
+        from . import dropout as _dropout
+        spec = _dropout.STATE.next(p, y.device, y.shape[1])
+    if _needs_grad(y, residual):
+        return _DropoutAddFn.apply(y, residual, spec)
+    return ops.dropout_add(y, residual, spec)
+
+
 # ------------------------------------------------------------------------------------ layernorm
 class _LayerNormFn(torch.autograd.Function):
     @staticmethod
@@ -149,16 +179,17 @@ def layernorm(x, gamma, beta, eps=1e-5):
 
 # ------------------------------------------------------------------------------------ attention
 def _attention_bwd(q, k, v, o, dout, dq, dk, dv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, causal,
-                   scale, lse):
+                   scale, lse, dropout=None):
     dvec = torch.empty((batch, heads, sq), dtype=torch.float32, device=q.device)
     lib = _lib.load()
     p = ops._ptr
+    drop = dropout.c_args() if dropout is not None else (ctypes.c_float(0.0), ctypes.c_uint64(0), ctypes.c_uint64(0), None)
     with torch.cuda.device(q.device):
-        _lib.check(lib.emdr2_attention_bwd(
+        _lib.check(lib.emdr2_attention_bwd_dropout(
             _DT[q.dtype], p(q), q.stride(0), p(k), k.stride(0), p(v), v.stride(0), p(o), o.stride(0),
             p(dout), dout.stride(0), p(dq), dq.stride(0), p(dk), dk.stride(0), p(dv), dv.stride(0),
             batch, heads, sq, sk, p(q_pad), p(k_pad), p(q_live), p(k_live), 1 if causal else 0, float(scale),
-            p(lse), p(dvec), ops._stream(q.device)), "emdr2_attention_bwd")
+            p(lse), p(dvec), *drop, ops._stream(q.device)), "emdr2_attention_bwd")
 
 
 def _u8(m, device):
@@ -169,51 +200,52 @@ class _SelfAttentionFn(torch.autograd.Function):
     """ctx = attention(q, k, v) with q | k | v the three column blocks of one [tokens, 3h] tensor."""
 
     @staticmethod
-    def forward(ctx, qkv, batch, heads, seq, pad, live, causal, scale):
+    def forward(ctx, qkv, batch, heads, seq, pad, live, causal, scale, dropout):
         h = heads * 64
         pad, live = _u8(pad, qkv.device), _u8(live, qkv.device)
         out, lse = ops.attention(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], batch, heads, seq, seq, q_pad=pad,
-                                 k_pad=pad, causal=causal, scale=scale, return_lse=True, q_live=live, k_live=live)
+                                 k_pad=pad, causal=causal, scale=scale, return_lse=True, q_live=live, k_live=live,
+                                 dropout=dropout)
         ctx.save_for_backward(qkv, out, lse, pad, live)
-        ctx.cfg = (batch, heads, seq, causal, scale)
+        ctx.cfg = (batch, heads, seq, causal, scale, dropout)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qkv, out, lse, pad, live = ctx.saved_tensors
-        batch, heads, seq, causal, scale = ctx.cfg
+        batch, heads, seq, causal, scale, dropout = ctx.cfg
         h = heads * 64
         dout = _c(dout)
         dqkv = torch.empty_like(qkv)
         _attention_bwd(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], out, dout, dqkv[:, :h], dqkv[:, h:2 * h],
-                       dqkv[:, 2 * h:], batch, heads, seq, seq, pad, pad, live, live, causal, scale, lse)
-        return dqkv, None, None, None, None, None, None, None
+                       dqkv[:, 2 * h:], batch, heads, seq, seq, pad, pad, live, live, causal, scale, lse, dropout)
+        return dqkv, None, None, None, None, None, None, None, None
 
 
 class _CrossAttentionFn(torch.autograd.Function):
     """ctx = attention(q, k, v) with k | v the two column blocks of one [batch*sk, 2h] tensor."""
 
     @staticmethod
-    def forward(ctx, q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale):
+    def forward(ctx, q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, dropout):
         h = heads * 64
         q_pad, k_pad = _u8(q_pad, q.device), _u8(k_pad, q.device)
         q_live, k_live = _u8(q_live, q.device), _u8(k_live, q.device)
         out, lse = ops.attention(q, kv[:, :h], kv[:, h:], batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad,
-                                 scale=scale, return_lse=True, q_live=q_live, k_live=k_live)
+                                 scale=scale, return_lse=True, q_live=q_live, k_live=k_live, dropout=dropout)
         ctx.save_for_backward(q, kv, out, lse, q_pad, k_pad, q_live, k_live)
-        ctx.cfg = (batch, heads, sq, sk, scale)
+        ctx.cfg = (batch, heads, sq, sk, scale, dropout)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         q, kv, out, lse, q_pad, k_pad, q_live, k_live = ctx.saved_tensors
-        batch, heads, sq, sk, scale = ctx.cfg
+        batch, heads, sq, sk, scale, dropout = ctx.cfg
         h = heads * 64
         dout = _c(dout)
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
         _attention_bwd(q, kv[:, :h], kv[:, h:], out, dout, dq, dkv[:, :h], dkv[:, h:], batch, heads, sq, sk,
-                       q_pad, k_pad, q_live, k_live, False, scale, lse)
-        return (dq, dkv) + (None,) * 9
+                       q_pad, k_pad, q_live, k_live, False, scale, lse, dropout)
+        return (dq, dkv) + (None,) * 10
 
 
 class _GroupedSelfAttentionFn(torch.autograd.Function):
@@ -223,58 +255,68 @@ class _GroupedSelfAttentionFn(torch.autograd.Function):
     launch per group in either direction, all reading / writing slices of the same buffers."""
 
     @staticmethod
-    def forward(ctx, qkv, heads, groups, causal, scale):
+    def forward(ctx, qkv, heads, groups, causal, scale, dropouts):
         h = heads * 64
         out = torch.empty((qkv.shape[0], h), dtype=qkv.dtype, device=qkv.device)
         lses = []
-        for off, b, s, pad, live in groups:
+        for (off, b, s, pad, live), drop in zip(groups, dropouts):
             part = qkv[off:off + b * s]
             _, lse = ops.attention(part[:, :h], part[:, h:2 * h], part[:, 2 * h:], b, heads, s, s, q_pad=pad,
                                    k_pad=pad, causal=causal, scale=scale, return_lse=True, q_live=live,
-                                   k_live=live, out=out[off:off + b * s])
+                                   k_live=live, out=out[off:off + b * s], dropout=drop)
             lses.append(lse)
         ctx.save_for_backward(qkv, out, *lses)
-        ctx.groups, ctx.cfg = groups, (heads, causal, scale)
+        ctx.groups, ctx.cfg = groups, (heads, causal, scale, dropouts)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qkv, out = ctx.saved_tensors[:2]
         lses = ctx.saved_tensors[2:]
-        heads, causal, scale = ctx.cfg
+        heads, causal, scale, dropouts = ctx.cfg
         h = heads * 64
         dout = _c(dout)
         dqkv = torch.empty_like(qkv)
-        for (off, b, s, pad, live), lse in zip(ctx.groups, lses):
+        for (off, b, s, pad, live), lse, drop in zip(ctx.groups, lses, dropouts):
             r = slice(off, off + b * s)
             q, dq = qkv[r], dqkv[r]
             _attention_bwd(q[:, :h], q[:, h:2 * h], q[:, 2 * h:], out[r], dout[r], dq[:, :h], dq[:, h:2 * h],
-                           dq[:, 2 * h:], b, heads, s, s, pad, pad, live, live, causal, scale, lse)
-        return dqkv, None, None, None, None
+                           dq[:, 2 * h:], b, heads, s, s, pad, pad, live, live, causal, scale, lse, drop)
+        return dqkv, None, None, None, None, None
 
 
-def self_attention_grouped(qkv, heads, groups, causal=False, scale=0.125):
+def _attn_spec(p, device, keys):
+    """A fresh DropoutSpec for one attention launch over `keys` key columns (None when p == 0)."""
+    from . import dropout as _dropout
+    return _dropout.STATE.next(p, device, keys) if p else None
+
+
+def self_attention_grouped(qkv, heads, groups, causal=False, scale=0.125, dropout_p=0.0):
     """ctx [T, h] for a packed projection qkv [T, 3h] whose rows are the concatenation of the groups'
     [batch*seq] token blocks.  groups: (row offset, batch, seq, pad, live) per group."""
     groups = [(int(off), int(b), int(s), _u8(pad, qkv.device), _u8(live, qkv.device))
               for off, b, s, pad, live in groups]
+    dropouts = [_attn_spec(dropout_p, qkv.device, g[2]) for g in groups]     # one mask plane per launch
     if _needs_grad(qkv):
-        return _GroupedSelfAttentionFn.apply(qkv, heads, groups, causal, scale)
+        return _GroupedSelfAttentionFn.apply(qkv, heads, groups, causal, scale, dropouts)
     h = heads * 64
     out = torch.empty((qkv.shape[0], h), dtype=qkv.dtype, device=qkv.device)
-    for off, b, s, pad, live in groups:
+    for (off, b, s, pad, live), drop in zip(groups, dropouts):
         part = qkv[off:off + b * s]
         ops.attention(part[:, :h], part[:, h:2 * h], part[:, 2 * h:], b, heads, s, s, q_pad=pad, k_pad=pad,
-                      causal=causal, scale=scale, q_live=live, k_live=live, out=out[off:off + b * s])
+                      causal=causal, scale=scale, q_live=live, k_live=live, out=out[off:off + b * s], dropout=drop)
     return out
 
 
-def self_attention(qkv, batch, heads, seq, pad=None, live=None, causal=False, scale=0.125):
+def self_attention(qkv, batch, heads, seq, pad=None, live=None, causal=False, scale=0.125, dropout_p=0.0,
+                   dropout=None):
+    """dropout_p draws a fresh mask; `dropout` (a DropoutSpec) replays a given one."""
+    drop = dropout if dropout is not None else _attn_spec(dropout_p, qkv.device, seq)
     if _needs_grad(qkv):
-        return _SelfAttentionFn.apply(qkv, batch, heads, seq, pad, live, causal, scale)
+        return _SelfAttentionFn.apply(qkv, batch, heads, seq, pad, live, causal, scale, drop)
     h = heads * 64
     return ops.attention(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], batch, heads, seq, seq, q_pad=pad, k_pad=pad,
-                         causal=causal, scale=scale, q_live=live, k_live=live)
+                         causal=causal, scale=scale, q_live=live, k_live=live, dropout=drop)
 
 
 #: Key-split ("flash-decoding") of long cross-attention in the no-grad path: with few (batch, head)
@@ -322,10 +364,15 @@ def _cross_attention_split(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_
     return merged.to(q.dtype).view(batch * sq, h)
 
 
-def cross_attention(q, kv, batch, heads, sq, sk, q_pad=None, k_pad=None, q_live=None, k_live=None, scale=0.125):
+def cross_attention(q, kv, batch, heads, sq, sk, q_pad=None, k_pad=None, q_live=None, k_live=None, scale=0.125,
+                    dropout_p=0.0, dropout=None):
+    drop = dropout if dropout is not None else _attn_spec(dropout_p, q.device, sk)
     if _needs_grad(q, kv):
-        return _CrossAttentionFn.apply(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale)
+        return _CrossAttentionFn.apply(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, drop)
     h = heads * 64
+    if drop is not None:         # a dropped-out pass keeps the mask plane of the unsplit key axis
+        return ops.attention(q, kv[:, :h], kv[:, h:], batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad, scale=scale,
+                             q_live=q_live, k_live=k_live, dropout=drop)
     splits = _cross_splits(batch, heads, sk)
     if splits > 1:
         return _cross_attention_split(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, splits)

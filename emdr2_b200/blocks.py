@@ -23,7 +23,11 @@ QKV layout: the reference packs the fused projection as [np, hn, 3] along the ou
 [3, np, hn] so that a head's q/k/v are 64 contiguous columns, and `_packed()` keeps a permuted copy
 keyed on the parameter version.
 
-Dropout is off (p = 0 / eval): hidden_dropout and attention_dropout are identity here.
+Dropout: cfg["hidden_dropout"] / cfg["attention_dropout"] (default 0.1 each, the reference's
+--hidden-dropout / --attention-dropout, arguments.py:218-221) act while a module is in training mode, exactly
+where the reference applies them — on the attention probabilities (transformer.py:345-346), on every
+bias-add-residual (:397-419, :511-515) and on the embedding sum (language_model.py:181) — with counter-based
+masks that the backward kernels regenerate (emdr2_b200/dropout.py, csrc/dropout.cuh).  eval() turns them off.
 Training: every op dispatches through emdr2_b200/autograd.py, whose backward passes are kernels of
 the same library (csrc/gemm.cu MN-major/split-K products, attention_bwd.cu, rowops_bwd.cu); under
 torch.no_grad() the plain forward ops run.  No CPU path: forward on a CPU tensor raises.
@@ -97,8 +101,9 @@ class _PackedProjection(nn.Module):
 
 
 class ParallelAttention(nn.Module):
-    def __init__(self, hidden, heads, dtype, attention_type="self"):
+    def __init__(self, hidden, heads, dtype, attention_type="self", attention_dropout=0.0, hidden_dropout=0.0):
         super().__init__()
+        self.attention_dropout, self.hidden_dropout = float(attention_dropout), float(hidden_dropout)
         if hidden // heads != 64 or hidden % heads:
             raise ValueError("the sm_100a attention kernel supports head dimension 64 only "
                              "(hidden=%d heads=%d)" % (hidden, heads))
@@ -113,43 +118,53 @@ class ParallelAttention(nn.Module):
 
     def forward(self, x, batch, sq, q_pad, residual, causal=False, encoder_output=None, sk=None,
                 k_pad=None, q_live=None, k_live=None, groups=None):
+        p_attn = self.attention_dropout if self.training else 0.0
+        p_hidden = self.hidden_dropout if self.training else 0.0
         if self.attention_type == "self":
             qkv = self.query_key_value(x)
             if groups is not None:      # token-packed rows of several [batch_g, seq_g] rectangles
-                ctx = ag.self_attention_grouped(qkv, self.heads, groups, causal=causal, scale=self.scale)
+                ctx = ag.self_attention_grouped(qkv, self.heads, groups, causal=causal, scale=self.scale,
+                                                dropout_p=p_attn)
             else:
                 ctx = ag.self_attention(qkv, batch, self.heads, sq, pad=q_pad, live=q_live, causal=causal,
-                                        scale=self.scale)
+                                        scale=self.scale, dropout_p=p_attn)
         else:
             q = self.query(x)
             kv = self.key_value(encoder_output)
             ctx = ag.cross_attention(q, kv, batch, self.heads, sq, sk, q_pad=q_pad, k_pad=k_pad,
-                                     q_live=q_live, k_live=k_live, scale=self.scale)
-        return self.dense(ctx, residual=residual)          # bias + residual fused (dropout p=0)
+                                     q_live=q_live, k_live=k_live, scale=self.scale, dropout_p=p_attn)
+        if p_hidden:                                       # residual + dropout(ctx W^T + b)   (transformer.py:397-419)
+            return ag.dropout_add(self.dense(ctx), residual, p_hidden)
+        return self.dense(ctx, residual=residual)          # bias + residual fused into the GEMM epilogue
 
 
 class ParallelMLP(nn.Module):
-    def __init__(self, hidden, ffn, dtype):
+    def __init__(self, hidden, ffn, dtype, hidden_dropout=0.0):
         super().__init__()
         self.dense_h_to_4h = Linear(hidden, ffn, dtype)
         self.dense_4h_to_h = Linear(ffn, hidden, dtype)
+        self.hidden_dropout = float(hidden_dropout)
 
     def forward(self, x, residual):
-        return ag.mlp(x, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, self.dense_4h_to_h.weight,
-                      self.dense_4h_to_h.bias, residual=residual)
+        w = (self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, self.dense_4h_to_h.weight, self.dense_4h_to_h.bias)
+        if self.training and self.hidden_dropout:          # residual + dropout(mlp(x))   (transformer.py:511-515)
+            return ag.dropout_add(ag.mlp(x, *w, residual=None), residual, self.hidden_dropout)
+        return ag.mlp(x, *w, residual=residual)
 
 
 class ParallelTransformerLayer(nn.Module):
-    def __init__(self, hidden, heads, ffn, eps, dtype, layer_type="encoder"):
+    def __init__(self, hidden, heads, ffn, eps, dtype, layer_type="encoder", attention_dropout=0.0,
+                 hidden_dropout=0.0):
         super().__init__()
         self.layer_type = layer_type
+        drop = dict(attention_dropout=attention_dropout, hidden_dropout=hidden_dropout)
         self.input_layernorm = LayerNorm(hidden, eps, dtype)
-        self.self_attention = ParallelAttention(hidden, heads, dtype)
+        self.self_attention = ParallelAttention(hidden, heads, dtype, **drop)
         self.post_attention_layernorm = LayerNorm(hidden, eps, dtype)
         if layer_type == "decoder":
-            self.inter_attention = ParallelAttention(hidden, heads, dtype, attention_type="cross")
+            self.inter_attention = ParallelAttention(hidden, heads, dtype, attention_type="cross", **drop)
             self.post_inter_attention_layernorm = LayerNorm(hidden, eps, dtype)
-        self.mlp = ParallelMLP(hidden, ffn, dtype)
+        self.mlp = ParallelMLP(hidden, ffn, dtype, hidden_dropout=hidden_dropout)
 
     def forward(self, x, batch, seq, pad, causal=False, encoder_output=None, enc_seq=None, enc_pad=None,
                 q_live=None, enc_live=None, groups=None):
@@ -164,9 +179,11 @@ class ParallelTransformerLayer(nn.Module):
 
 
 class ParallelTransformer(nn.Module):
-    def __init__(self, hidden, heads, ffn, num_layers, eps, dtype, layer_type="encoder"):
+    def __init__(self, hidden, heads, ffn, num_layers, eps, dtype, layer_type="encoder", attention_dropout=0.0,
+                 hidden_dropout=0.0):
         super().__init__()
-        self.layers = nn.ModuleList([ParallelTransformerLayer(hidden, heads, ffn, eps, dtype, layer_type)
+        self.layers = nn.ModuleList([ParallelTransformerLayer(hidden, heads, ffn, eps, dtype, layer_type,
+                                                              attention_dropout, hidden_dropout)
                                      for _ in range(num_layers)])
         self.final_layernorm = LayerNorm(hidden, eps, dtype)
 
@@ -183,16 +200,20 @@ class _Table(nn.Module):
 
 
 class Embedding(nn.Module):
-    def __init__(self, hidden, vocab, max_positions, num_tokentypes, dtype):
+    def __init__(self, hidden, vocab, max_positions, num_tokentypes, dtype, hidden_dropout=0.0):
         super().__init__()
         self.word_embeddings = _Table(vocab, hidden, dtype)
         self.position_embeddings = _Table(max_positions, hidden, dtype)
         self.tokentype_embeddings = _Table(num_tokentypes, hidden, dtype) if num_tokentypes > 0 else None
+        self.hidden_dropout = float(hidden_dropout)
 
     def forward(self, input_ids, tokentype_ids=None):
         typ = self.tokentype_embeddings.weight if tokentype_ids is not None else None
-        return ag.embedding(input_ids, self.word_embeddings.weight, self.position_embeddings.weight,
-                            tokentype_ids, typ)
+        x = ag.embedding(input_ids, self.word_embeddings.weight, self.position_embeddings.weight,
+                         tokentype_ids, typ)
+        if self.training and self.hidden_dropout:          # embedding_dropout (language_model.py:181)
+            x = ag.dropout_add(x, None, self.hidden_dropout)
+        return x
 
 
 class TransformerLanguageModel(nn.Module):
@@ -200,14 +221,16 @@ class TransformerLanguageModel(nn.Module):
         super().__init__()
         d = cfg["dtype"]
         self.hidden = cfg["hidden"]
+        # the reference's defaults (arguments.py:218-221); only active in training mode
+        drop = dict(attention_dropout=cfg.get("attention_dropout", 0.1), hidden_dropout=cfg.get("hidden_dropout", 0.1))
         self.embedding = Embedding(cfg["hidden"], vocab_size or cfg["vocab"], cfg["max_pos"],
-                                   num_tokentypes, d)
+                                   num_tokentypes, d, hidden_dropout=drop["hidden_dropout"])
         self.encoder = ParallelTransformer(cfg["hidden"], cfg["heads"], cfg["ffn"], cfg["layers"],
-                                           cfg.get("eps", 1e-5), d)
+                                           cfg.get("eps", 1e-5), d, **drop)
         self.add_decoder = add_decoder
         if add_decoder:
             self.decoder = ParallelTransformer(cfg["hidden"], cfg["heads"], cfg["ffn"], cfg["layers"],
-                                               cfg.get("eps", 1e-5), d, layer_type="decoder")
+                                               cfg.get("eps", 1e-5), d, layer_type="decoder", **drop)
 
     #: True: attention skips padding (zeros at padding positions, identical results at every
     #: non-padding position); False: the reference's values at padding positions too.

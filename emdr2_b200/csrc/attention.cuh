@@ -26,6 +26,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dropout.cuh"
+
 namespace emdr2 {
 
 constexpr int kAttnHeadDim = 64;
@@ -55,6 +57,10 @@ struct AttnArgs {
   const uint8_t* k_live;   // [batch, ceil(sk/128)] or nullptr: 0 = key block is all padding (skipped);
                            // every batch entry must have at least one live key block
   float* lse;              // [batch, heads, sq] natural-log sum-exp of the masked scores, or nullptr
+  // attention dropout (transformer.py:345-346): P is multiplied by keep / (1 - p) AFTER the softmax
+  // normalisation — row sums and lse come from the undropped probabilities; element (row, col) =
+  // ((b * heads + head) * sq + query, key).  threshold 0 = off.
+  DropoutArgs drop;
 };
 
 struct AttnBwdArgs {
@@ -69,6 +75,7 @@ struct AttnBwdArgs {
   const uint8_t* k_live;
   const float* lse;        // [batch, heads, sq] from the forward
   const float* dvec;       // [batch, heads, sq] rowsum(dO * O), from launch_attention_bwd_prep
+  DropoutArgs drop;        // the forward's dropout, regenerated: dP = keep / (1 - p) * (dO . V^T)
 };
 
 cudaError_t attention_bwd_prepare();

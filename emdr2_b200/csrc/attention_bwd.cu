@@ -119,7 +119,7 @@ __device__ __forceinline__ void reg_alloc() {
 // smem: Q 16K | dO 16K | ring 2 x (K 8K + V 8K) | dS 16K | bars.   TMEM: S [0,64) dP [64,128) dQ [128,192)
 constexpr int kDqSmem = 2 * kTile + 2 * 2 * kHalfTile + kTile + 256;
 
-template <bool kBf16>
+template <bool kBf16, bool kDrop>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -251,6 +251,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const float lse2 = a.lse[stat] * kLog2e;
       const float dsum = a.dvec[stat];
       const bool row_dead = q_is_pad || !row_active;     // no gradient reaches any score of this row
+      uint32_t drop_row = 0;
+      if constexpr (kDrop)
+        drop_row = dropout_row_hash(a.drop.key_a, a.drop.key_b, (static_cast<uint64_t>(b) * a.heads + head) * a.sq + qi);
       uint32_t n = 0;
       for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1), ++n) {
         const uint32_t kb0 = j * kBwdBlk;
@@ -278,11 +281,21 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float ds[8];
+          uint32_t cb[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if constexpr (kDrop) {   // column hashes of this group's 8 keys: the same address in every lane
+            const uint4* src = reinterpret_cast<const uint4*>(a.drop.colhash + kb0 + ch * 32 + g * 8);
+            const uint4 c0 = __ldg(src), c1 = __ldg(src + 1);
+            cb[0] = c0.x; cb[1] = c0.y; cb[2] = c0.z; cb[3] = c0.w;
+            cb[4] = c1.x; cb[5] = c1.y; cb[6] = c1.z; cb[7] = c1.w;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int c = g * 8 + i;
             const float p = ex2(fmaf(__uint_as_float(s[c]), a.scale_log2, -lse2));
-            float d = p * (__uint_as_float(dp[c]) - dsum) * a.scale;
+            float dpv = __uint_as_float(dp[c]);
+            if constexpr (kDrop)     // dP = keep / (1 - p_drop) * (dO . V^T): the forward's mask, regenerated
+              dpv = dropout_keep(drop_row, cb[i], a.drop.threshold) ? dpv * a.drop.inv_keep : 0.f;
+            float d = p * (dpv - dsum) * a.scale;
             if (!plain) {
               const uint32_t cc = ch * 32 + c;
               const bool masked = row_dead || ((kmw >> c) & 1u) || (a.causal && kb0 + cc > qi) || cc >= valid;
@@ -333,9 +346,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 // ============================================================================ dK, dV
 // smem: K 16K | V 16K | ring 2 x (Q 8K + dO 8K) | P^T 16K | dS^T 16K | stats 2 x 512 B | bars
 // TMEM: S^T [0,64) dP^T [64,128) dV [128,192) dK [192,256)
-constexpr int kDkvSmem = 2 * kTile + 2 * 2 * kHalfTile + 2 * kTile + 1024 + 256;
+constexpr int kDkvSmem = 2 * kTile + 2 * 2 * kHalfTile + 2 * kTile + 2048 + 256;
 
-template <bool kBf16>
+template <bool kBf16, bool kDrop>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -343,9 +356,9 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                          const AttnBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr uint32_t off_k = 0, off_v = kTile, off_ring = 2 * kTile, off_p = off_ring + 4 * kHalfTile,
-                     off_ds = off_p + kTile, off_stat = off_ds + kTile, off_bar = off_stat + 1024;
+                     off_ds = off_p + kTile, off_stat = off_ds + kTile, off_bar = off_stat + 2048;
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + off_bar);
-  float* stat_smem = reinterpret_cast<float*>(smem + off_stat);   // [2][64] x {lse*log2e, D}
+  float* stat_smem = reinterpret_cast<float*>(smem + off_stat);   // [2][64] x {lse*log2e, D, dropout row hash}
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t k0 = blockIdx.x * kAttnBK, head = blockIdx.y, b = blockIdx.z;
@@ -473,16 +486,21 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       fence_proxy_async_smem();
     } else {
       const bool k_is_pad = row_active && a.k_pad && a.k_pad[static_cast<size_t>(b) * a.sk + kj] != 0;
+      uint32_t drop_col = 0;   // this thread's key column of the dropout plane (table covers roundup(sk, 128))
+      if constexpr (kDrop) drop_col = __ldg(a.drop.colhash + kj);
       uint32_t n = 0;
       for (uint32_t i = next_live(0); i < nqblk; i = next_live(i + 1), ++n) {
         const uint32_t qb0 = i * kBwdBlk;
         // per-query statistics of this block -> shared memory (threads 0..63 load query qb0 + row)
-        float* st = stat_smem + (n & 1) * 128;
+        float* st = stat_smem + (n & 1) * 192;
         if (ch == 0 && row < kBwdBlk) {
           const uint32_t qi = qb0 + row;
           const size_t sidx = (static_cast<size_t>(b) * a.heads + head) * a.sq + (qi < a.sq ? qi : 0);
           st[row] = a.lse[sidx] * kLog2e;
           st[64 + row] = a.dvec[sidx];
+          if constexpr (kDrop)
+            st[128 + row] = __uint_as_float(dropout_row_hash(
+                a.drop.key_a, a.drop.key_b, (static_cast<uint64_t>(b) * a.heads + head) * a.sq + qi));
         }
         uint32_t qm[2];
 #pragma unroll
@@ -516,6 +534,13 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           const float4 d1 = *reinterpret_cast<const float4*>(lp + 68);
           const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
           const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          uint32_t rh[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if constexpr (kDrop) {
+            const uint4 r0 = *reinterpret_cast<const uint4*>(lp + 128);
+            const uint4 r1 = *reinterpret_cast<const uint4*>(lp + 132);
+            rh[0] = r0.x; rh[1] = r0.y; rh[2] = r0.z; rh[3] = r0.w;
+            rh[4] = r1.x; rh[5] = r1.y; rh[6] = r1.z; rh[7] = r1.w;
+          }
 #pragma unroll
           for (int i2 = 0; i2 < 8; ++i2) {
             const int c = g * 8 + i2;                 // column inside this thread's 32
@@ -528,8 +553,15 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             }
             float p = ex2(t - lv[i2]);
             if (!plain) p = (cc < valid && row_active) ? p : 0.f;
-            const float d = p * (__uint_as_float(dp[c]) - dv[i2]) * a.scale;
-            pv[i2] = p;
+            float dpv = __uint_as_float(dp[c]);
+            float pd = p;            // what multiplied V in the forward: the dropped, rescaled probability
+            if constexpr (kDrop) {
+              const bool keep = dropout_keep(rh[i2], drop_col, a.drop.threshold);
+              dpv = keep ? dpv * a.drop.inv_keep : 0.f;
+              pd = keep ? p * a.drop.inv_keep : 0.f;
+            }
+            const float d = p * (dpv - dv[i2]) * a.scale;
+            pv[i2] = pd;
             ds[i2] = masked ? 0.f : d;
           }
           const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
@@ -580,16 +612,21 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 
 }  // namespace
 
+template <bool kBf16, bool kDrop>
+cudaError_t bwd_prepare_one() {
+  cudaError_t e = cudaFuncSetAttribute(attention_bwd_dq_kernel<kBf16, kDrop>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_bwd_dkv_kernel<kBf16, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kDkvSmem);
+  return e;
+}
+
 cudaError_t attention_bwd_prepare() {
-  cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem);
+  cudaError_t e = bwd_prepare_one<true, false>();
+  if (e == cudaSuccess) e = bwd_prepare_one<false, false>();
+  if (e == cudaSuccess) e = bwd_prepare_one<true, true>();
+  if (e == cudaSuccess) e = bwd_prepare_one<false, true>();
   return e;
 }
 
@@ -609,17 +646,24 @@ cudaError_t launch_attention_bwd_prep(bool bf16, const void* dout, int64_t lddo,
   return cudaGetLastError();
 }
 
+template <bool kBf16, bool kDrop>
+void bwd_launch_one(const AttnBwdMaps& m, const AttnBwdArgs& a, dim3 gq, dim3 gk, cudaStream_t stream) {
+  attention_bwd_dq_kernel<kBf16, kDrop><<<gq, kBwdThreads, kDqSmem, stream>>>(m.q128, m.k64, m.v64, m.do128,
+                                                                             m.dq128, a);
+  attention_bwd_dkv_kernel<kBf16, kDrop><<<gk, kBwdThreads, kDkvSmem, stream>>>(m.q64, m.k128, m.v128, m.do64,
+                                                                               m.dk128, m.dv128, a);
+}
+
 cudaError_t launch_attention_bwd(const AttnBwdMaps& m, const AttnBwdArgs& a, bool bf16, cudaStream_t stream) {
   dim3 gq((a.sq + kAttnBQ - 1) / kAttnBQ, a.heads, a.batch);
   dim3 gk((a.sk + kAttnBK - 1) / kAttnBK, a.heads, a.batch);
+  const bool drop = a.drop.threshold != 0;
   if (bf16) {
-    attention_bwd_dq_kernel<true><<<gq, kBwdThreads, kDqSmem, stream>>>(m.q128, m.k64, m.v64, m.do128, m.dq128, a);
-    attention_bwd_dkv_kernel<true><<<gk, kBwdThreads, kDkvSmem, stream>>>(m.q64, m.k128, m.v128, m.do64, m.dk128,
-                                                                          m.dv128, a);
+    if (drop) bwd_launch_one<true, true>(m, a, gq, gk, stream);
+    else bwd_launch_one<true, false>(m, a, gq, gk, stream);
   } else {
-    attention_bwd_dq_kernel<false><<<gq, kBwdThreads, kDqSmem, stream>>>(m.q128, m.k64, m.v64, m.do128, m.dq128, a);
-    attention_bwd_dkv_kernel<false><<<gk, kBwdThreads, kDkvSmem, stream>>>(m.q64, m.k128, m.v128, m.do64, m.dk128,
-                                                                           m.dv128, a);
+    if (drop) bwd_launch_one<false, true>(m, a, gq, gk, stream);
+    else bwd_launch_one<false, false>(m, a, gq, gk, stream);
   }
   return cudaGetLastError();
 }

@@ -86,7 +86,7 @@ struct Item {
   uint32_t qb, head, b;
 };
 
-template <bool kBf16>
+template <bool kBf16, bool kDrop>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                 const __grid_constant__ CUtensorMap tmap_k,
@@ -263,6 +263,10 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q,
       } else {
         const bool q_is_pad = row_active && a.q_pad && a.q_pad[static_cast<size_t>(it.b) * a.sq + qi] != 0;
         const uint8_t* k_live = a.k_live ? a.k_live + static_cast<size_t>(it.b) * nblk : nullptr;
+        uint32_t drop_row = 0;
+        if constexpr (kDrop)
+          drop_row = dropout_row_hash(a.drop.key_a, a.drop.key_b,
+                                      (static_cast<uint64_t>(it.b) * a.heads + it.head) * a.sq + qi);
         float m_run = kNegInf;
         float l_run = 0.f;
         bool first = true;
@@ -380,10 +384,17 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q,
               uint32_t w[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float p0 = ex2(fmaf(__uint_as_float(t[c * 32 + 2 * i]), mul, negm));
-                const float p1 = ex2(fmaf(__uint_as_float(t[c * 32 + 2 * i + 1]), mul, negm));
-                sum0 += p0;
+                float p0 = ex2(fmaf(__uint_as_float(t[c * 32 + 2 * i]), mul, negm));
+                float p1 = ex2(fmaf(__uint_as_float(t[c * 32 + 2 * i + 1]), mul, negm));
+                sum0 += p0;      // the normaliser is the sum of the UNDROPPED probabilities
                 sum1 += p1;
+                if constexpr (kDrop) {
+                  // column hashes of keys kb0 + c*32 + 2i, +1: the same address in every lane (one broadcast
+                  // load per pair; keys past the end carry p = 0 whatever the table holds)
+                  const uint2 cb = __ldg(reinterpret_cast<const uint2*>(a.drop.colhash + kb0 + c * 32 + 2 * i));
+                  p0 = dropout_keep(drop_row, cb.x, a.drop.threshold) ? p0 : 0.f;
+                  p1 = dropout_keep(drop_row, cb.y, a.drop.threshold) ? p1 : 0.f;
+                }
                 w[i] = pack2<kBf16>(p0, p1);
               }
               tmem_st_32x32b_x16(tmem_base + lane_tmem + c * 16, w);
@@ -402,7 +413,7 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc_fence_after();
         ++live_it;
         if (warp_active) {
-          const float inv_l = 1.0f / l_run;
+          const float inv_l = kDrop ? a.drop.inv_keep / l_run : 1.0f / l_run;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t o[32];
@@ -453,11 +464,18 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q,
 }  // namespace
 
 cudaError_t attention_persistent_prepare() {
-  cudaError_t e = cudaFuncSetAttribute(attention_fwd_persistent_kernel<true>,
+  cudaError_t e = cudaFuncSetAttribute(attention_fwd_persistent_kernel<true, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(attention_fwd_persistent_kernel<false>,
-                              cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_fwd_persistent_kernel<false, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_fwd_persistent_kernel<true, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_fwd_persistent_kernel<false, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes);
+  return e;
 }
 
 void launch_attention_fwd_persistent(const CUtensorMap& tmap_q, const CUtensorMap& tmap_k,
@@ -485,12 +503,18 @@ void launch_attention_fwd_persistent(const CUtensorMap& tmap_q, const CUtensorMa
     while (ctas > 1 && gcd(ctas, nqb) != 1) --ctas;
   }
   const dim3 grid(ctas);
-  if (bf16)
-    attention_fwd_persistent_kernel<true><<<grid, kAttnThreads, kPersistSmemBytes, stream>>>(
-        tmap_q, tmap_k, tmap_v, tmap_o, args);
-  else
-    attention_fwd_persistent_kernel<false><<<grid, kAttnThreads, kPersistSmemBytes, stream>>>(
-        tmap_q, tmap_k, tmap_v, tmap_o, args);
+#define EMDR2_ATTN_LAUNCH(BF, DROP)                                                                     \
+  attention_fwd_persistent_kernel<BF, DROP><<<grid, kAttnThreads, kPersistSmemBytes, stream>>>(tmap_q, tmap_k, \
+                                                                                                tmap_v, tmap_o, args)
+  const bool drop = args.drop.threshold != 0;
+  if (bf16) {
+    if (drop) EMDR2_ATTN_LAUNCH(true, true);
+    else EMDR2_ATTN_LAUNCH(true, false);
+  } else {
+    if (drop) EMDR2_ATTN_LAUNCH(false, true);
+    else EMDR2_ATTN_LAUNCH(false, false);
+  }
+#undef EMDR2_ATTN_LAUNCH
 }
 
 }  // namespace emdr2

@@ -213,11 +213,29 @@ int emdr2_gemm(int dtype, const void* a, int64_t lda, const void* b, int64_t ldb
                        cuda_stream);
 }
 
+static int check_dropout(float p, const uint32_t* colhash) {
+  if (!(p >= 0.f) || p >= 1.f) return fail(EMDR2_EINVAL, "dropout probability %g is not in [0, 1)", p);
+  if (p > 0.f && (!colhash || !aligned16(colhash)))
+    return fail(EMDR2_EINVAL, "dropout needs a 16-byte aligned column-hash table (emdr2_dropout_colhash)");
+  return EMDR2_OK;
+}
+
 int emdr2_attention_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk,
                         const void* v, int64_t ldv, void* o, int64_t ldo, int batch, int heads,
                         int sq, int sk, const uint8_t* q_pad, const uint8_t* k_pad,
                         const uint8_t* q_live, const uint8_t* k_live, int causal, float scale,
                         float* lse, void* cuda_stream) {
+  return emdr2_attention_fwd_dropout(dtype, q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, sk, q_pad, k_pad,
+                                     q_live, k_live, causal, scale, lse, 0.f, 0, 0, nullptr, cuda_stream);
+}
+
+int emdr2_attention_fwd_dropout(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                const void* v, int64_t ldv, void* o, int64_t ldo, int batch, int heads,
+                                int sq, int sk, const uint8_t* q_pad, const uint8_t* k_pad,
+                                const uint8_t* q_live, const uint8_t* k_live, int causal, float scale,
+                                float* lse, float p, uint64_t seed, uint64_t offset, const uint32_t* colhash,
+                                void* cuda_stream) {
+  if (check_dropout(p, colhash) != EMDR2_OK) return EMDR2_EINVAL;
   if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
     return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
   if (batch < 0 || heads < 1 || sq < 0 || sk < 0)
@@ -266,6 +284,8 @@ int emdr2_attention_fwd(int dtype, const void* q, int64_t ldq, const void* k, in
   aa.q_live = q_live;
   aa.k_live = k_live;
   aa.lse = lse;
+  aa.drop = emdr2::make_dropout_args(p, seed, offset, colhash);
+  if (aa.drop.threshold && legacy) return fail(EMDR2_EUNSUPPORTED, "the legacy attention kernel has no dropout");
   ScopedTimer timer(EMDR2_KIND_ATTENTION, static_cast<cudaStream_t>(cuda_stream),
                     4.0 * batch * heads * sq * static_cast<double>(sk) * emdr2::kAttnHeadDim);
   if (legacy)
@@ -375,6 +395,19 @@ int emdr2_attention_bwd(int dtype, const void* q, int64_t ldq, const void* k, in
                         int sq, int sk, const uint8_t* q_pad, const uint8_t* k_pad, const uint8_t* q_live,
                         const uint8_t* k_live, int causal, float scale, const float* lse, float* dvec_ws,
                         void* cuda_stream) {
+  return emdr2_attention_bwd_dropout(dtype, q, ldq, k, ldk, v, ldv, o, ldo, dout, lddo, dq, lddq, dk, lddk, dv, lddv,
+                                     batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, causal, scale, lse, dvec_ws,
+                                     0.f, 0, 0, nullptr, cuda_stream);
+}
+
+int emdr2_attention_bwd_dropout(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                int64_t ldv, const void* o, int64_t ldo, const void* dout, int64_t lddo, void* dq,
+                                int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int batch, int heads,
+                                int sq, int sk, const uint8_t* q_pad, const uint8_t* k_pad, const uint8_t* q_live,
+                                const uint8_t* k_live, int causal, float scale, const float* lse, float* dvec_ws,
+                                float p, uint64_t seed, uint64_t offset, const uint32_t* colhash,
+                                void* cuda_stream) {
+  if (check_dropout(p, colhash) != EMDR2_OK) return EMDR2_EINVAL;
   if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
     return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
   if (batch < 0 || heads < 1 || sq < 0 || sk < 1)
@@ -427,6 +460,7 @@ int emdr2_attention_bwd(int dtype, const void* q, int64_t ldq, const void* k, in
   aa.k_live = k_live;
   aa.lse = lse;
   aa.dvec = dvec_ws;
+  aa.drop = emdr2::make_dropout_args(p, seed, offset, colhash);
   CUDA_TRY(emdr2::launch_attention_bwd(mp, aa, bf16, stream));
   return EMDR2_OK;
 }
@@ -500,6 +534,50 @@ int emdr2_embedding_bwd(int dtype, const void* dx, const int64_t* ids, const int
   ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
   CUDA_TRY(emdr2::launch_embedding_bwd(dtype == EMDR2_DTYPE_BF16, dx, ids, types, dword, dpos, dtype_emb, tokens, seq,
                                        h, vocab, num_types, static_cast<cudaStream_t>(cuda_stream)));
+  return EMDR2_OK;
+}
+
+int emdr2_dropout_colhash(uint64_t seed, uint32_t* dev_table, int n, void* cuda_stream) {
+  if (n < 0 || (n > 0 && !dev_table)) return fail(EMDR2_EINVAL, "bad column-hash table (n=%d)", n);
+  DeviceInfo info;
+  int rc = require_b200(&info);
+  if (rc != EMDR2_OK) return rc;
+  CUDA_TRY(emdr2::launch_dropout_colhash(seed, dev_table, n, static_cast<cudaStream_t>(cuda_stream)));
+  return EMDR2_OK;
+}
+
+int emdr2_dropout_mask(float p, uint64_t seed, uint64_t offset, const uint32_t* colhash, uint8_t* dev_mask,
+                       int64_t rows, int cols, void* cuda_stream) {
+  if (!(p > 0.f) || p >= 1.f || !colhash || !dev_mask || rows < 0 || cols < 0)
+    return fail(EMDR2_EINVAL, "emdr2_dropout_mask needs 0 < p < 1, a column-hash table and an output buffer");
+  DeviceInfo info;
+  int rc = require_b200(&info);
+  if (rc != EMDR2_OK) return rc;
+  CUDA_TRY(emdr2::launch_dropout_mask(emdr2::make_dropout_args(p, seed, offset, colhash), dev_mask, rows, cols,
+                                      static_cast<cudaStream_t>(cuda_stream)));
+  return EMDR2_OK;
+}
+
+int emdr2_dropout_add(int dtype, const void* y, int64_t ldy, const void* residual, int64_t ldr, void* out,
+                      int64_t ldo, int rows, int cols, float p, uint64_t seed, uint64_t offset,
+                      const uint32_t* colhash, void* cuda_stream) {
+  if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
+    return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
+  if (!(p > 0.f) || p >= 1.f) return fail(EMDR2_EINVAL, "emdr2_dropout_add needs 0 < p < 1 (got %g)", p);
+  if (check_dropout(p, colhash) != EMDR2_OK) return EMDR2_EINVAL;
+  if (rows < 0 || cols < 0 || (cols % 8) || (ldy % 8) || (ldo % 8) || ldy < cols || ldo < cols ||
+      (residual && ((ldr % 8) || ldr < cols)))
+    return fail(EMDR2_EINVAL, "dropout_add needs cols %% 8 == 0 and row pitches %% 8 == 0, >= cols");
+  if (rows == 0 || cols == 0) return EMDR2_OK;
+  if (!y || !out || !aligned16(y) || !aligned16(out) || (residual && !aligned16(residual)))
+    return fail(EMDR2_EINVAL, "NULL or misaligned pointer passed to emdr2_dropout_add");
+  DeviceInfo info;
+  int rc = require_b200(&info);
+  if (rc != EMDR2_OK) return rc;
+  ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
+  CUDA_TRY(emdr2::launch_dropout_add(dtype == EMDR2_DTYPE_BF16, y, ldy, residual, ldr, out, ldo, rows, cols,
+                                     emdr2::make_dropout_args(p, seed, offset, colhash),
+                                     static_cast<cudaStream_t>(cuda_stream)));
   return EMDR2_OK;
 }
 

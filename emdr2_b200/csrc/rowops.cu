@@ -258,3 +258,80 @@ cudaError_t launch_embedding_fwd(bool bf16, const int64_t* ids, const int64_t* t
 }
 
 }  // namespace emdr2
+
+// ------------------------------------------------------------------------------------- dropout
+namespace emdr2 {
+namespace {
+
+__global__ void dropout_colhash_kernel(uint64_t seed, uint32_t* __restrict__ table, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) table[c] = dropout_col_hash(seed, static_cast<uint32_t>(c));
+}
+
+__global__ void dropout_mask_kernel(DropoutArgs d, uint8_t* __restrict__ mask, int64_t rows, int cols) {
+  const int64_t r = blockIdx.x;
+  const uint32_t a = dropout_row_hash(d.key_a, d.key_b, static_cast<uint64_t>(r));
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    mask[r * cols + c] = dropout_keep(a, __ldg(d.colhash + c), d.threshold) ? 1 : 0;
+}
+
+// One warp per row, 8 elements per lane per step (16-byte loads/stores).
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+dropout_add_kernel(const uint16_t* __restrict__ y, int64_t ldy, const uint16_t* __restrict__ res, int64_t ldr,
+                   uint16_t* __restrict__ out, int64_t ldo, int rows, int cols, DropoutArgs d) {
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (int row = blockIdx.x * warps + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps) {
+    const uint32_t a = dropout_row_hash(d.key_a, d.key_b, static_cast<uint64_t>(row));
+    const uint16_t* yr = y + static_cast<size_t>(row) * ldy;
+    const uint16_t* rr = res ? res + static_cast<size_t>(row) * ldr : nullptr;
+    uint16_t* orow = out + static_cast<size_t>(row) * ldo;
+    for (int col = lane * 8; col < cols; col += 256) {
+      float v[8], r[8];
+      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(yr + col)), v);
+      const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(d.colhash + col));
+      const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(d.colhash + col + 4));
+      const uint32_t hb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+      if (rr) unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(rr + col)), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float kept = dropout_keep(a, hb[i], d.threshold) ? v[i] * d.inv_keep : 0.f;
+        v[i] = rr ? r[i] + kept : kept;
+      }
+      *reinterpret_cast<uint4*>(orow + col) = pack8<kBf16>(v);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_dropout_colhash(uint64_t seed, uint32_t* table, int n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  dropout_colhash_kernel<<<(n + 255) / 256, 256, 0, stream>>>(seed, table, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dropout_mask(const DropoutArgs& d, uint8_t* mask, int64_t rows, int cols, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  dropout_mask_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(d, mask, rows, cols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dropout_add(bool bf16, const void* y, int64_t ldy, const void* residual, int64_t ldr, void* out,
+                               int64_t ldo, int rows, int cols, const DropoutArgs& d, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  const int warps = 8;
+  const int blocks = static_cast<int>(((rows + warps - 1) / warps) < 148 * 16 ? (rows + warps - 1) / warps : 148 * 16);
+  if (bf16)
+    dropout_add_kernel<true><<<blocks, 32 * warps, 0, stream>>>(
+        static_cast<const uint16_t*>(y), ldy, static_cast<const uint16_t*>(residual), ldr,
+        static_cast<uint16_t*>(out), ldo, rows, cols, d);
+  else
+    dropout_add_kernel<false><<<blocks, 32 * warps, 0, stream>>>(
+        static_cast<const uint16_t*>(y), ldy, static_cast<const uint16_t*>(residual), ldr,
+        static_cast<uint16_t*>(out), ldo, rows, cols, d);
+  return cudaGetLastError();
+}
+
+}  // namespace emdr2

@@ -51,3 +51,17 @@ cudaError_t launch_embedding_bwd(bool bf16, const void* dx, const int64_t* ids, 
                                  int vocab, int num_types, cudaStream_t stream);
 
 }  // namespace emdr2
+
+// ---- dropout (dropout.cuh) ---------------------------------------------------------------------
+#include "dropout.cuh"
+namespace emdr2 {
+// table[c] = B(c) for c < n (one table per seed; every dropout launch of that seed reads it)
+cudaError_t launch_dropout_colhash(uint64_t seed, uint32_t* table, int n, cudaStream_t stream);
+// mask[r, c] = 1 where element (r, c) is kept (test / inspection aid)
+cudaError_t launch_dropout_mask(const DropoutArgs& d, uint8_t* mask, int64_t rows, int cols, cudaStream_t stream);
+// out[r, :] = residual[r, :] + dropout(y[r, :])   (residual may be NULL; out may alias y): the
+// bias-dropout-add of transformer.py:397-419 once the bias is in y, the embedding dropout of
+// language_model.py:181, and — with y = the incoming gradient — their backward.
+cudaError_t launch_dropout_add(bool bf16, const void* y, int64_t ldy, const void* residual, int64_t ldr, void* out,
+                               int64_t ldo, int rows, int cols, const DropoutArgs& d, cudaStream_t stream);
+}  // namespace emdr2

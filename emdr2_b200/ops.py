@@ -81,12 +81,37 @@ def live_blocks(pad, block=128):
     return live.to(torch.uint8).contiguous()
 
 
+def dropout_add(y, residual, spec, out=None):
+    """out = residual + dropout(y) (residual may be None; out may be y): csrc/rowops.cu dropout_add_kernel.
+    `spec` is an emdr2_b200.dropout.DropoutSpec; the same spec regenerates the same mask."""
+    dtype, device = y.dtype, y.device
+    if dtype not in _DTYPES or not y.is_cuda:
+        raise TypeError("dropout_add takes CUDA float16/bfloat16 tensors")
+    _check_2d("y", y, dtype, device)
+    rows, cols = y.shape
+    if residual is not None:
+        _check_2d("residual", residual, dtype, device)
+        if tuple(residual.shape) != (rows, cols):
+            raise ValueError("residual must have y's shape")
+    if out is None:
+        out = torch.empty((rows, cols), dtype=dtype, device=device)
+    _check_2d("out", out, dtype, device)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.emdr2_dropout_add(
+            _DTYPES[dtype], _ptr(y), max(cols, y.stride(0)), _ptr(residual),
+            0 if residual is None else max(cols, residual.stride(0)), _ptr(out), max(cols, out.stride(0)), rows, cols,
+            *spec.c_args(), _stream(device)), "emdr2_dropout_add")
+    return out
+
+
 def attention(q, k, v, batch, heads, sq, sk, q_pad=None, k_pad=None, causal=False, scale=None,
-              out=None, return_lse=False, q_live=None, k_live=None):
+              out=None, return_lse=False, q_live=None, k_live=None, dropout=None):
     """Fused attention forward (head dim 64).  q/out: [batch*sq, >= heads*64] views, k/v:
     [batch*sk, >= heads*64] views (unit inner stride; e.g. column blocks of a fused QKV buffer).
     q_pad [batch, sq] / k_pad [batch, sk]: uint8/bool, 1 = padding.  Masked scores are replaced by
-    -10000 (the reference's attention_mask_func), not -inf.  q_live / k_live (uint8 block maps, see
+    -10000 (the reference's attention_mask_func), not -inf.  dropout: a DropoutSpec (attention dropout on the
+    normalised probabilities, transformer.py:345-346) or None.  q_live / k_live (uint8 block maps, see
     live_blocks) switch on padding skipping: identical results at non-padding queries, zeros at
     all-padding query blocks."""
     dtype, device = q.dtype, q.device
@@ -115,11 +140,12 @@ def attention(q, k, v, batch, heads, sq, sk, q_pad=None, k_pad=None, causal=Fals
     if scale is None:
         scale = 1.0 / 8.0
     lib = _lib.load()
+    drop = dropout.c_args() if dropout is not None else (ctypes.c_float(0.0), ctypes.c_uint64(0), ctypes.c_uint64(0), None)
     with torch.cuda.device(device):
-        _lib.check(lib.emdr2_attention_fwd(
+        _lib.check(lib.emdr2_attention_fwd_dropout(
             _DTYPES[dtype], _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
             _ptr(out), out.stride(0), batch, heads, sq, sk, _ptr(masks[0]), _ptr(masks[1]),
-            _ptr(q_live), _ptr(k_live), 1 if causal else 0, float(scale), _ptr(lse), _stream(device)),
+            _ptr(q_live), _ptr(k_live), 1 if causal else 0, float(scale), _ptr(lse), *drop, _stream(device)),
             "emdr2_attention_fwd")
     return (out, lse) if return_lse else out
 

@@ -222,6 +222,44 @@ EMDR2_API int emdr2_embedding_bwd(int dtype, const void* dx, const int64_t* ids,
                                   float* dword, float* dpos, float* dtype_emb, int tokens, int seq, int h,
                                   int vocab, int num_types, void* cuda_stream);
 
+/* ---- dropout (csrc/dropout.cuh).  The reference trains with torch dropout, p = 0.1, on the attention
+ * probabilities (megatron/model/transformer.py:345-346), on every bias-add-residual (transformer.py:397-419,
+ * 511-515) and on the embedding sum (language_model.py:181), and stores the masks for the backward pass.
+ * Here the mask is a counter-based function of (seed, offset, row, column): the caller picks one `offset`
+ * per dropout call site and training step and hands the SAME (p, seed, offset) to the backward entry point,
+ * which regenerates the mask.  p_eff = round(p * 2^32) / 2^32; kept values are scaled by 1 / (1 - p_eff).
+ * `colhash` is a caller-owned device table of column hashes for `seed` (emdr2_dropout_colhash), at least
+ * as long as the op's column count rounded up to 128. */
+EMDR2_API int emdr2_dropout_colhash(uint64_t seed, uint32_t* dev_table, int n, void* cuda_stream);
+
+/* mask[r, c] = 1 where (r, c) is kept, [rows, cols] bytes: for tests that replay a mask in a reference. */
+EMDR2_API int emdr2_dropout_mask(float p, uint64_t seed, uint64_t offset, const uint32_t* colhash,
+                                 uint8_t* dev_mask, int64_t rows, int cols, void* cuda_stream);
+
+/* out = residual + dropout(y) over [rows, cols] 16-bit tensors (residual may be NULL, out may alias y):
+ * bias_dropout_add once the bias is in y; with y = the incoming gradient and residual = NULL, its backward. */
+EMDR2_API int emdr2_dropout_add(int dtype, const void* y, int64_t ldy, const void* residual, int64_t ldr,
+                                void* out, int64_t ldo, int rows, int cols, float p, uint64_t seed,
+                                uint64_t offset, const uint32_t* colhash, void* cuda_stream);
+
+/* emdr2_attention_fwd / emdr2_attention_bwd with attention dropout: P is multiplied by keep / (1 - p) after
+ * the softmax normalisation (lse is that of the undropped probabilities); dropout plane row =
+ * (b * heads + head) * sq + query, column = key.  p = 0 is exactly the entry points above. */
+EMDR2_API int emdr2_attention_fwd_dropout(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                          const void* v, int64_t ldv, void* o, int64_t ldo, int batch, int heads,
+                                          int sq, int sk, const uint8_t* q_pad, const uint8_t* k_pad,
+                                          const uint8_t* q_live, const uint8_t* k_live, int causal, float scale,
+                                          float* lse, float p, uint64_t seed, uint64_t offset,
+                                          const uint32_t* colhash, void* cuda_stream);
+EMDR2_API int emdr2_attention_bwd_dropout(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                          const void* v, int64_t ldv, const void* o, int64_t ldo, const void* dout,
+                                          int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv,
+                                          int64_t lddv, int batch, int heads, int sq, int sk, const uint8_t* q_pad,
+                                          const uint8_t* k_pad, const uint8_t* q_live, const uint8_t* k_live,
+                                          int causal, float scale, const float* lse, float* dvec_ws, float p,
+                                          uint64_t seed, uint64_t offset, const uint32_t* colhash,
+                                          void* cuda_stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-side integer work of the step (no device code, callable without a GPU).
  * ---------------------------------------------------------------------------------------------- */

@@ -69,7 +69,9 @@ def to_oracle_input(t):
 
 
 # ------------------------------------------------------------------ tiny BERT/T5 config (blocks)
-TINY = dict(hidden=128, heads=2, layers=2, ffn=256, vocab=128, max_pos=64)
+# dropout off unless a test turns it on: the parity tests compare against dropout-free references
+TINY = dict(hidden=128, heads=2, layers=2, ffn=256, vocab=128, max_pos=64, hidden_dropout=0.0,
+            attention_dropout=0.0)
 
 
 def seeded_weights(name, shape):

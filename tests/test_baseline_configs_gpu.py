@@ -119,7 +119,8 @@ def test_t5_base_shape_reader_vs_oracle():
     from emdr2_b200.blocks import T5Reader
     from oracle import blocks as ob
     dtype = torch.bfloat16
-    cfg = dict(hidden=768, heads=12, layers=12, ffn=3072, vocab=30720, max_pos=512, dtype=dtype)
+    cfg = dict(hidden=768, heads=12, layers=12, ffn=3072, vocab=30720, max_pos=512, dtype=dtype, hidden_dropout=0.0,
+               attention_dropout=0.0)
     model = T5Reader(cfg).to(DEV)
     w32 = {}
     with torch.no_grad():

@@ -126,7 +126,8 @@ def test_bert_base_shape_vs_oracle():
     from emdr2_b200.blocks import BertTower
     from oracle import blocks as ob
     dtype = torch.bfloat16
-    cfg = dict(hidden=768, heads=12, layers=12, ffn=3072, vocab=1024, max_pos=256, dtype=dtype)
+    cfg = dict(hidden=768, heads=12, layers=12, ffn=3072, vocab=1024, max_pos=256, dtype=dtype, hidden_dropout=0.0,
+               attention_dropout=0.0)
     model = BertTower(cfg).to(DEV)
     model.language_model.skip_padding = False
     w32 = _fill(model, dtype)

@@ -17,7 +17,7 @@ from emdr2_b200.model import DualEncoder
 DEV = "cuda:0"
 BATCH, SEQ, BATCHES = int(os.environ.get("BATCH", "128")), 256, int(os.environ.get("BATCHES", "60"))
 torch.manual_seed(0)
-model = DualEncoder(bert_base_config(torch.bfloat16), bert_vocab_size=30592, only_context_model=True).to(DEV)
+model = DualEncoder(bert_base_config(torch.bfloat16), bert_vocab_size=30592, only_context_model=True).to(DEV).eval()
 with torch.no_grad():
     for name, p in model.named_parameters():
         p.normal_(0.0, 0.02) if p.dim() > 1 else p.zero_()

@@ -74,7 +74,7 @@ def main():  # noqa
 
     from emdr2_b200.blocks import BertTower, bert_base_config
     cfg = bert_base_config(dtype)
-    model = BertTower(cfg).to(DEV)
+    model = BertTower(cfg).to(DEV).eval()
     with torch.no_grad():
         for p in model.parameters():
             p.normal_(0, 0.02)
