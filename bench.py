@@ -70,6 +70,9 @@ def parse_args():
     p.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-gpu-reference", action="store_true")
+    p.add_argument("--no-train-step", action="store_true", help="skip the train_step block of the default line")
+    p.add_argument("--train-steps", type=int, default=6, help="timed training steps of the train_step block")
+    p.add_argument("--no-dropout", action="store_true", help="train with hidden/attention dropout 0 (A/B only)")
     a = p.parse_args()
     if a.steps is None:
         a.steps = 200 if a.retrieve_only else 20
@@ -631,6 +634,76 @@ def gpu_reference_leg(torch, rows, q_dev, a):
         return {"unavailable": str(exc).splitlines()[0][:200]}
 
 
+def gpu_reference_read_leg(a, d, model, rows, all_q, dev, iters=3):
+    """What the REFERENCE executes on a GPU for one step of this workload, on the same B200 and the same
+    inputs: its retrieval (DistributedBruteForceIndex, megatron/data/emdr2_index.py:281-295: fp16 matmul into a
+    C[nq, N] score matrix in HBM, then torch.topk) and its towers / reader as eager fp16 PyTorch — cuBLAS + ATen
+    kernels, dense [b, s, s] masks, padded rectangles, unfused softmax — through oracle/blocks.py, the restatement
+    of megatron/model/{transformer,language_model,t5_model,dualencoder_model}.py that tests/golden pins to the
+    reference's own modules.  (The reference itself cannot travel to the GPU box, and its FusedLayerNorm / fused
+    softmax need apex / THC.)  A reported baseline: nothing of this repo's kernels runs in it, and nothing of it
+    runs in the product path.  The reference's Python retrieval tail (400 iterations with bisect + mmap reads per
+    step, emdr2_model.py:457-468) and formatting loops are NOT included, which flatters the reference."""
+    torch = d.torch
+    try:
+        from oracle import blocks as ob
+        from emdr2_b200 import formatter
+        st = model.settings
+        h, heads, layers = a.dim, a.dim // 64, a.layers
+
+        def w16(module):
+            return {n: p.detach().to(torch.float16) for n, p in module.named_parameters()}
+
+        wq, wc = w16(model.retriever_model.query_model), w16(model.retriever_model.context_model)
+        wt = w16(model.language_model)
+        rows16 = rows if rows.dtype == torch.float16 else rows.to(torch.float16)
+        with torch.no_grad():
+            topk_data, _ = model.evidence_retriever.get_topk(all_q[:a.batch].contiguous() if d.world == 1 else
+                                                             all_q[d.rank * a.batch:(d.rank + 1) * a.batch].contiguous(),
+                                                             as_packed=True)
+            (ctx_ids, ctx_types, ext_ids, _one), _ = formatter.postprocess(
+                dev["uid"], dev["q_t5"], dev["q_len"], topk_data, a.k, a.seq_ret, a.seq, st["cls_id"], st["sep_id"],
+                st["pad_id"], device=dev["q_bert"].device, return_lengths=True)
+        ctx_ids, ctx_types = ctx_ids.reshape(-1, a.seq_ret), ctx_types.reshape(-1, a.seq_ret)
+        ext_ids = ext_ids.reshape(-1, a.seq)
+        parts = {}
+
+        def step():
+            with torch.no_grad():
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record()
+                q = ob.bert_pooled(dev["q_bert"], dev["q_types"], wq, heads, layers)
+                ev[1].record()
+                c_mat = torch.matmul(all_q.to(torch.float16), rows16.T)              # C[nq, N] fp16 in HBM (:281-292)
+                torch.topk(c_mat, a.k, dim=1)                                         # (:295)
+                ev[2].record()
+                ctx = ob.bert_pooled(ctx_ids, ctx_types, wc, heads, layers).reshape(a.batch, a.k, h)
+                sim = torch.bmm(q.unsqueeze(1).float(), ctx.float().transpose(1, 2)) / h ** 0.5
+                torch.log_softmax(sim, dim=2)
+                enc = ob.t5_encode(ext_ids, wt, heads, layers)
+                logits = ob.t5_decode(dev["dec"], enc.reshape(a.batch, a.k * a.seq, h),
+                                      ext_ids.reshape(a.batch, a.k * a.seq), wt, heads, layers)
+                ev[3].record()
+            return ev, logits
+
+        step()
+        torch.cuda.synchronize()
+        tot = [0.0, 0.0, 0.0]
+        for _ in range(iters):
+            ev, _ = step()
+            torch.cuda.synchronize()
+            for j in range(3):
+                tot[j] += ev[j].elapsed_time(ev[j + 1]) / iters
+        ms = d.max_over_ranks(sum(tot))
+        return {"value": a.batch * d.world / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
+                "query_tower_ms": tot[0], "retrieve_ms": tot[1], "read_ms": tot[2], "steps": iters, "dtype": "fp16",
+                "what": "eager fp16 PyTorch (cuBLAS + ATen) restatement of the reference's GPU step on the same B200, same "
+                        "inputs, full shapes (oracle/blocks.py towers + reader, matmul -> C[nq,N] -> topk retrieval); the "
+                        "reference's Python retrieval tail and formatting loops excluded"}
+    except Exception as exc:
+        return {"unavailable": (type(exc).__name__ + ": " + str(exc)).splitlines()[0][:300]}
+
+
 def run_retrieve_read(a):
     import torch
     from emdr2_b200 import ops
@@ -652,7 +725,9 @@ def run_retrieve_read(a):
     searcher = retriever.mips_index._searcher
 
     # ---- model: 2 x BERT-base towers + T5-base-shaped reader, random init N(0, 0.02)
-    cfg = dict(hidden=a.dim, heads=a.dim // 64, layers=a.layers, ffn=4 * a.dim, vocab=30720, max_pos=512, dtype=mdtype)
+    p_drop = 0.0 if a.no_dropout else 0.1        # the reference's --hidden-dropout / --attention-dropout defaults
+    cfg = dict(hidden=a.dim, heads=a.dim // 64, layers=a.layers, ffn=4 * a.dim, vocab=30720, max_pos=512, dtype=mdtype,
+               hidden_dropout=p_drop, attention_dropout=p_drop)
     settings = dict(topk_retrievals=a.k, seq_length=a.seq, seq_length_ret=a.seq_ret, retriever_score_scaling=True,
                     update_retriever=a.train, cls_id=101, sep_id=102, pad_id=0)
     torch.manual_seed(1234)
@@ -676,89 +751,160 @@ def run_retrieve_read(a):
     def forward(x):
         return model(x["uid"], x["q_bert"], x["q_types"], None, x["q_t5"], x["q_len"], x["dec"])
 
-    if a.train:
+    labels_host = host["dec"].roll(-1, dims=1)
+    labels_host[:, -1] = 0
+    host["labels"] = labels_host
+    pinned["labels"] = labels_host.pin_memory()
+    dev["labels"] = labels_host.to(device)
+    out_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+    trainer = {}
+
+    def train_step(x):
+        """forward (dropout on, incl. the no-grad one-context pass) -> both losses -> backward with the bucketed
+        gradient all-reduce running underneath it -> AdamW on flat fp32 masters -> copy-back, one op per bucket."""
         from emdr2_b200 import losses
-        params = [p for p in model.parameters()]
-        masters = [p.detach().float().clone().requires_grad_(True) for p in params]   # fp32 master weights
-        optimizer = torch.optim.AdamW(masters, lr=2e-5, weight_decay=0.01, fused=True)
-        labels_host = host["dec"].roll(-1, dims=1)
-        labels_host[:, -1] = 0
-        host["labels"] = labels_host
-        pinned["labels"] = labels_host.pin_memory()
-        dev["labels"] = labels_host.to(device)
-        out_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+        if not trainer:
+            from emdr2_b200.data_parallel import GradientBuckets, flatten_parameters
+            trainer["buckets"] = gb = GradientBuckets(list(model.parameters()), group=d.group)
+            trainer["pflat"] = flatten_parameters(gb)
+            trainer["masters"] = [f.float().requires_grad_(True) for f in trainer["pflat"]]
+            for m in trainer["masters"]:
+                m.grad = torch.zeros_like(m)
+            # torch.optim (library): the reference uses apex FusedAdam; the optimizer is a caller of the hot path
+            trainer["opt"] = torch.optim.AdamW(trainer["masters"], lr=2e-5, weight_decay=0.01, fused=True)
+        gb = trainer["buckets"]
+        gb.start_step()
+        lm_logits, topk_log_probs, one_ctx = forward(x)
+        mask = (x["labels"] > 0).float()
+        lm_loss = losses.reader_cross_entropy(lm_logits, x["labels"], mask)
+        r_loss, _, _ = losses.get_loss_and_retriever_utility(one_ctx, topk_log_probs, x["labels"], mask, 30523)
+        (lm_loss + r_loss).backward()
+        gb.finish()
+        for m, b in zip(trainer["masters"], gb.buckets):
+            m.grad.copy_(b.grad)
+            if world > 1:
+                m.grad.mul_(1.0 / world)
+        trainer["opt"].step()
+        with torch.no_grad():
+            for f, m in zip(trainer["pflat"], trainer["masters"]):
+                f.copy_(m)
+        return lm_loss, r_loss
 
-        def train_step(x):
-            lm_logits, topk_log_probs, one_ctx = forward(x)
-            mask = (x["labels"] > 0).float()
-            lm_loss = losses.reader_cross_entropy(lm_logits, x["labels"], mask)
-            r_loss, _, _ = losses.get_loss_and_retriever_utility(one_ctx, topk_log_probs, x["labels"], mask, 30523)
-            (lm_loss + r_loss).backward()
-            grads = [p.grad for p in params if p.grad is not None]
-            if world > 1:     # local DDP: one flat all-reduce of the gradients (model/distributed.py:35-63)
-                flat = torch._utils._flatten_dense_tensors(grads)
-                flat.div_(world)
-                d.dist.all_reduce(flat)
-                for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                    g.copy_(f)
-            for m, p in zip(masters, params):
-                m.grad = None if p.grad is None else p.grad.float()
-            optimizer.step()
-            with torch.no_grad():
-                torch._foreach_copy_(params, masters)
-            for p in params:
-                p.grad = None
-            return lm_loss, r_loss
+    def train_resident_step(i):
+        return train_step(dev)
 
-        def resident_step(i):
-            return train_step(dev)
+    def train_e2e_step(i):
+        x = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
+        lm_loss, r_loss = train_step(x)
+        out_loss.copy_(torch.stack([lm_loss.detach(), r_loss.detach()]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
-        def e2e_step(i):
-            x = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
-            lm_loss, r_loss = train_step(x)
-            out_loss.copy_(torch.stack([lm_loss.detach(), r_loss.detach()]), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-    else:
-        def resident_step(i):
-            with torch.no_grad():
-                return forward(dev)
+    def fwd_resident_step(i):
+        with torch.no_grad():
+            return forward(dev)
 
-        def e2e_step(i):
-            x = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
-            with torch.no_grad():
-                lm_logits, topk_log_probs, _, _ = forward(x)
-            out_ids.copy_(lm_logits.argmax(dim=-1), non_blocking=True)
-            out_lp.copy_(topk_log_probs, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+    def fwd_e2e_step(i):
+        x = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
+        with torch.no_grad():
+            lm_logits, topk_log_probs, _, _ = forward(x)
+        out_ids.copy_(lm_logits.argmax(dim=-1), non_blocking=True)
+        out_lp.copy_(topk_log_probs, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    nq_search = a.batch * world
+    peak_t, peak_t_src = measured_peak("bf16_tflops_sustained")
+
+    def measure(resident_step, e2e_step, steps, warm):
+        """Timed region of one mode: `steps` resident steps with per-kernel-kind CUDA events on, then `steps`
+        end-to-end steps (pinned host batch in, results out)."""
+        for i in range(warm):
+            resident_step(i)
+        e2e_step(0)
+        torch.cuda.synchronize()
+        with ClockSampler(d.local_rank) as clocks:
+            searcher.set_option("timing", 1)
+            ops.timing(True)
+            ms_total = d.timed(resident_step, steps)
+            roof_mips = mips_roofline(a, d, searcher, hi - lo, nq_search)
+            gemm_s, gemm_n, gemm_fl = ops.timing_read(ops.KIND_GEMM)
+            attn_s, attn_n, attn_fl = ops.timing_read(ops.KIND_ATTENTION)
+            row_s, row_n, _ = ops.timing_read(ops.KIND_ROWOP)
+            ops.timing(False)
+            searcher.set_option("timing", 0)
+            ms_e2e = d.timed(e2e_step, steps)
+        gemm_tf = gemm_fl / d.max_over_ranks(gemm_s) / 1e12
+        return dict(ms_step=ms_total / steps, ms_e2e_step=ms_e2e / steps, roof_mips=roof_mips, clocks=clocks.summary(),
+                    gemm_ms=gemm_s / steps * 1e3, attn_ms=attn_s / steps * 1e3, row_ms=row_s / steps * 1e3,
+                    gemm_tf=gemm_tf, attn_tf=attn_fl / max(attn_s, 1e-12) / 1e12, gemm_flops_step=gemm_fl / steps,
+                    gemm_launches=gemm_n, launches_step=(gemm_n + attn_n + row_n) // steps + (2 if world == 1 else 3))
 
     warm = max(3, a.warmup)
-    for i in range(warm):
-        resident_step(i)
-    e2e_step(0)
-    torch.cuda.synchronize()
-    nq_search = a.batch * world
-    with ClockSampler(d.local_rank) as clocks:
-        searcher.set_option("timing", 1)
-        ops.timing(True)
-        ms_total = d.timed(resident_step, a.steps)
-        roof_mips = mips_roofline(a, d, searcher, hi - lo, nq_search)
-        gemm_s, gemm_n, gemm_fl = ops.timing_read(ops.KIND_GEMM)
-        attn_s, attn_n, attn_fl = ops.timing_read(ops.KIND_ATTENTION)
-        row_s, row_n, _ = ops.timing_read(ops.KIND_ROWOP)
-        ops.timing(False)
-        searcher.set_option("timing", 0)
-        ms_e2e = d.timed(e2e_step, a.steps)
-    ms_step = ms_total / a.steps
-    peak_t, peak_t_src = measured_peak("bf16_tflops_sustained")
-    gemm_tf = gemm_fl / d.max_over_ranks(gemm_s) / 1e12
-    attn_tf = attn_fl / max(attn_s, 1e-12) / 1e12
-    launches_step = (gemm_n + attn_n + row_n) // a.steps + (2 if world == 1 else 3)
     tokens = a.batch * (a.seq_ret + a.k * a.seq_ret + a.k * a.seq)
     fmt_h2d = a.batch * a.k * (a.seq_ret + 2 * a.seq) * 8      # ids of the three layouts (types are zeros made on the device)
     in_bytes = sum(v.numel() * 8 for v in host.values())
+
+    def train_block(steps, warm_steps):
+        """The full EMDR2 training step (BASELINE config 4: forward with dropout 0.1, backward, gradient all-reduce,
+        optimizer) measured in this same run."""
+        from emdr2_b200 import dropout
+        dropout.manual_seed(1234 + rank)
+        model.train(True)
+        model.settings["update_retriever"] = True
+        m = measure(train_resident_step, train_e2e_step, steps, warm_steps)
+        gb = trainer["buckets"]
+        ar_ms = None
+        if world > 1:          # the exchange alone: all buckets back to back, nothing to hide behind
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                for b in gb.buckets:
+                    d.dist.all_reduce(b.grad)
+            e1.record()
+            torch.cuda.synchronize()
+            ar_ms = d.max_over_ranks(e0.elapsed_time(e1) / 3)
+        return {"value": a.batch * world / (m["ms_step"] * 1e-3), "unit": "queries/s", "ms_per_step": m["ms_step"],
+                "steps": steps, "warmup": warm_steps,
+                "e2e": {"value": a.batch * world / (m["ms_e2e_step"] * 1e-3), "unit": "queries/s",
+                        "h2d_bytes_per_step": in_bytes + fmt_h2d, "d2h_bytes_per_step": 8 + a.batch * a.k * 4},
+                "kernel_time_ms_per_step": {"gemm": m["gemm_ms"], "attention": m["attn_ms"], "rowops": m["row_ms"],
+                                            "mips_scan": m["roof_mips"]["kernel_ms"], "gemm_tflops": m["gemm_tf"],
+                                            "attention_tflops": m["attn_tf"]},
+                "gemm_frac_of_sustained_peak": m["gemm_tf"] / peak_t,
+                "gradient_allreduce": {"buckets": len(gb.buckets), "bytes": sum(b.grad.numel() * b.grad.element_size() for b in gb.buckets),
+                                       "launched_from_backward_hooks": gb.launched,
+                                       "exposed_alone_ms": ar_ms,
+                                       "how": "one async NCCL all-reduce per 64 MB bucket, launched when the bucket's last "
+                                              "gradient is accumulated (overlaps the rest of backward); gradients live in "
+                                              "flat buffers (no flatten/unflatten copies)"},
+                "dropout": {"hidden": cfg["hidden_dropout"], "attention": cfg["attention_dropout"],
+                            "how": "counter-based masks regenerated in the backward kernels (csrc/dropout.cuh)"},
+                "gpu_launches": int(m["launches_step"] * steps), "clocks": m["clocks"],
+                "stage": "full training step: forward incl. the no-grad one-context pass (dropout on), reader + retriever "
+                         "losses, backward, bucketed gradient all-reduce overlapped with backward, fused AdamW on flat fp32 "
+                         "masters (torch.optim, library — the reference uses apex FusedAdam)"}
+
+    if a.train:
+        steps = a.steps
+        tb = train_block(steps, warm)
+        head = {"value": tb["value"], "ms_step": tb["ms_per_step"], "e2e": tb["e2e"], "clocks": tb["clocks"],
+                "launches": tb["gpu_launches"]}
+        m = None
+    else:
+        model.train(False)
+        m = measure(fwd_resident_step, fwd_e2e_step, a.steps, warm)
+        head = {"value": a.batch * world / (m["ms_step"] * 1e-3), "ms_step": m["ms_step"], "clocks": m["clocks"],
+                "launches": int(m["launches_step"] * a.steps),
+                "e2e": {"value": a.batch * world / (m["ms_e2e_step"] * 1e-3), "unit": "queries/s",
+                        "h2d_bytes_per_step": in_bytes + fmt_h2d,
+                        "d2h_bytes_per_step": out_ids.numel() * 8 + out_lp.numel() * 4 + a.batch * a.k * 4}}
+    head["e2e"]["api"] = ("EMDR2Model.forward + losses + backward + optimizer (pinned host batch in; the two losses out)"
+                          if a.train else
+                          "EMDR2Model.forward (pinned host question tensors in; greedy token ids + passage log-probs out)") + \
+        "; includes the host-side passage lookup/formatting"
     line = {
-        "metric": metric_name(a), "value": a.batch * world / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
-        "steps": a.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "metric": metric_name(a), "value": head["value"], "unit": "queries/s", "n_gpus": world,
+        "steps": a.steps, "warmup": warm, "ms_per_step": head["ms_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": a.model_dtype + " reader/retriever, " + a.dtype + " evidence, fp32 accumulate",
         "data": "synthetic",
         "config": {
@@ -768,30 +914,31 @@ def run_retrieve_read(a):
             "exchange": "none" if world == 1 else "all-gather of queries [B,768] + all-gather of [nq,k] (score,id) pairs + merge",
             "l2": "inputs larger than L2 (%.2f GB evidence + %.1f GB of activations streamed per step vs 126 MB L2)" % (
                 (hi - lo) * a.dim * 2 / 1e9, tokens * a.dim * 2 * 40 / 1e9),
-            "stage": ("full training step: forward incl. no-grad one-context pass, reader + retriever losses, backward, "
-                      "flat gradient all-reduce, fused AdamW on fp32 masters (torch.optim, library — the reference uses apex FusedAdam)")
-            if a.train else "retrieve + read FORWARD (EMDR2Model.forward eval path); no backward/optimizer in the timed region"},
-        "e2e": {"value": a.batch * world / (ms_e2e / a.steps * 1e-3), "unit": "queries/s",
-                "h2d_bytes_per_step": in_bytes + fmt_h2d, "d2h_bytes_per_step": out_ids.numel() * 8 + out_lp.numel() * 4 + a.batch * a.k * 4,
-                "api": ("EMDR2Model.forward + losses + backward + optimizer (pinned host batch in; the two losses out)" if a.train else
-                        "EMDR2Model.forward (pinned host question tensors in; greedy token ids + passage log-probs out)") +
-                       "; includes the host-side passage lookup/formatting"},
-        "gpu_launches": int(launches_step * a.steps),
-        "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_t, "unit": "TFLOP/s", "frac": gemm_tf / peak_t,
-                     "traffic": recorded_gemm_traffic(),
-                     "traffic_note": "mean DRAM bytes/launch of the layer's four projections at 102400 tokens (ncu --set full, "
-                                     "profiles/roofline_traffic.json); the bound is the tensor pipe, not DRAM",
-                     "kernel": "emdr2::gemm_kernel (+ emdr2::gemm_pair_kernel for residual epilogues over >=100k rows)",
-                     "algorithmic_flops_per_step": gemm_fl / a.steps,
-                     "kernel_ms_per_step": gemm_s / a.steps * 1e3, "launches_timed": gemm_n, "peak_source": peak_t_src},
-        "roofline_mips": roof_mips,
-        "kernel_time_ms_per_step": {"gemm": gemm_s / a.steps * 1e3, "attention": attn_s / a.steps * 1e3,
-                                    "rowops": row_s / a.steps * 1e3, "mips_scan": roof_mips["kernel_ms"],
-                                    "attention_tflops": attn_tf},
-        "clocks": clocks.summary(),
+            "stage": tb["stage"] if a.train else
+            "retrieve + read FORWARD (EMDR2Model.forward eval path); no backward/optimizer in the timed region "
+            "(the full training step measured in the same run is under train_step)"},
+        "e2e": head["e2e"], "gpu_launches": head["launches"], "clocks": head["clocks"],
     }
+    if m is not None:
+        line["roofline"] = {
+            "bound": "tensor", "achieved": m["gemm_tf"], "peak": peak_t, "unit": "TFLOP/s", "frac": m["gemm_tf"] / peak_t,
+            "traffic": recorded_gemm_traffic(),
+            "traffic_note": "mean DRAM bytes/launch of the layer's four projections at 102400 tokens (ncu --set full, "
+                            "profiles/roofline_traffic.json); the bound is the tensor pipe, not DRAM",
+            "kernel": "emdr2::gemm_kernel (+ emdr2::gemm_pair_kernel for residual epilogues over >=100k rows)",
+            "algorithmic_flops_per_step": m["gemm_flops_step"], "kernel_ms_per_step": m["gemm_ms"],
+            "launches_timed": m["gemm_launches"], "peak_source": peak_t_src}
+        line["roofline_mips"] = m["roof_mips"]
+        line["kernel_time_ms_per_step"] = {"gemm": m["gemm_ms"], "attention": m["attn_ms"], "rowops": m["row_ms"],
+                                           "mips_scan": m["roof_mips"]["kernel_ms"], "attention_tflops": m["attn_tf"]}
+    else:
+        line["roofline"] = {"bound": "tensor", "achieved": tb["kernel_time_ms_per_step"]["gemm_tflops"], "peak": peak_t,
+                            "unit": "TFLOP/s", "frac": tb["gemm_frac_of_sustained_peak"], "traffic": recorded_gemm_traffic(),
+                            "kernel": "emdr2::gemm_kernel (forward, dX and split-K dW products)", "peak_source": peak_t_src}
+        line["train_step"] = tb
     # parity of THIS step's retrieval (outside the timed region): the question embeddings the query tower
     # produces for the batch, gathered over the ranks exactly as get_topk does, searched by the index
+    model.train(False)
     with torch.no_grad():
         q_emb = model.retriever_embedder(dev["q_bert"], None, dev["q_types"], "query").to(edtype).contiguous()
         if world > 1:
@@ -800,6 +947,10 @@ def run_retrieve_read(a):
         else:
             all_q = q_emb
         line["parity"] = retrieval_parity(d, retriever.mips_index, rows, lo, all_q, retriever.topk)
+    if not a.train and not a.no_gpu_reference:
+        line["gpu_reference"] = gpu_reference_read_leg(a, d, model, rows, all_q, dev)
+    if not a.train and not a.no_train_step:
+        line["train_step"] = train_block(a.train_steps, 2)
     line["cpu_baseline"] = cpu_baseline(a) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -40,7 +40,7 @@ def pad_mask_3d(source_ids, target_ids):
 
 def history_mask_3d(ids):
     n = ids.shape[1]
-    ar = torch.arange(n)
+    ar = torch.arange(n, device=ids.device)
     return (ar[None, :] <= ar[:, None])[None].expand(ids.shape[0], n, n)
 
 
