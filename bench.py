@@ -73,6 +73,8 @@ def parse_args():
     p.add_argument("--no-train-step", action="store_true", help="skip the train_step block of the default line")
     p.add_argument("--train-steps", type=int, default=6, help="timed training steps of the train_step block")
     p.add_argument("--no-dropout", action="store_true", help="train with hidden/attention dropout 0 (A/B only)")
+    p.add_argument("--refresh-rows", type=int, default=32768,
+                   help="passages each GPU re-encodes in the index_refresh block (BASELINE config 5, bounded sample); 0 = skip")
     a = p.parse_args()
     if a.steps is None:
         a.steps = 200 if a.retrieve_only else 20
@@ -389,7 +391,7 @@ def run_reference_arm(a):
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -604,7 +606,7 @@ def run_retrieve_only(a):
         line["gpu_reference"] = gpu_reference_leg(torch, rows, q_dev, a)
     line["cpu_baseline"] = cpu_baseline(a) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     d.finish()
     return 0
 
@@ -884,6 +886,77 @@ def run_retrieve_read(a):
                          "losses, backward, bucketed gradient all-reduce overlapped with backward, fused AdamW on flat fp32 "
                          "masters (torch.optim, library — the reference uses apex FusedAdam)"}
 
+    def refresh_block(train_ms_alone):
+        """BASELINE config 5 on the SAME GPUs: every rank re-encodes rows of its own shard with a frozen copy of the
+        context tower on a side stream (async_indexer.ConcurrentShardRefresher) while the training steps keep
+        running; then all ranks swap the standby shard in between two steps.  Bounded sample: --refresh-rows
+        passages per GPU (S = 256, indexer batch 128, arguments.py:589), the rest of the standby copied."""
+        import numpy as np
+        from emdr2_b200.async_indexer import ConcurrentShardRefresher
+        index = retriever.mips_index
+        n_rows = min(a.refresh_rows, hi - lo) // 128 * 128
+        if n_rows <= 0:
+            return {"unavailable": "shard smaller than one indexer batch"}
+        rng = np.random.RandomState(77 + rank)
+        host_batches = []
+        for b0 in range(0, n_rows, 128):
+            ids = np.zeros((128, a.seq_ret), dtype=np.int64)
+            for r, ln in enumerate(rng.randint(105, 192, size=128)):
+                ids[r, 0] = 101
+                ids[r, 1:ln] = rng.randint(1000, 30000, size=ln - 1)
+            host_batches.append((torch.arange(lo + b0 + 1, lo + b0 + 129), torch.from_numpy(ids).pin_memory(),
+                                 torch.zeros((128, a.seq_ret), dtype=torch.int64).pin_memory()))
+        refresher = ConcurrentShardRefresher(index, model.retriever_model.context_model, lambda: iter(host_batches),
+                                             group=d.group, partial=True)
+        # (1) the refresh alone (no training running): the rate the GPU gives the indexer when it has it all
+        d.barrier()
+        refresher.start()
+        while not refresher.maybe_swap():
+            time.sleep(0.002)
+        alone_s = d.max_over_ranks(refresher.seconds)
+        # (2) the refresh while training steps run
+        d.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        refresher.start()
+        e0.record()
+        steps_during, swapped = 0, False
+        while not swapped and steps_during < 400:
+            train_resident_step(steps_during)
+            steps_during += 1
+            swapped = refresher.maybe_swap()
+        e1.record()
+        torch.cuda.synchronize()
+        busy_s = d.max_over_ranks(refresher.seconds)
+        ms_during = d.max_over_ranks(e0.elapsed_time(e1)) / max(1, steps_during)
+        # (3) after the swap: the step's retrieval against an independent search of the NEW resident rows, and the
+        # refreshed rows themselves against the frozen tower (first indexer batch)
+        model.train(False)
+        with torch.no_grad():
+            q_emb = model.retriever_embedder(dev["q_bert"], None, dev["q_types"], "query").to(edtype).contiguous()
+            if world > 1:
+                all_q2 = torch.empty((world * q_emb.shape[0], q_emb.shape[1]), dtype=q_emb.dtype, device=device)
+                d.dist.all_gather_into_tensor(all_q2, q_emb)
+            else:
+                all_q2 = q_emb
+            par = retrieval_parity(d, index, index.evidence_embeds, lo, all_q2, retriever.topk)
+            rid, tok, typ = host_batches[0]
+            t = tok.numpy()
+            lens = ((t != 0) * np.arange(1, t.shape[1] + 1)).max(axis=1)
+            again = refresher.tower(tok.to(device), None, typ.to(device), max_len=int(lens.max()), row_lengths=lens)
+            rows_match = bool(torch.equal(again.to(edtype), index.evidence_embeds[:128]))
+        model.train(True)
+        return {"passages_per_s_while_training": n_rows * world / busy_s, "passages_per_s_alone": n_rows * world / alone_s,
+                "unit": "passages/s (all %d GPUs)" % world, "rows_reencoded_per_gpu": n_rows,
+                "train_ms_per_step_alone": train_ms_alone, "train_ms_per_step_during_refresh": ms_during,
+                "step_time_inflation": ms_during / train_ms_alone, "training_steps_during_refresh": steps_during,
+                "full_refresh_21M_s_at_this_rate": a.rows / (n_rows * world / busy_s),
+                "swap": {"collective": "all ranks agree (all-reduce of ready flags) and swap between the same two steps",
+                         "swapped": bool(swapped), "rounds": refresher.rounds, "parity_after_swap": par["ids"],
+                         "refreshed_rows_equal_frozen_tower_output": rows_match},
+                "how": "each rank re-encodes its OWN row range (frozen context-tower copy, side CUDA stream, worker "
+                       "thread) straight into a standby shard in HBM while training steps run on the main stream; "
+                       "bounded sample, remaining standby rows copied from the live shard"}
+
     if a.train:
         steps = a.steps
         tb = train_block(steps, warm)
@@ -951,14 +1024,39 @@ def run_retrieve_read(a):
         line["gpu_reference"] = gpu_reference_read_leg(a, d, model, rows, all_q, dev)
     if not a.train and not a.no_train_step:
         line["train_step"] = train_block(a.train_steps, 2)
+    if "train_step" in line and a.refresh_rows > 0:
+        try:
+            line["index_refresh"] = refresh_block(line["train_step"]["ms_per_step"])
+        except Exception as exc:
+            line["index_refresh"] = {"unavailable": (type(exc).__name__ + ": " + str(exc)).splitlines()[0][:300]}
     line["cpu_baseline"] = cpu_baseline(a) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     d.finish()
     return 0
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: keep a private handle on the real stdout and point
+    fd 1 at stderr for everything else (NCCL's version banner, library chatter, stray prints)."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     a = parse_args()
     if a.impl == "reference":
         return run_reference_arm(a)

@@ -210,6 +210,122 @@ class ShardReceiver(object):
         self.standby = 1 - self.standby
 
 
+# --------------------------------------------------------------- same GPUs, second stream (config 5)
+class ConcurrentShardRefresher(object):
+    """Index refresh CONCURRENT with training on the same GPUs (BASELINE config 5; the reference needs a second
+    set of 8 GPUs for it, README.md:113-115, async_indexer.py:116-144).
+
+    Every trainer rank re-encodes ITS OWN row range of the evidence — rows are independent, so the refresh shards
+    exactly like the index and nothing has to be sent anywhere: a worker thread drives the context
+    tower on a side CUDA stream (a private, frozen copy of the weights taken at `start`: the checkpoint the
+    reference's indexers load, :127-129) and writes the embeddings straight into a STANDBY shard buffer in this
+    GPU's HBM, while the training thread keeps stepping on the main stream and the live shard keeps serving
+    searches.  `maybe_swap()` is called by the training thread between two steps: the ranks agree (one tiny
+    all-reduce of ready flags — the NEW_INDEX_READY of the reference's protocol) that every standby is complete,
+    and only then do ALL of them swap, so a collective search never mixes old and new shards.  The retired
+    buffer becomes the next standby; writes to it are ordered after the searches that may still read it.
+
+    tower           the context tower (BertTower-like: tower(tokens, None, types, max_len=, row_lengths=) -> [b, d])
+    make_batches()  fresh iterable of (row_id int64 [b] — 1-based doc ids of rows in [row_lo, row_hi) —,
+                    tokens int64 [b, s], types int64 [b, s]) covering this rank's range (pinned host tensors)
+    partial=True    rows no batch covers are copied from the live shard (bounded benchmark runs)
+    """
+
+    def __init__(self, index, tower, make_batches, group=None, partial=False):
+        import copy
+        self.index, self.group, self.partial = index, group, partial
+        self.make_batches = make_batches
+        self.device = index.device
+        self.live_tower = tower
+        self.tower = copy.deepcopy(tower).eval()
+        for p in self.tower.parameters():
+            p.requires_grad_(False)
+        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self.standby = None
+        self._retired_free = None          # event: the retired buffer's last reader has been enqueued before it
+        self._thread = None
+        self._done = None
+        self.error = None
+        self.rows_done = 0
+        self.seconds = None
+        self.rounds = 0
+
+    def start(self):
+        """Snapshot the context-tower weights and start re-encoding on the side stream."""
+        import threading
+        if self._thread is not None and self._thread.is_alive():
+            raise RuntimeError("a refresh is already running")
+        n_local, d = self.index.evidence_embeds.shape
+        if self.standby is None:
+            self.standby = torch.empty((n_local, d), dtype=self.index.dtype, device=self.device)
+        self.rows_done, self.error, self.seconds = 0, None, None
+        fork = None
+        if self.stream is not None:
+            fork = torch.cuda.Event()
+            fork.record(torch.cuda.current_stream(self.device))      # weights as of this point of the training stream
+        self._thread = threading.Thread(target=self._run, args=(fork,), daemon=True)
+        self._thread.start()
+
+    def _run(self, fork):
+        import contextlib
+        import time as _time
+        try:
+            t0 = _time.perf_counter()
+            if self.stream is not None:
+                torch.cuda.set_device(self.device)                   # a new thread starts on device 0
+            ctx = torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+            with ctx, torch.no_grad():
+                if self.stream is not None:
+                    self.stream.wait_event(fork)
+                    if self._retired_free is not None:
+                        self.stream.wait_event(self._retired_free)
+                for dst, src in zip(self.tower.parameters(), self.live_tower.parameters()):
+                    dst.copy_(src)                                   # the "checkpoint" the indexer works from
+                if self.partial:
+                    self.standby.copy_(self.index.evidence_embeds)
+                lo = self.index.row_lo
+                takes_lengths = IndexBuilder._tower_takes_lengths(self.tower)
+                for row_id, tokens, types in self.make_batches():
+                    kw = {}
+                    if takes_lengths and not tokens.is_cuda:
+                        t = tokens.numpy()
+                        lens = ((t != 0) * np.arange(1, t.shape[1] + 1)).max(axis=1)
+                        kw = dict(max_len=int(lens.max()) if lens.size else 0, row_lengths=lens)
+                    emb = self.tower(tokens.to(self.device, non_blocking=True), None,
+                                     types.to(self.device, non_blocking=True), **kw)
+                    rows = torch.as_tensor(row_id, dtype=torch.int64).to(self.device, non_blocking=True) - 1 - lo
+                    self.standby.index_copy_(0, rows, emb.to(self.standby.dtype))
+                    self.rows_done += int(len(row_id))
+                if self.stream is not None:
+                    self._done = torch.cuda.Event()
+                    self._done.record(self.stream)
+                    self._done.synchronize()                         # this THREAD waits; the training thread does not
+            self.seconds = _time.perf_counter() - t0
+        except BaseException as exc:                                 # surfaced by ready() / maybe_swap()
+            self.error = exc
+
+    def ready(self):
+        if self.error is not None:
+            raise RuntimeError("index refresh failed") from self.error
+        return self._thread is not None and not self._thread.is_alive()
+
+    def maybe_swap(self):
+        """Training thread, between two steps.  True when every rank's standby was complete and all swapped."""
+        if self._thread is None:
+            return False
+        flag = torch.tensor([1.0 if self.ready() else 0.0], device=self.device)
+        if self.group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if float(flag.item()) < 1.0:
+            return False
+        self._thread.join()
+        self._thread = None
+        (old_ids, old_rows), free = self.index.swap_local_shard(self.index.local_ids, self.standby)
+        self.standby, self._retired_free = old_rows, free
+        self.rounds += 1
+        return True
+
+
 # ----------------------------------------------------------------------------------- indexer loop
 class AsyncIndexBuilder(IndexBuilder):
     """The indexer process (async_indexer.py:87-144): wait for the first checkpoint, then forever

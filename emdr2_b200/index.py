@@ -25,6 +25,8 @@ Ranking contract: fp32-accumulated score, ties by ascending row inside a shard a
 the cross-shard merge (include/emdr2_b200.h).  There is no CPU path: constructing an index on a
 machine without a CUDA device raises.
 """
+import threading
+
 import numpy as np
 import torch
 
@@ -91,6 +93,8 @@ class B200BruteForceIndex(object):
         self.row_lo = self.row_hi = 0
         self._searcher = None
         self._aux_searcher = None        # second handle for the row-range scans of k > 64
+        self._lock = threading.RLock()   # a search sees the shard before or after a swap, never between
+        self.generation = 0              # bumped by every shard (re)binding
         self._set_mips_index()
 
     # ------------------------------------------------------------------ construction / refresh
@@ -203,6 +207,37 @@ class B200BruteForceIndex(object):
         self.chunksize = -(-self.num_rows // self.world) if self.num_rows else 0
         self._searcher = self.searcher_factory(self.embed_size, self.dtype, self.device)
         self._searcher.set_shard(rows, ids, id_base=self.row_lo + 1)
+        self.generation += 1
+
+    def swap_local_shard(self, local_ids, local_rows):
+        """Index refresh without a rebuild: bind a new [n_local, d] shard of the SAME row range
+        (already resident on this device, e.g. the standby buffer an indexer stream has filled) and return the
+        retired (ids, rows) so the caller can reuse them as the next standby.  Atomic with respect to `search`
+        on other threads of this process; on a sharded index every rank must swap between the same two
+        collective searches (async_indexer.ConcurrentShardRefresher.maybe_swap agrees on that point).
+        Kernels already enqueued keep reading the retired buffer: order any writer after them (the returned
+        CUDA event, None on CPU doubles)."""
+        rows = local_rows
+        if rows.device != self.device or rows.dtype != self.dtype or not rows.is_contiguous():
+            raise ValueError("swap_local_shard takes a contiguous %s tensor on %s" % (self.dtype, self.device))
+        if rows.shape != self.evidence_embeds.shape:
+            raise ValueError("the new shard must cover the same row range (%s != %s)" % (
+                tuple(rows.shape), tuple(self.evidence_embeds.shape)))
+        ids = None if local_ids is None else torch.as_tensor(local_ids, dtype=torch.int64).to(self.device).contiguous()
+        with self._lock:
+            retired = (self.local_ids, self.evidence_embeds)
+            self._searcher.set_shard(rows, ids, id_base=self.row_lo + 1)
+            if self._aux_searcher is not None:
+                self._aux_searcher.close()
+                self._aux_searcher = None
+            self.evidence_embeds, self.local_ids = rows, ids
+            self.indices_arr = None
+            self.generation += 1
+            done = None
+            if self.device.type == "cuda":
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(self.device))
+        return retired, done
 
     # ------------------------------------------------------------------ search
     def search(self, query_embeds, top_k):
@@ -213,7 +248,8 @@ class B200BruteForceIndex(object):
         q = query_embeds.detach().to(device=self.device, dtype=self.dtype)
         if q.dim() != 2 or q.shape[1] != self.embed_size:
             raise ValueError("query_embeds must be [nq, %d]" % self.embed_size)
-        scores, ids = self._search_local(q, int(top_k))
+        with self._lock:
+            scores, ids = self._search_local(q, int(top_k))
         if self.world == 1:
             return scores, ids
         import torch.distributed as dist

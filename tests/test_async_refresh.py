@@ -206,3 +206,150 @@ def test_protocol_argument_checks():
         RefreshProtocol(0, 2, 0)
     with pytest.raises(ValueError):
         AsyncIndexBuilder(StubDual(), None, RefreshProtocol(1, 2, 1), mode="direct")
+
+
+# ------------------------------------------------ same devices, second stream (ConcurrentShardRefresher)
+class _ScaledTower(torch.nn.Module):
+    """Context tower stand-in: embedding = scale * onehot-ish function of the first token (exact arithmetic)."""
+
+    def __init__(self, dim, scale):
+        super().__init__()
+        self.scale = torch.nn.Parameter(torch.tensor([float(scale)]))
+        self.dim = dim
+
+    def forward(self, tokens, mask, types, max_len=None, row_lengths=None):
+        t = tokens[:, :1].float()
+        cols = torch.arange(1, self.dim + 1).float()[None]
+        return (((t * cols) % 17.0 - 8.0) / 8.0 * self.scale.detach()).to(torch.float16)
+
+
+def _refresh_setup(n, d, world=1, rank=0, group=None, delay=0.0):
+    from test_host_logic import CpuDoubleIndex
+    from emdr2_b200.async_indexer import ConcurrentShardRefresher
+    import time as _time
+    tower = _ScaledTower(d, 1.0)
+    doc_ids = np.arange(1, n + 1, dtype=np.int64)
+    old_rows = tower(torch.from_numpy(doc_ids)[:, None], None, None).numpy()
+    index = CpuDoubleIndex(d, device="cpu", group=group)
+    index.add_arrays(doc_ids, old_rows)
+    lo, hi = index.row_lo, index.row_hi
+
+    def make_batches():
+        for a in range(lo, hi, 7):
+            ids = doc_ids[a:min(hi, a + 7)]
+            if delay:
+                _time.sleep(delay)
+            yield torch.from_numpy(ids), torch.from_numpy(ids)[:, None].repeat(1, 4), torch.zeros(len(ids), 4, dtype=torch.int64)
+
+    refresher = ConcurrentShardRefresher(index, tower, make_batches, group=group)
+    return index, tower, refresher, doc_ids, old_rows
+
+
+def test_concurrent_refresh_swaps_whole_shards_and_searches_never_see_a_mix():
+    """c5 on one process: the refresher thread re-encodes the shard with the tower's CURRENT weights into a standby
+    buffer while another thread keeps searching; every search result equals the old index's answer or the new
+    one's, never a blend, and after the swap the index serves exactly the new embeddings."""
+    import threading
+    from oracle import mips as oracle
+    n, d, k = 400, 16, 9
+    index, tower, refresher, doc_ids, old_rows = _refresh_setup(n, d, delay=0.002)
+    queries = torch.from_numpy((np.random.RandomState(3).randint(-8, 9, size=(5, d)) / 8).astype(np.float16))
+    with torch.no_grad():
+        tower.scale.fill_(-1.0)                               # "training" moved the weights: new rows = -old rows
+    new_rows = (-old_rows.astype(np.float32)).astype(np.float16)
+    want_old = oracle.mips_topk(old_rows, queries.numpy(), k, ids=doc_ids)
+    want_new = oracle.mips_topk(new_rows, queries.numpy(), k, ids=doc_ids)
+    assert not np.array_equal(want_old[1], want_new[1])
+    seen, stop = [], threading.Event()
+
+    def hammer():
+        while not stop.is_set():
+            s, i = index.search(queries, k)
+            seen.append((s.numpy().copy(), i.numpy().copy(), index.generation))
+
+    th = threading.Thread(target=hammer)
+    th.start()
+    refresher.start()
+    with torch.no_grad():
+        tower.scale.fill_(5.0)                                # later training steps must not leak into this refresh
+    swapped = False
+    for _ in range(2000):
+        if refresher.maybe_swap():
+            swapped = True
+            break
+        import time as _time
+        _time.sleep(0.005)
+    for _ in range(20):
+        index.search(queries, k)
+    stop.set()
+    th.join()
+    assert swapped and refresher.rounds == 1 and refresher.rows_done == n
+    olds = news = 0
+    for s, i, _gen in seen:
+        if np.array_equal(i, want_old[1]) and np.array_equal(s, want_old[0]):
+            olds += 1
+        elif np.array_equal(i, want_new[1]) and np.array_equal(s, want_new[0]):
+            news += 1
+        else:
+            raise AssertionError("a search saw a mixture of the old and the new shard")
+    assert olds > 0 and news > 0
+    s, i = index.search(queries, k)
+    assert np.array_equal(i.numpy(), want_new[1]) and np.array_equal(s.numpy(), want_new[0])
+    # second round reuses the retired buffer as the standby
+    retired = refresher.standby
+    assert np.array_equal(retired.numpy(), old_rows)
+    refresher.start()
+    while not refresher.maybe_swap():
+        pass
+    assert refresher.rounds == 2 and refresher.standby is not retired
+
+
+def _worker_concurrent(rank, world, port, out_dir):
+    import torch.distributed as dist
+    import time as _time
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    n, d, k = 300, 16, 7
+    # rank 1 re-encodes more slowly: rank 0 must NOT swap before rank 1 is ready too
+    index, tower, refresher, doc_ids, old_rows = _refresh_setup(n, d, world, rank, dist.group.WORLD,
+                                                                delay=0.001 if rank == 0 else 0.01)
+    queries = torch.from_numpy((np.random.RandomState(3).randint(-8, 9, size=(4, d)) / 8).astype(np.float16))
+    with torch.no_grad():
+        tower.scale.fill_(-1.0)
+    refresher.start()
+    results, swaps_at = [], None
+    for step in range(400):
+        s, i = index.search(queries, k)                       # collective: both ranks, same step
+        results.append(i.numpy().copy())
+        if refresher.maybe_swap():
+            swaps_at = step
+            break
+        _time.sleep(0.002)
+    s, i = index.search(queries, k)
+    np.savez(os.path.join(out_dir, "c%d.npz" % rank), results=np.stack(results), final=i.numpy(), swaps_at=swaps_at,
+             finals=s.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_concurrent_refresh_world2_all_ranks_swap_between_the_same_two_searches(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import mips as oracle
+    for attempt in range(2):
+        try:
+            mp.spawn(_worker_concurrent, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+            break
+        except Exception:
+            if attempt:
+                raise
+    n, d, k = 300, 16, 7
+    doc_ids = np.arange(1, n + 1, dtype=np.int64)
+    old_rows = _ScaledTower(d, 1.0)(torch.from_numpy(doc_ids)[:, None], None, None).numpy()
+    queries = (np.random.RandomState(3).randint(-8, 9, size=(4, d)) / 8).astype(np.float16)
+    want_old = oracle.mips_topk(old_rows, queries, k, ids=doc_ids)[1]
+    want_new = oracle.mips_topk((-old_rows.astype(np.float32)).astype(np.float16), queries, k, ids=doc_ids)[1]
+    r0, r1 = (np.load(str(tmp_path / ("c%d.npz" % r)), allow_pickle=True) for r in range(2))
+    assert int(r0["swaps_at"]) == int(r1["swaps_at"])        # agreed swap point
+    assert np.array_equal(r0["results"], r1["results"])      # both ranks saw the same merged answers throughout
+    for res in r0["results"]:
+        assert np.array_equal(res, want_old)                  # ... and all of them came from the OLD index
+    assert np.array_equal(r0["final"], want_new) and np.array_equal(r1["final"], want_new)

@@ -136,3 +136,70 @@ def test_index_refresh_from_the_flat_store_on_the_gpu(tmp_path):
     assert np.array_equal(i1.cpu().numpy(), w1[1]) and np.array_equal(s1.cpu().numpy(), w1[0])
     index.reset_index()
     assert torch.equal(index.search(torch.from_numpy(queries).to(DEV), 20)[1], i1)
+
+
+def test_concurrent_index_refresh_on_the_gpu_searches_see_old_or_new_never_a_mix():
+    """BASELINE config 5 on one GPU (async_indexer.ConcurrentShardRefresher): a worker thread re-encodes the shard
+    with a frozen copy of a real (tiny) context tower on a side CUDA stream into a standby buffer while this
+    thread keeps searching the live shard through the scan kernel; every answer equals the OLD index's or — after
+    the swap — the NEW index's, and the new shard holds exactly the frozen tower's embeddings."""
+    import threading
+    from emdr2_b200.async_indexer import ConcurrentShardRefresher
+    from emdr2_b200.blocks import BertTower
+    from emdr2_b200.index import B200BruteForceIndex
+    dtype = torch.float16
+    tower = BertTower(dict(TINY, dtype=dtype)).to(DEV).eval()
+    with torch.no_grad():
+        for name, p in tower.named_parameters():
+            p.copy_(seeded_weights(name, tuple(p.shape)).to(dtype))
+    n, d, k, s = 1536, TINY["hidden"], 10, 32
+    rng = np.random.RandomState(6)
+    tokens = rng.randint(1, TINY["vocab"], size=(n, s)).astype(np.int64)
+    for i, ln in enumerate(rng.randint(5, s + 1, size=n)):
+        tokens[i, ln:] = 0
+    tok_t = torch.from_numpy(tokens)
+
+    def encode(model):
+        with torch.no_grad():
+            return torch.cat([model(tok_t[a:a + 128].to(DEV), None, torch.zeros(128, s, dtype=torch.int64, device=DEV))
+                              for a in range(0, n, 128)]).to(dtype)
+
+    old_rows = encode(tower)
+    index = B200BruteForceIndex(d, device=DEV)
+    index.add_local_shard(None, old_rows.clone(), num_rows=n, row_lo=0)
+    queries = torch.randn(6, d, generator=torch.Generator().manual_seed(1)).to(dtype).to(DEV)
+    want_old = index.search(queries, k)
+    with torch.no_grad():                                     # "training" changes the context tower
+        for p in tower.parameters():
+            p.mul_(0.9)
+
+    def make_batches():
+        for a in range(0, n, 128):
+            yield (torch.arange(a + 1, a + 129), tok_t[a:a + 128].pin_memory(),
+                   torch.zeros(128, s, dtype=torch.int64).pin_memory())
+
+    refresher = ConcurrentShardRefresher(index, tower, make_batches)
+    refresher.start()
+    with torch.no_grad():                                     # later steps: must not leak into the running refresh
+        for p in tower.parameters():
+            p.mul_(0.5)
+    seen = []
+    swapped = False
+    for _ in range(20000):
+        sc, ids = index.search(queries, k)
+        seen.append((sc.clone(), ids.clone()))
+        if refresher.maybe_swap():
+            swapped = True
+            break
+    assert swapped and refresher.rows_done == n
+    new_rows = encode(refresher.tower)
+    assert torch.equal(index.evidence_embeds, new_rows)       # the frozen snapshot (x0.9), not the live weights (x0.45)
+    assert not torch.equal(new_rows, old_rows)
+    want_new = index.search(queries, k)
+    fresh = B200BruteForceIndex(d, device=DEV)
+    fresh.add_local_shard(None, new_rows.clone(), num_rows=n, row_lo=0)
+    check = fresh.search(queries, k)
+    assert torch.equal(want_new[1], check[1]) and torch.equal(want_new[0], check[0])
+    for sc, ids in seen:                                      # everything before the swap came from the old shard
+        assert torch.equal(ids, want_old[1]) and torch.equal(sc, want_old[0])
+    assert len(seen) >= 1
