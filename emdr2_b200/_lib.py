@@ -95,6 +95,16 @@ _SIGNATURES = {
                                                   ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_void_p]),
+    "emdr2_attention_varlen_fwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
+                                                  ctypes.c_void_p, ctypes.c_void_p]),
+    "emdr2_embedding_fwd_pos": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                               ctypes.c_void_p]),
     "emdr2_dropout_colhash": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "emdr2_dropout_mask": (ctypes.c_int, [ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
@@ -118,6 +128,7 @@ _SIGNATURES = {
     "emdr2_ops_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "emdr2_ops_get_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)]),
     "emdr2_ops_timing": (ctypes.c_int, [ctypes.c_int]),
+    "emdr2_ops_timing_add_flops": (ctypes.c_int, [ctypes.c_int, ctypes.c_double]),
     "emdr2_ops_timing_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
                                              ctypes.POINTER(ctypes.c_int64),
                                              ctypes.POINTER(ctypes.c_double)]),

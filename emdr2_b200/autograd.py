@@ -380,6 +380,27 @@ def cross_attention(q, kv, batch, heads, sq, sk, q_pad=None, k_pad=None, q_live=
                          q_live=q_live, k_live=k_live)
 
 
+def cross_attention_packed(q, kv, heads, plan, scale=0.125):
+    """FiD cross-attention over TOKEN-PACKED encoder states (no-grad forward path): q [n_sets * sq, h], kv [T, 2h]
+    = the key/value projection of the packed states, plan = packed.CrossPlan.  Every key set is cut into ranges
+    that run as separate work items of one varlen launch; the partial outputs are merged with their
+    log-sum-exp weights (an absent range weighs exp(-inf) = 0)."""
+    h = heads * 64
+    sq, n_slots = plan.sq, plan.n_slots
+    part = torch.zeros(((n_slots + 1) * sq, h), dtype=q.dtype, device=q.device)
+    lse = torch.full(((n_slots + 1) * heads * sq,), float("-inf"), dtype=torch.float32, device=q.device)
+    ops.attention_varlen(q, kv[:, :h], kv[:, h:], heads, plan.items, plan.n_items, scale=scale, out=part, lse=lse,
+                         flops=plan.attention_flops)
+    if plan.max_chunks == 1 and n_slots == plan.n_sets:
+        return part[:n_slots * sq]
+    idx = plan.slot_index.reshape(-1).long()
+    w = torch.softmax(lse.view(n_slots + 1, heads, sq).index_select(0, idx)
+                      .view(plan.n_sets, plan.max_chunks, heads, sq), dim=1)                    # [sets, chunks, heads, sq]
+    o = part.view(n_slots + 1, sq, heads, 64).index_select(0, idx).view(plan.n_sets, plan.max_chunks, sq, heads, 64)
+    merged = (o.float() * w.permute(0, 1, 3, 2).unsqueeze(-1)).sum(dim=1)
+    return merged.to(q.dtype).view(plan.n_sets * sq, h)
+
+
 # ------------------------------------------------------------------------------------ embedding
 class _EmbeddingFn(torch.autograd.Function):
     @staticmethod

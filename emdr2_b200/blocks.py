@@ -117,9 +117,20 @@ class ParallelAttention(nn.Module):
         self.scale = 1.0 / math.sqrt(hidden // heads)
 
     def forward(self, x, batch, sq, q_pad, residual, causal=False, encoder_output=None, sk=None,
-                k_pad=None, q_live=None, k_live=None, groups=None):
+                k_pad=None, q_live=None, k_live=None, groups=None, packed=None, cross_plan=None, cross_kv=None):
         p_attn = self.attention_dropout if self.training else 0.0
         p_hidden = self.hidden_dropout if self.training else 0.0
+        if packed is not None:          # token-packed sequences, one varlen launch (no-grad forward path)
+            qkv = self.query_key_value(x)
+            h = self.hidden
+            ctx = ops.attention_varlen(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], self.heads, packed.items,
+                                       packed.n_items, scale=self.scale, flops=packed.attention_flops)
+            return self.dense(ctx, residual=residual)
+        if cross_plan is not None:      # FiD cross-attention over token-packed encoder states
+            q = self.query(x)
+            kv = cross_kv if cross_kv is not None else self.key_value(encoder_output)
+            ctx = ag.cross_attention_packed(q, kv, self.heads, cross_plan, scale=self.scale)
+            return self.dense(ctx, residual=residual)
         if self.attention_type == "self":
             qkv = self.query_key_value(x)
             if groups is not None:      # token-packed rows of several [batch_g, seq_g] rectangles
@@ -167,13 +178,14 @@ class ParallelTransformerLayer(nn.Module):
         self.mlp = ParallelMLP(hidden, ffn, dtype, hidden_dropout=hidden_dropout)
 
     def forward(self, x, batch, seq, pad, causal=False, encoder_output=None, enc_seq=None, enc_pad=None,
-                q_live=None, enc_live=None, groups=None):
+                q_live=None, enc_live=None, groups=None, packed=None, cross_plan=None):
         x = self.self_attention(self.input_layernorm(x), batch, seq, pad, residual=x, causal=causal,
-                                q_live=q_live, groups=groups)
+                                q_live=q_live, groups=groups, packed=packed)
         ln = self.post_attention_layernorm(x)
         if self.layer_type == "decoder":
             x = self.inter_attention(ln, batch, seq, pad, residual=x, encoder_output=encoder_output,
-                                     sk=enc_seq, k_pad=enc_pad, q_live=q_live, k_live=enc_live)
+                                     sk=enc_seq, k_pad=enc_pad, q_live=q_live, k_live=enc_live,
+                                     cross_plan=cross_plan)
             ln = self.post_inter_attention_layernorm(x)
         return self.mlp(ln, residual=x)
 
@@ -207,8 +219,11 @@ class Embedding(nn.Module):
         self.tokentype_embeddings = _Table(num_tokentypes, hidden, dtype) if num_tokentypes > 0 else None
         self.hidden_dropout = float(hidden_dropout)
 
-    def forward(self, input_ids, tokentype_ids=None):
+    def forward(self, input_ids, tokentype_ids=None, pos_ids=None):
         typ = self.tokentype_embeddings.weight if tokentype_ids is not None else None
+        if pos_ids is not None:         # token-packed sequences (no-grad forward path): explicit positions
+            return ops.embedding(input_ids, self.word_embeddings.weight, self.position_embeddings.weight,
+                                 tokentype_ids, typ, seq=input_ids.numel(), pos_ids=pos_ids)
         x = ag.embedding(input_ids, self.word_embeddings.weight, self.position_embeddings.weight,
                          tokentype_ids, typ)
         if self.training and self.hidden_dropout:          # embedding_dropout (language_model.py:181)
@@ -286,6 +301,8 @@ class TransformerLanguageModel(nn.Module):
         slice.  Cut columns are padding in every member of the group, so non-padding positions are
         unchanged; the cut columns of the returned states are zero (no consumer reads padding
         positions: the decoder masks them through the ids)."""
+        if self._use_packed(ids, row_lengths):
+            return self._encode_packed(ids, tokentype_ids, row_lengths, cls_only)
         s_keep = self.trimmed_width(ids.shape[1], max_len)
         if s_keep != ids.shape[1]:
             ids = ids[:, :s_keep].contiguous()
@@ -300,6 +317,46 @@ class TransformerLanguageModel(nn.Module):
         q_live = ops.live_blocks(pad) if self.skip_padding else None
         y = self.encoder(x, b, s, pad, q_live=q_live).view(b, s, self.hidden)
         return y[:, 0, :] if cls_only else y
+
+    #: Token-packed (variable-length) execution of the no-grad forward path (emdr2_b200/packed.py): applies when
+    #: the caller hands over per-row lengths and no gradient is being recorded.
+    packed_varlen = True
+    packed_min_rows = 2
+
+    def _use_packed(self, ids, row_lengths):
+        return (self.packed_varlen and row_lengths is not None and ids.shape[0] >= self.packed_min_rows
+                and not torch.is_grad_enabled() and not self.training)
+
+    def _encode_packed(self, ids, tokentype_ids, row_lengths, cls_only):
+        """Encoder over the b sequences laid back to back: [T, h] activations, T = sum of the lengths.  Returns the
+        position-0 states [b, h] (cls_only) or a packed.PackedStates."""
+        from .packed import PackedBatch, PackedStates
+        b, s = ids.shape
+        heads = self.encoder.layers[0].self_attention.heads
+        pb = PackedBatch(row_lengths, s, heads, ids.device)
+        flat_ids = ids.reshape(-1).index_select(0, pb.gather)
+        flat_types = tokentype_ids.reshape(-1).index_select(0, pb.gather) if tokentype_ids is not None else None
+        x = self.embedding(flat_ids, flat_types, pos_ids=pb.pos_ids)
+        y = self.encoder(x, None, None, None, packed=pb)                       # [T, h]
+        if cls_only:
+            return y.index_select(0, pb.first_rows)
+        return PackedStates(y, pb.lens, pb.cu)
+
+    def decode_packed(self, dec_ids, states, group):
+        """Decoder over token-packed encoder states (packed.PackedStates): question q attends the `group`
+        consecutive sequences [q*group, (q+1)*group) — the FiD concatenation (emdr2_model.py:159-164) without the
+        padding.  Decoder self-attention keeps the rectangular kernel (b x L is tiny)."""
+        b, sq = dec_ids.shape
+        heads = self.decoder.layers[0].self_attention.heads
+        plan = states.cross_plan(group, sq, heads)
+        if plan.n_sets != b:
+            raise ValueError("%d key sets for %d decoder rows" % (plan.n_sets, b))
+        x = self.embedding(dec_ids)
+        dec_pad = dec_ids < 1
+        q_live = ops.live_blocks(dec_pad) if self.skip_padding else None
+        y = self.decoder(x, b, sq, dec_pad, causal=True, encoder_output=states.states, q_live=q_live,
+                         cross_plan=plan)
+        return y.view(b, sq, self.hidden)
 
     def _encode_bucketed(self, ids, tokentype_ids, plan, cls_only):
         import numpy as np
@@ -339,7 +396,11 @@ class TransformerLanguageModel(nn.Module):
         LayerNorm rows are independent, a query's softmax runs over the same keys in the same order — but
         each token passes through the stack once and the encoder states are projected once per layer."""
         rows, t_total = dec_ids.shape
-        b, sk = enc_states.shape[0], enc_states.shape[1]
+        packed_states = enc_states if hasattr(enc_states, "cross_plan") else None
+        if packed_states is not None:
+            b, sk = len(packed_states.lens) // cache.group, None
+        else:
+            b, sk = enc_states.shape[0], enc_states.shape[1]
         if rows % b:
             raise ValueError("decoder rows (%d) must be a multiple of the question batch (%d)" % (rows, b))
         r = rows // b
@@ -352,10 +413,11 @@ class TransformerLanguageModel(nn.Module):
         h, heads, dev = self.hidden, self.decoder.layers[0].self_attention.heads, dec_ids.device
         dtype = self.embedding.word_embeddings.weight.dtype
         if cache.cross_kv is None:
-            enc2d = enc_states.reshape(b * sk, h)
+            enc2d = packed_states.states if packed_states is not None else enc_states.reshape(b * sk, h)
             cache.cross_kv = [layer.inter_attention.key_value(enc2d) for layer in self.decoder.layers]
-            cache.enc_pad = enc_pad.to(torch.uint8).contiguous()
-            cache.enc_live = ops.live_blocks(enc_pad) if self.skip_padding else None
+            if packed_states is None:
+                cache.enc_pad = enc_pad.to(torch.uint8).contiguous()
+                cache.enc_live = ops.live_blocks(enc_pad) if self.skip_padding else None
         if cache.self_kv is None or cache.self_kv[0].shape[0] != rows:
             if cache.self_kv is not None:
                 raise ValueError("hypothesis rows changed without DecoderCache.reorder")
@@ -377,8 +439,13 @@ class TransformerLanguageModel(nn.Module):
             ln = layer.post_attention_layernorm(x)
             cross = layer.inter_attention
             q = cross.query(ln)                                                     # [b * (r*n_new), h]
-            ctx = ag.cross_attention(q, cache.cross_kv[li], b, heads, r * n_new, sk, k_pad=cache.enc_pad,
-                                     k_live=cache.enc_live, scale=cross.scale)
+            if packed_states is not None:
+                ctx = ag.cross_attention_packed(q, cache.cross_kv[li], heads,
+                                                packed_states.cross_plan(cache.group, r * n_new, heads),
+                                                scale=cross.scale)
+            else:
+                ctx = ag.cross_attention(q, cache.cross_kv[li], b, heads, r * n_new, sk, k_pad=cache.enc_pad,
+                                         k_live=cache.enc_live, scale=cross.scale)
             x = cross.dense(ctx, residual=x)
             x = layer.mlp(layer.post_inter_attention_layernorm(x), residual=x)
         cache.t = t_total
@@ -408,8 +475,9 @@ class DecoderCache(object):
     t            tokens consumed; rows = b * r hypotheses (r = 1 greedy, beam size in beam search; the r
                  hypotheses of a question are consecutive rows and share its encoder states)."""
 
-    def __init__(self, max_len):
+    def __init__(self, max_len, group=1):
         self.max_len = int(max_len)
+        self.group = int(group)          # sequences per key set when the encoder states are token-packed (FiD top-k)
         self.cross_kv = None
         self.self_kv = None
         self.enc_pad = self.enc_live = None
@@ -478,19 +546,30 @@ class T5Reader(nn.Module):
     def forward(self, encoder_input_ids, decoder_input_ids, encoder_attn_mask=None,
                 decoder_attn_mask=None, encoder_decoder_attn_mask=None, tokentype_ids=None,
                 lm_labels=None, enc_hidden_states=None, output_enc_hidden=False,
-                enc_ids_for_mask=None, enc_max_len=None, enc_row_lengths=None, decoder_cache=None):
+                enc_ids_for_mask=None, enc_max_len=None, enc_row_lengths=None, decoder_cache=None, fid_group=None):
         _require_cuda(encoder_input_ids)
         lm = self.language_model
         if enc_hidden_states is None:
-            # enc_max_len (opt-in): encoder states come back as [b, s', h] with s' = roundup(max_len, 64)
+            # enc_max_len (opt-in): encoder states come back as [b, s', h] with s' = roundup(max_len, 64); with
+            # per-row lengths and no gradient they come back token-packed (packed.PackedStates)
             enc = lm.encode(encoder_input_ids, tokentype_ids, max_len=enc_max_len, row_lengths=enc_row_lengths)
-            mask_ids = encoder_input_ids[:, :enc.shape[1]]
+            mask_ids = None if hasattr(enc, "cross_plan") else encoder_input_ids[:, :enc.shape[1]]
+        elif hasattr(enc_hidden_states, "cross_plan"):
+            enc, mask_ids = enc_hidden_states, None
         else:
             enc = enc_hidden_states.to(lm.embedding.word_embeddings.weight.dtype)
             mask_ids = enc_ids_for_mask if enc_ids_for_mask is not None else encoder_input_ids
         if output_enc_hidden:
             return enc
-        if decoder_cache is not None:          # evaluation decode loop: only the not-yet-decoded positions
+        if mask_ids is None:                   # token-packed encoder states: `fid_group` sequences per question
+            group = len(enc.lens) // decoder_input_ids.shape[0] if fid_group is None else fid_group
+            if decoder_cache is not None:
+                decoder_cache.group = group
+                with torch.no_grad():
+                    dec = lm.decode_incremental(decoder_input_ids, enc, None, decoder_cache)
+            else:
+                dec = lm.decode_packed(decoder_input_ids, enc, group)
+        elif decoder_cache is not None:        # evaluation decode loop: only the not-yet-decoded positions
             with torch.no_grad():
                 dec = lm.decode_incremental(decoder_input_ids, enc, mask_ids < 1, decoder_cache)
         else:

@@ -78,6 +78,34 @@ struct AttnBwdArgs {
   DropoutArgs drop;        // the forward's dropout, regenerated: dP = keep / (1 - p) * (dO . V^T)
 };
 
+// ---- variable-length forward over token-packed activations (attention_varlen.cu)
+struct AttnVarlenItem {      // 32 bytes, read as two int4
+  int32_t q_row0;            // first row of the 128-query tile in the packed Q matrix
+  int32_t q_valid;           // rows of the tile that belong to the sequence (1..128)
+  int32_t k_row0;            // first row of the item's key range in the packed K / V matrices
+  int32_t k_len;             // keys in the range (>= 1)
+  int32_t head;
+  int32_t o_row0;            // output row of the tile's first query
+  int32_t lse_idx0;          // index of the first query's entry in the lse buffer
+  int32_t reserved;
+};
+static_assert(sizeof(AttnVarlenItem) == 32, "work items are read as two int4");
+
+struct AttnVarlenArgs {
+  const AttnVarlenItem* items;   // device, sorted by decreasing cost; dealt round-robin to the CTAs
+  uint32_t n_items;
+  uint32_t idesc_s, idesc_o;
+  float scale_log2;
+  void* out;                     // packed output matrix (row-wise stores of partial tiles)
+  int64_t ldo;
+  float* lse;                    // optional
+};
+
+cudaError_t attention_varlen_prepare();
+void launch_attention_varlen(const CUtensorMap& tmap_q, const CUtensorMap& tmap_k, const CUtensorMap& tmap_v,
+                             const CUtensorMap& tmap_o, const AttnVarlenArgs& args, bool bf16, int sm_count,
+                             cudaStream_t stream);
+
 cudaError_t attention_bwd_prepare();
 cudaError_t launch_attention_bwd_prep(bool bf16, const void* dout, int64_t lddo, const void* out, int64_t ldo,
                                       float* dvec, int batch, int heads, int sq, cudaStream_t stream);

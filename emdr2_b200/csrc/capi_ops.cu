@@ -321,6 +321,14 @@ int emdr2_layernorm_fwd(int dtype, const void* x, int64_t ldx, const void* gamma
 int emdr2_embedding_fwd(int dtype, const int64_t* ids, const int64_t* types, const void* word,
                         const void* pos, const void* type_emb, void* out, int tokens, int seq, int h,
                         int vocab, int num_types, void* cuda_stream) {
+  return emdr2_embedding_fwd_pos(dtype, ids, types, word, pos, type_emb, out, tokens, seq, h, vocab, num_types,
+                                 nullptr, seq, cuda_stream);
+}
+
+int emdr2_embedding_fwd_pos(int dtype, const int64_t* ids, const int64_t* types, const void* word,
+                            const void* pos, const void* type_emb, void* out, int tokens, int seq, int h,
+                            int vocab, int num_types, const int32_t* pos_ids, int max_pos, void* cuda_stream) {
+  if (pos_ids && max_pos < 1) return fail(EMDR2_EINVAL, "explicit positions need the position table's row count");
   if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
     return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
   if (tokens < 0 || seq < 1 || h < 8 || (h % 8) || vocab < 1)
@@ -337,7 +345,7 @@ int emdr2_embedding_fwd(int dtype, const int64_t* ids, const int64_t* types, con
   ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
   CUDA_TRY(emdr2::launch_embedding_fwd(dtype == EMDR2_DTYPE_BF16, ids, types, word, pos, type_emb, out,
                                        tokens, seq, h, vocab, num_types,
-                                       static_cast<cudaStream_t>(cuda_stream)));
+                                       static_cast<cudaStream_t>(cuda_stream), pos_ids, max_pos));
   return EMDR2_OK;
 }
 
@@ -367,6 +375,14 @@ int emdr2_ops_timing(int enable) {
     g_timers[k].used = 0;
     g_timers[k].flops = 0.0;
   }
+  return EMDR2_OK;
+}
+
+int emdr2_ops_timing_add_flops(int kind, double flops) {
+  if (kind < 0 || kind >= EMDR2_KIND_COUNT) return fail(EMDR2_EINVAL, "unknown kernel kind %d", kind);
+  if (!g_timing.load(std::memory_order_relaxed)) return EMDR2_OK;
+  std::lock_guard<std::mutex> guard(g_timer_mutex);
+  g_timers[kind].flops += flops;
   return EMDR2_OK;
 }
 
@@ -578,6 +594,55 @@ int emdr2_dropout_add(int dtype, const void* y, int64_t ldy, const void* residua
   CUDA_TRY(emdr2::launch_dropout_add(dtype == EMDR2_DTYPE_BF16, y, ldy, residual, ldr, out, ldo, rows, cols,
                                      emdr2::make_dropout_args(p, seed, offset, colhash),
                                      static_cast<cudaStream_t>(cuda_stream)));
+  return EMDR2_OK;
+}
+
+int emdr2_attention_varlen_fwd(int dtype, const void* q, int64_t ldq, int64_t q_rows, const void* k, int64_t ldk,
+                               const void* v, int64_t ldv, int64_t k_rows, void* o, int64_t ldo, int64_t o_rows,
+                               int heads, const int32_t* dev_items, int n_items, float scale, float* lse,
+                               void* cuda_stream) {
+  if (dtype != EMDR2_DTYPE_FP16 && dtype != EMDR2_DTYPE_BF16)
+    return fail(EMDR2_EINVAL, "dtype %d is not EMDR2_DTYPE_FP16/BF16", dtype);
+  if (heads < 1 || n_items < 0 || q_rows < 0 || k_rows < 0 || o_rows < 0)
+    return fail(EMDR2_EINVAL, "bad varlen attention shape heads=%d items=%d", heads, n_items);
+  if (n_items == 0) return EMDR2_OK;
+  if (q_rows == 0 || k_rows == 0 || o_rows == 0) return fail(EMDR2_EINVAL, "work items over empty matrices");
+  if (q_rows > 0x7fffffff || k_rows > 0x7fffffff || o_rows > 0x7fffffff)
+    return fail(EMDR2_EINVAL, "packed matrices are limited to 2^31 - 1 rows");
+  if (!q || !k || !v || !o || !dev_items) return fail(EMDR2_EINVAL, "NULL pointer passed to emdr2_attention_varlen_fwd");
+  if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) || !aligned16(dev_items))
+    return fail(EMDR2_EINVAL, "q/k/v/o and the item list must be 16-byte aligned");
+  const int64_t width = static_cast<int64_t>(heads) * emdr2::kAttnHeadDim;
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || ldq < width || ldk < width || ldv < width || ldo < width)
+    return fail(EMDR2_EINVAL, "row pitches must be multiples of 8 and >= heads*64 = %lld", static_cast<long long>(width));
+  DeviceInfo info;
+  int rc = require_b200(&info);
+  if (rc != EMDR2_OK) return rc;
+  static bool prepared[64] = {};
+  if (!prepared[info.device]) {
+    CUDA_TRY(emdr2::attention_varlen_prepare());
+    prepared[info.device] = true;
+  }
+  CUtensorMap tq, tk, tv, to;
+  if ((rc = make_tmap_2d(&tq, dtype, q, q_rows, width, ldq, emdr2::kAttnBQ)) != EMDR2_OK) return rc;
+  if ((rc = make_tmap_2d(&tk, dtype, k, k_rows, width, ldk, emdr2::kAttnBK)) != EMDR2_OK) return rc;
+  if ((rc = make_tmap_2d(&tv, dtype, v, k_rows, width, ldv, emdr2::kAttnBK)) != EMDR2_OK) return rc;
+  if ((rc = make_tmap_2d(&to, dtype, o, o_rows, width, ldo, emdr2::kAttnBQ)) != EMDR2_OK) return rc;
+  emdr2::AttnVarlenArgs aa;
+  aa.items = reinterpret_cast<const emdr2::AttnVarlenItem*>(dev_items);
+  aa.n_items = static_cast<uint32_t>(n_items);
+  const int fmt = dtype == EMDR2_DTYPE_BF16 ? 1 : 0;
+  aa.idesc_s = emdr2::ptx::instr_desc_f16(fmt, emdr2::kAttnBQ, emdr2::kAttnBK);
+  aa.idesc_o = emdr2::ptx::instr_desc_f16(fmt, emdr2::kAttnBQ, emdr2::kAttnHeadDim, 0, 1);
+  aa.scale_log2 = scale * 1.4426950408889634f;
+  aa.out = o;
+  aa.ldo = ldo;
+  aa.lse = lse;
+  // algorithmic work is not known here without reading the items back: callers that time this kind pass
+  // through emdr2_ops_timing and account flops themselves; count the launch with zero flops
+  ScopedTimer timer(EMDR2_KIND_ATTENTION, static_cast<cudaStream_t>(cuda_stream), 0.0);
+  emdr2::launch_attention_varlen(tq, tk, tv, to, aa, fmt == 1, info.sm_count, static_cast<cudaStream_t>(cuda_stream));
+  CUDA_TRY(cudaGetLastError());
   return EMDR2_OK;
 }
 

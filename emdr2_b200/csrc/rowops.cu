@@ -102,14 +102,16 @@ __global__ void __launch_bounds__(256)
 embedding_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ types,
                      const uint16_t* __restrict__ word, const uint16_t* __restrict__ pos,
                      const uint16_t* __restrict__ type_emb, uint16_t* __restrict__ out, int tokens,
-                     int seq, int h, int vocab, int num_types) {
+                     int seq, int h, int vocab, int num_types, const int32_t* __restrict__ pos_ids, int max_pos) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= tokens) return;
   int64_t id = ids[t];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);   // clamp: never read outside the table
   const uint16_t* wr = word + static_cast<size_t>(id) * h;
-  const uint16_t* pr = pos + static_cast<size_t>(t % seq) * h;
+  int p = pos_ids ? pos_ids[t] : t % seq;             // packed sequences carry their positions explicitly
+  p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
+  const uint16_t* pr = pos + static_cast<size_t>(p) * h;
   const uint16_t* tr = nullptr;
   if (types && type_emb) {
     int64_t ty = types[t];
@@ -241,9 +243,10 @@ cudaError_t launch_layernorm_fwd(bool bf16, const void* x, int64_t ldx, const vo
 cudaError_t launch_embedding_fwd(bool bf16, const int64_t* ids, const int64_t* types,
                                  const void* word, const void* pos, const void* type_emb, void* out,
                                  int tokens, int seq, int h, int vocab, int num_types,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, const int32_t* pos_ids, int max_pos) {
   if (tokens <= 0) return cudaSuccess;
   if (h % 8) return cudaErrorInvalidValue;
+  if (max_pos <= 0) max_pos = seq;
   const int warps = 8;
   const int grid = (tokens + warps - 1) / warps;
   auto ws = static_cast<const uint16_t*>(word);
@@ -251,9 +254,9 @@ cudaError_t launch_embedding_fwd(bool bf16, const int64_t* ids, const int64_t* t
   auto ts = static_cast<const uint16_t*>(type_emb);
   auto os = static_cast<uint16_t*>(out);
   if (bf16)
-    embedding_fwd_kernel<true><<<grid, warps * 32, 0, stream>>>(ids, types, ws, ps, ts, os, tokens, seq, h, vocab, num_types);
+    embedding_fwd_kernel<true><<<grid, warps * 32, 0, stream>>>(ids, types, ws, ps, ts, os, tokens, seq, h, vocab, num_types, pos_ids, max_pos);
   else
-    embedding_fwd_kernel<false><<<grid, warps * 32, 0, stream>>>(ids, types, ws, ps, ts, os, tokens, seq, h, vocab, num_types);
+    embedding_fwd_kernel<false><<<grid, warps * 32, 0, stream>>>(ids, types, ws, ps, ts, os, tokens, seq, h, vocab, num_types, pos_ids, max_pos);
   return cudaGetLastError();
 }
 

@@ -19,7 +19,7 @@ cudaError_t launch_layernorm_fwd(bool bf16, const void* x, int64_t ldx, const vo
 cudaError_t launch_embedding_fwd(bool bf16, const int64_t* ids, const int64_t* types,
                                  const void* word, const void* pos, const void* type_emb, void* out,
                                  int tokens, int seq, int h, int vocab, int num_types,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, const int32_t* pos_ids = nullptr, int max_pos = 0);
 
 // logprob[r] = logits[r, labels[r]] - log(sum_v exp(logits[r, v])) and lse[r] = that log-sum-exp:
 // the log_softmax + gather of the reader / retriever losses (reference

@@ -164,13 +164,24 @@ class EMDR2Model(nn.Module):
             # then K * s' instead of the reference's K * seq_length, with the ids trimmed alike.
             enc = self.language_model(all_query_extended_context_ids, dec_ids, output_enc_hidden=True,
                                       enc_max_len=len_ext, enc_row_lengths=rows_ext)
-            s_enc = enc.shape[1]
-            all_query_context_hidden_states = enc.reshape(bsize, topk * s_enc, hidden)
-            all_query_context_ids_unflat = all_query_extended_context_ids[:, :s_enc].reshape(bsize, topk * s_enc)
+            if hasattr(enc, "cross_plan"):
+                # token-packed encoder states (no-grad forward path with host-known lengths): question b's keys are
+                # its top-k sequences, contiguous and unpadded; there is no id matrix to mask with
+                if not st.get("packed_states", True):
+                    enc = enc.to_padded(self.language_model.language_model.trimmed_width(seq_length, len_ext))
+            if hasattr(enc, "cross_plan"):
+                all_query_context_hidden_states = enc
+                all_query_context_ids_unflat = all_query_extended_context_ids
+            else:
+                s_enc = enc.shape[1]
+                all_query_context_hidden_states = enc.reshape(bsize, topk * s_enc, hidden)
+                all_query_context_ids_unflat = all_query_extended_context_ids[:, :s_enc].reshape(bsize, topk * s_enc)
 
         # decoder_cache (blocks.DecoderCache, evaluation decoding only): logits come back for the positions
         # not decoded yet; the decode loops read [:, -1, :] either way
         extra = {} if decoder_cache is None else {"decoder_cache": decoder_cache}
+        if hasattr(all_query_context_hidden_states, "cross_plan"):
+            extra["fid_group"] = topk
         lm_logits, _ = self.language_model(all_query_context_ids_unflat[:, :1], dec_ids,
                                            enc_hidden_states=all_query_context_hidden_states,
                                            enc_ids_for_mask=all_query_context_ids_unflat, **extra)

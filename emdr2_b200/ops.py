@@ -150,6 +150,37 @@ def attention(q, k, v, batch, heads, sq, sk, q_pad=None, k_pad=None, causal=Fals
     return (out, lse) if return_lse else out
 
 
+def attention_varlen(q, k, v, heads, items, n_items, scale=0.125, out=None, out_rows=None, lse=None, flops=0.0):
+    """Variable-length attention over token-packed matrices (csrc/attention_varlen.cu): q [Tq, >= heads*64],
+    k / v [Tk, >= heads*64] (unit inner stride, e.g. column blocks of a fused projection); `items` int32 [n, 8]
+    on the device (emdr2_b200/packed.py builds them).  out: [out_rows, heads*64] (default: q's rows).  Rows no
+    item covers are left untouched."""
+    dtype, device = q.dtype, q.device
+    if dtype not in _DTYPES or not q.is_cuda:
+        raise TypeError("attention_varlen takes CUDA float16/bfloat16 tensors")
+    width = heads * 64
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _check_2d(name, t, dtype, device)
+        if t.shape[1] != width:
+            raise ValueError("%s must have %d columns" % (name, width))
+    if k.shape[0] != v.shape[0]:
+        raise ValueError("k and v must have the same number of rows")
+    if out is None:
+        out = torch.empty((q.shape[0] if out_rows is None else out_rows, width), dtype=dtype, device=device)
+    _check_2d("out", out, dtype, device)
+    if items.dtype != torch.int32 or items.device != device or not items.is_contiguous():
+        raise ValueError("items must be a contiguous int32 tensor on %s" % (device,))
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.emdr2_attention_varlen_fwd(
+            _DTYPES[dtype], _ptr(q), q.stride(0), q.shape[0], _ptr(k), k.stride(0), _ptr(v), v.stride(0), k.shape[0],
+            _ptr(out), out.stride(0), out.shape[0], heads, _ptr(items), int(n_items), float(scale), _ptr(lse),
+            _stream(device)), "emdr2_attention_varlen_fwd")
+    if flops:
+        timing_add_flops(KIND_ATTENTION, flops)
+    return out
+
+
 def layernorm(x, gamma, beta, eps=1e-5, out=None, return_stats=False):
     """Row-wise LayerNorm of a 2-D [rows, h] view (h % 8 == 0, h <= 1024), fp32 statistics."""
     dtype, device = x.dtype, x.device
@@ -171,8 +202,9 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None, return_stats=False):
     return (out, mean, rstd) if return_stats else out
 
 
-def embedding(ids, word, pos, types=None, type_emb=None, seq=None):
-    """out[b*s + i] = word[ids[b,i]] + pos[i] (+ type_emb[types[b,i]]); ids int64 [b, s]."""
+def embedding(ids, word, pos, types=None, type_emb=None, seq=None, pos_ids=None):
+    """out[b*s + i] = word[ids[b,i]] + pos[i] (+ type_emb[types[b,i]]); ids int64 [b, s].  pos_ids (int32, one per
+    token): explicit positions for token-packed sequences instead of i."""
     dtype, device = word.dtype, word.device
     if dtype not in _DTYPES or not word.is_cuda:
         raise TypeError("embedding takes CUDA float16/bfloat16 tables")
@@ -181,18 +213,20 @@ def embedding(ids, word, pos, types=None, type_emb=None, seq=None):
         seq = ids.shape[-1]
     tokens = ids.numel()
     h = word.shape[1]
-    if pos.shape[0] < seq:
+    if pos_ids is None and pos.shape[0] < seq:
         raise ValueError("sequence length %d exceeds the position table (%d rows)" % (seq, pos.shape[0]))
+    if pos_ids is not None and (pos_ids.dtype != torch.int32 or pos_ids.numel() != tokens or not pos_ids.is_contiguous()):
+        raise ValueError("pos_ids must be a contiguous int32 tensor with one entry per token")
     if types is not None:
         types = types.to(device=device, dtype=torch.int64).contiguous()
     out = torch.empty((tokens, h), dtype=dtype, device=device)
     lib = _lib.load()
     with torch.cuda.device(device):
-        _lib.check(lib.emdr2_embedding_fwd(
+        _lib.check(lib.emdr2_embedding_fwd_pos(
             _DTYPES[dtype], _ptr(ids), _ptr(types), _ptr(word.contiguous()), _ptr(pos.contiguous()),
             _ptr(type_emb.contiguous()) if type_emb is not None else None, _ptr(out), tokens, int(seq), h,
-            word.shape[0], type_emb.shape[0] if type_emb is not None else 0, _stream(device)),
-            "emdr2_embedding_fwd")
+            word.shape[0], type_emb.shape[0] if type_emb is not None else 0, _ptr(pos_ids), pos.shape[0],
+            _stream(device)), "emdr2_embedding_fwd")
     return out
 
 
@@ -238,6 +272,12 @@ def get_option(name):
 def timing(enable):
     """Bracket every block-operator launch of this thread with CUDA events (measurement aid)."""
     _lib.check(_lib.load().emdr2_ops_timing(1 if enable else 0), "emdr2_ops_timing")
+
+
+def timing_add_flops(kind, flops):
+    """Credit algorithmic work to a kernel kind whose entry point cannot know it (varlen attention: the work is
+    in the item list)."""
+    _lib.check(_lib.load().emdr2_ops_timing_add_flops(kind, ctypes.c_double(flops)), "emdr2_ops_timing_add_flops")
 
 
 def timing_read(kind):

@@ -222,6 +222,25 @@ EMDR2_API int emdr2_embedding_bwd(int dtype, const void* dx, const int64_t* ids,
                                   float* dword, float* dpos, float* dtype_emb, int tokens, int seq, int h,
                                   int vocab, int num_types, void* cuda_stream);
 
+/* Variable-length attention forward over TOKEN-PACKED activations (csrc/attention_varlen.cu): q [q_rows, >= heads*64],
+ * k / v [k_rows, >= heads*64] and o [o_rows, >= heads*64] are matrices in which sequences follow each other without
+ * padding; `items` (device, n_items x 8 int32: q_row0, q_valid (1..128), k_row0, k_len (>= 1), head, o_row0, lse_idx0,
+ * reserved) lists the (128-query tile, head, key range) products to compute — the self-attention of every sequence of
+ * a batch in ONE launch (transformer.py:301-383 over emdr2_model.py:118-120,148-149's padded rectangles), or the
+ * key ranges of a FiD cross-attention, to be merged by the caller with the lse weights.  No masks: a key outside the
+ * item's range has probability 0 (what masked_fill(-10000) + softmax gives a padding key).  Rows of a partial tile
+ * beyond q_valid are not written.  lse (optional): natural-log sum-exp per query at lse_idx0 + row. */
+EMDR2_API int emdr2_attention_varlen_fwd(int dtype, const void* q, int64_t ldq, int64_t q_rows, const void* k,
+                                         int64_t ldk, const void* v, int64_t ldv, int64_t k_rows, void* o, int64_t ldo,
+                                         int64_t o_rows, int heads, const int32_t* dev_items, int n_items, float scale,
+                                         float* lse, void* cuda_stream);
+
+/* emdr2_embedding_fwd with explicit positions: pos_ids int32 [tokens] (NULL = t % seq), for packed sequences. */
+EMDR2_API int emdr2_embedding_fwd_pos(int dtype, const int64_t* ids, const int64_t* types, const void* word,
+                                      const void* pos, const void* type_emb, void* out, int tokens, int seq, int h,
+                                      int vocab, int num_types, const int32_t* pos_ids, int max_pos,
+                                      void* cuda_stream);
+
 /* ---- dropout (csrc/dropout.cuh).  The reference trains with torch dropout, p = 0.1, on the attention
  * probabilities (megatron/model/transformer.py:345-346), on every bias-add-residual (transformer.py:397-419,
  * 511-515) and on the embedding sum (language_model.py:181), and stores the masks for the backward pass.
@@ -323,6 +342,8 @@ EMDR2_API int emdr2_ops_get_option(const char* name, int64_t* out_value);
 #define EMDR2_KIND_ROWOP 2
 #define EMDR2_KIND_COUNT 3
 EMDR2_API int emdr2_ops_timing(int enable);
+/* Credit algorithmic flops to a kind whose entry point cannot know them (emdr2_attention_varlen_fwd). */
+EMDR2_API int emdr2_ops_timing_add_flops(int kind, double flops);
 EMDR2_API int emdr2_ops_timing_read(int kind, int64_t* out_ns, int64_t* out_launches, double* out_flops);
 
 #ifdef __cplusplus
