@@ -99,6 +99,7 @@ struct AttnVarlenArgs {
   void* out;                     // packed output matrix (row-wise stores of partial tiles)
   int64_t ldo;
   float* lse;                    // optional
+  uint32_t sched;                // 0: S(j+1) issued ahead of P.V(j) (production); 1: behind it (A/B, EMDR2_VARLEN_SCHED=1)
 };
 
 cudaError_t attention_varlen_prepare();

@@ -24,6 +24,15 @@
 // the NEXT sequence (or zeros past the end of the matrix) — those key columns get probability 0 and
 // those query rows are never stored (partial tiles store row by row, full tiles by TMA).
 // Items are sorted by decreasing cost on the host and dealt round-robin to the resident CTAs.
+//
+// Scheduling inside a CTA (what distinguishes this kernel from attention_persist.cu): P has its OWN tensor-memory
+// columns — S [0,128) fp32, P [128,192) 16-bit pairs, O [192,256) — so the score tile is free again as soon as the
+// softmax warps have pulled it into registers (`s_free`), long before P exists.  The MMA thread therefore issues
+// S(j+1) — of the same item or of the next one — right after `s_free(j)` and only then waits for P(j): by the time the
+// softmax warps have finished block j their next score tile has been sitting in TMEM for ~1000 cycles, and they run
+// block after block without waiting on the tensor core (ncu of the previous schedule: MUFU pipe 46 % busy, warps
+// mostly stalled on barriers; the exp2 stream is what bounds head-dim-64 attention).  `pv_done` orders the two
+// things that must not overtake P.V(j-1): the O rescale and the overwrite of P by block j.
 #include "attention.cuh"
 
 #include <cuda_bf16.h>
@@ -46,9 +55,11 @@ struct VBars {
   uint64_t q_empty[2];
   uint64_t kv_full[kAttnStages];
   uint64_t kv_empty[kAttnStages];
-  uint64_t s_full;
-  uint64_t p_full;
-  uint64_t o_full;
+  uint64_t s_full;     // S(g) has landed in TMEM                          (tcgen05.commit)
+  uint64_t s_free;     // all four softmax warps hold S(g) in registers    (4 arrivals)
+  uint64_t p_full;     // P(g) is in TMEM                                  (4 arrivals)
+  uint64_t pv_done;    // P.V(g) has completed: P may be overwritten, O rescaled (tcgen05.commit)
+  uint64_t o_full;     // last P.V of the item has completed
   uint32_t tmem_base;
 };
 static_assert(sizeof(VBars) <= kAttnBarBytes, "barrier block too large");
@@ -122,7 +133,9 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       mbar_init(smem_u32(&bars->kv_empty[s]), 1);
     }
     mbar_init(smem_u32(&bars->s_full), 1);
+    mbar_init(smem_u32(&bars->s_free), 4);
     mbar_init(smem_u32(&bars->p_full), 4);
+    mbar_init(smem_u32(&bars->pv_done), 1);
     mbar_init(smem_u32(&bars->o_full), 1);
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -141,7 +154,8 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const uint32_t tmem_o = tmem_base + kAttnBK;
+  const uint32_t tmem_p = tmem_base + kAttnBK;             // 64 columns of 16-bit pairs
+  const uint32_t tmem_o = tmem_base + kAttnBK + 64;        // 64 fp32 columns
 
   if (warp < 4) {
     reg_dealloc<40>();   // warpgroup 0 (TMA, MMA, allocator, spare) hands its registers to the softmax warps
@@ -173,51 +187,75 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
     } else if (warp == 1 && lane == 0) {
       // ===================================================== MMA issuer
-      uint32_t stage = 0, phase = 0;   // K/V ring position of the next S product
-      uint32_t blk = 0;                // running count of key blocks (p_full phase)
-      uint32_t n = 0;
-      for (uint32_t idx = blockIdx.x; idx < a.n_items; idx += gridDim.x, ++n) {
-        const AttnVarlenItem it = load_item(a.items, idx);
-        const uint32_t nblk = (static_cast<uint32_t>(it.k_len) + kAttnBK - 1) / kAttnBK;
-        const uint32_t buf = n & 1;
-        mbar_wait(smem_u32(&bars->q_full[buf]), (n >> 1) & 1);
+      // Two cursors over the same (item, key block) sequence: `sc` issues score products one block AHEAD of `pc`,
+      // which issues the P.V products.  Order of issue: S(0); then per block g: S(g+1) once S(g) is in registers,
+      // P.V(g) once P(g) is in TMEM.
+      struct Cursor {
+        uint32_t idx, n, j, nblk;
+        bool ok;
+      };
+      auto load = [&](Cursor& c) {
+        c.ok = c.idx < a.n_items;
+        if (c.ok) c.nblk = (static_cast<uint32_t>(load_item(a.items, c.idx).k_len) + kAttnBK - 1) / kAttnBK;
+      };
+      auto advance = [&](Cursor& c) {
+        if (++c.j == c.nblk) {
+          c.idx += gridDim.x;
+          ++c.n;
+          c.j = 0;
+          load(c);
+        }
+      };
+      Cursor sc{blockIdx.x, 0, 0, 0, false}, pc{blockIdx.x, 0, 0, 0, false};
+      load(sc);
+      load(pc);
+      uint32_t s_stage = 0, s_phase = 0;   // K/V ring position of the next S product
+      uint32_t pv_stage = 0;               // ... and of the next P.V product
+      auto issue_s = [&]() {
+        const uint32_t buf = sc.n & 1;
+        if (sc.j == 0) {
+          mbar_wait(smem_u32(&bars->q_full[buf]), (sc.n >> 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(smem_u32(&bars->kv_full[s_stage]), s_phase);
         tc_fence_after();
         const uint64_t qdesc = smem_desc_sw128(smem_base + kOffQ + buf * kAttnTileBytes);
-        auto issue_s = [&]() {
-          mbar_wait(smem_u32(&bars->kv_full[stage]), phase);
-          tc_fence_after();
-          const uint64_t kdesc = smem_desc_sw128(smem_base + kOffKV + stage * 2 * kAttnTileBytes);
+        const uint64_t kdesc = smem_desc_sw128(smem_base + kOffKV + s_stage * 2 * kAttnTileBytes);
 #pragma unroll
-          for (int kk = 0; kk < kAttnHeadDim / 16; ++kk)
-            mma_f16_ss(tmem_base, qdesc + static_cast<uint64_t>(kk * 2),
-                       kdesc + static_cast<uint64_t>(kk * 2), a.idesc_s, kk != 0 ? 1u : 0u);
-          mma_commit(smem_u32(&bars->s_full));
-        };
-        issue_s();
-        for (uint32_t j = 0; j < nblk; ++j) {
-          mbar_wait(smem_u32(&bars->p_full), blk & 1);
-          tc_fence_after();
-          const uint32_t vbase = smem_base + kOffKV + stage * 2 * kAttnTileBytes + kAttnTileBytes;
-#pragma unroll
-          for (int ks = 0; ks < kAttnBK / 16; ++ks) {
-            // A = P in TMEM: row = lane, 16 keys = 8 packed 32-bit columns; B = V MN-major, 16 keys =
-            // two 8-row groups of 1024 B
-            const uint64_t vdesc = smem_desc_sw128_mn(vbase + ks * 2048, 1024, 1024);
-            mma_f16_ts(tmem_o, tmem_base + ks * 8, vdesc, a.idesc_o, (j != 0 || ks != 0) ? 1u : 0u);
-          }
-          mma_commit(smem_u32(&bars->kv_empty[stage]));
-          if (++stage == kAttnStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-          ++blk;
-          if (j + 1 < nblk) {
-            issue_s();
-          } else {
-            mma_commit(smem_u32(&bars->q_empty[buf]));
-            mma_commit(smem_u32(&bars->o_full));
-          }
+        for (int kk = 0; kk < kAttnHeadDim / 16; ++kk)
+          mma_f16_ss(tmem_base, qdesc + static_cast<uint64_t>(kk * 2), kdesc + static_cast<uint64_t>(kk * 2),
+                     a.idesc_s, kk != 0 ? 1u : 0u);
+        mma_commit(smem_u32(&bars->s_full));
+        if (sc.j + 1 == sc.nblk) mma_commit(smem_u32(&bars->q_empty[buf]));   // Q is only read by the S products
+        if (++s_stage == kAttnStages) {
+          s_stage = 0;
+          s_phase ^= 1;
         }
+        advance(sc);
+      };
+      if (sc.ok) issue_s();
+      for (uint32_t g = 0; pc.ok; ++g) {
+        if (sc.ok && a.sched == 0) {
+          mbar_wait(smem_u32(&bars->s_free), g & 1);     // S(g) is in the softmax warps' registers
+          tc_fence_after();
+          issue_s();                                     // S(g+1)
+        }
+        mbar_wait(smem_u32(&bars->p_full), g & 1);
+        tc_fence_after();
+        const uint32_t vbase = smem_base + kOffKV + pv_stage * 2 * kAttnTileBytes + kAttnTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < kAttnBK / 16; ++ks) {
+          // A = P in TMEM: row = lane, 16 keys = 8 packed 32-bit columns; B = V MN-major, 16 keys =
+          // two 8-row groups of 1024 B
+          const uint64_t vdesc = smem_desc_sw128_mn(vbase + ks * 2048, 1024, 1024);
+          mma_f16_ts(tmem_o, tmem_p + ks * 8, vdesc, a.idesc_o, (pc.j != 0 || ks != 0) ? 1u : 0u);
+        }
+        mma_commit(smem_u32(&bars->kv_empty[pv_stage]));
+        mma_commit(smem_u32(&bars->pv_done));
+        if (pc.j + 1 == pc.nblk) mma_commit(smem_u32(&bars->o_full));
+        if (++pv_stage == kAttnStages) pv_stage = 0;
+        advance(pc);
+        if (sc.ok && a.sched != 0) issue_s();            // conservative order (debug): S(g+1) behind P.V(g)
       }
     }
   } else {
@@ -255,6 +293,9 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           tmem_ld_32x32b_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&t[64]));
           tmem_ld_32x32b_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&t[96]));
           tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->s_free));   // the tensor core may overwrite S now
           // ---- block maximum.  A full block (every block but a range's last): raw maximum, one scale.
           // The last block: 32-key chunks inside the range keep their raw accumulators, chunks past its
           // end contribute nothing (multiplier 0, bias -inf), and the one chunk the end falls into is
@@ -309,6 +350,12 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
               mx = fmaxf(mx, m);
             }
           }
+          // P.V of the previous block (of this item or the one before) must have completed before O is rescaled
+          // or P overwritten; it was issued ~a block ago, so this wait is normally free
+          if (blk > 0) {
+            mbar_wait(smem_u32(&bars->pv_done), (blk - 1) & 1);
+            tc_fence_after();
+          }
           // ---- running maximum: raised only when the block exceeds it by more than 2^8
           const bool first = j == 0;
           const bool raise = first || mx > m_run + kLazyRescale;
@@ -319,8 +366,7 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           }
           l_run *= alpha;
           if (!first && __any_sync(kFull, raise)) {
-            // O *= alpha in TMEM (P.V of the previous block has completed: s_full is committed
-            // behind it).  Warp-uniform branch: tcgen05.ld/st are .sync.aligned.
+            // O *= alpha in TMEM.  Warp-uniform branch: tcgen05.ld/st are .sync.aligned.
 #pragma unroll
             for (int c = 0; c < kAttnHeadDim / 16; ++c) {
               uint32_t o[16];
@@ -346,23 +392,24 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
               sum1 += p1;
               w[i] = pack2<kBf16>(p0, p1);
             }
-            tmem_st_32x32b_x16(tmem_base + lane_tmem + c * 16, w);
+            tmem_st_32x32b_x16(tmem_p + lane_tmem + c * 16, w);
           }
           l_run += sum0 + sum1;
           tmem_st_wait();
         } else {
-          // rows of an inactive warp are never stored, but the tensor core reads P for all 128 lanes:
-          // give it zeros so that nothing non-finite enters the (discarded) accumulator rows
-          uint32_t z[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) z[i] = 0u;
-#pragma unroll
-          for (int c = 0; c < kAttnBK / 32; ++c) tmem_st_32x32b_x16(tmem_base + lane_tmem + c * 16, z);
-          tmem_st_wait();
+          // a warp whose 32 rows are all past the end of the tile: its rows of P / O are never stored (the tensor
+          // core computes them from whatever the lanes hold; rows are independent) — it only keeps the barriers going
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->s_free));
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->p_full));
+        // An idle warp has nothing to do until the next score tile, which now lands BEFORE the working warps have
+        // finished this block: without this wait it would run a block ahead and its next arrival would be counted
+        // into THIS block's p_full phase, releasing P.V before P is written.
+        if (!warp_active) mbar_wait(smem_u32(&bars->p_full), blk & 1);
       }
 
       // ---- item epilogue: O / l -> 16-bit row

@@ -638,6 +638,11 @@ int emdr2_attention_varlen_fwd(int dtype, const void* q, int64_t ldq, int64_t q_
   aa.out = o;
   aa.ldo = ldo;
   aa.lse = lse;
+  static const uint32_t sched = [] {
+    const char* e = getenv("EMDR2_VARLEN_SCHED");
+    return (e && e[0] == '1') ? 1u : 0u;
+  }();
+  aa.sched = sched;
   // algorithmic work is not known here without reading the items back: callers that time this kind pass
   // through emdr2_ops_timing and account flops themselves; count the launch with zero flops
   ScopedTimer timer(EMDR2_KIND_ATTENTION, static_cast<cudaStream_t>(cuda_stream), 0.0);
