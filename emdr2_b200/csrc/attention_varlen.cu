@@ -166,13 +166,13 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const AttnVarlenItem it = load_item(a.items, idx);
         const int32_t col_h = it.head * kAttnHeadDim;
         const uint32_t buf = n & 1;
-        mbar_wait(smem_u32(&bars->q_empty[buf]), ((n >> 1) & 1) ^ 1);
+        mbar_wait_backoff<200>(smem_u32(&bars->q_empty[buf]), ((n >> 1) & 1) ^ 1);
         const uint32_t qbar = smem_u32(&bars->q_full[buf]);
         mbar_arrive_expect_tx(qbar, kAttnTileBytes);
         tma_load_2d(smem_base + kOffQ + buf * kAttnTileBytes, &tmap_q, qbar, col_h, it.q_row0, kEvictNormal);
         const uint32_t nblk = (static_cast<uint32_t>(it.k_len) + kAttnBK - 1) / kAttnBK;
         for (uint32_t j = 0; j < nblk; ++j) {
-          mbar_wait(smem_u32(&bars->kv_empty[stage]), phase ^ 1);
+          mbar_wait_backoff<100>(smem_u32(&bars->kv_empty[stage]), phase ^ 1);
           const uint32_t fbar = smem_u32(&bars->kv_full[stage]);
           mbar_arrive_expect_tx(fbar, 2 * kAttnTileBytes);
           const uint32_t dst = smem_base + kOffKV + stage * 2 * kAttnTileBytes;

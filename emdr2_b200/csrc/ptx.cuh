@@ -57,6 +57,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Same, for single-thread roles whose waits are long (a TMA producer waiting for a free stage, an MMA issuer
+// waiting for the softmax warps): a bare try_wait loop retires an instruction every few cycles and takes issue
+// slots from the working warps of its scheduler (ncu: a third of the varlen attention kernel's executed
+// instructions were such polls); sleeping between polls costs at most `ns` of reaction time.
+template <unsigned kNs>
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(kNs);
+}
 
 // ---------------------------------------------------------------- TMA
 // L2 eviction-priority policies (createpolicy encodings).
