@@ -767,11 +767,11 @@ def run_retrieve_read(a):
         from emdr2_b200 import losses
         if not trainer:
             from emdr2_b200.data_parallel import GradientBuckets, flatten_parameters
-            trainer["buckets"] = gb = GradientBuckets(list(model.parameters()), group=d.group)
+            trainer["buckets"] = gb = GradientBuckets(list(model.parameters()), group=d.group, main_grad=True)
             trainer["pflat"] = flatten_parameters(gb)
             trainer["masters"] = [f.float().requires_grad_(True) for f in trainer["pflat"]]
-            for m in trainer["masters"]:
-                m.grad = torch.zeros_like(m)
+            for m, b in zip(trainer["masters"], gb.buckets):
+                m.grad = b.grad              # the fp32 main-grad bucket IS the master gradient: nothing to cast or copy
             # torch.optim (library): the reference uses apex FusedAdam; the optimizer is a caller of the hot path
             trainer["opt"] = torch.optim.AdamW(trainer["masters"], lr=2e-5, weight_decay=0.01, fused=True)
         gb = trainer["buckets"]
@@ -782,10 +782,9 @@ def run_retrieve_read(a):
         r_loss, _, _ = losses.get_loss_and_retriever_utility(one_ctx, topk_log_probs, x["labels"], mask, 30523)
         (lm_loss + r_loss).backward()
         gb.finish()
-        for m, b in zip(trainer["masters"], gb.buckets):
-            m.grad.copy_(b.grad)
-            if world > 1:
-                m.grad.mul_(1.0 / world)
+        if world > 1:
+            for b in gb.buckets:
+                b.grad.mul_(1.0 / world)
         trainer["opt"].step()
         with torch.no_grad():
             for f, m in zip(trainer["pflat"], trainer["masters"]):
@@ -876,9 +875,10 @@ def run_retrieve_read(a):
                 "gradient_allreduce": {"buckets": len(gb.buckets), "bytes": sum(b.grad.numel() * b.grad.element_size() for b in gb.buckets),
                                        "launched_from_backward_hooks": gb.launched,
                                        "exposed_alone_ms": ar_ms,
-                                       "how": "one async NCCL all-reduce per 64 MB bucket, launched when the bucket's last "
-                                              "gradient is accumulated (overlaps the rest of backward); gradients live in "
-                                              "flat buffers (no flatten/unflatten copies)"},
+                                       "how": "one async NCCL all-reduce per 64 MB fp32 bucket, launched when the bucket's "
+                                              "last gradient contribution is enqueued (overlaps the rest of backward); the "
+                                              "backward kernels accumulate straight into the flat fp32 buckets, which are also "
+                                              "the optimizer's master gradients (no zero fills, casts, flatten/unflatten)"},
                 "dropout": {"hidden": cfg["hidden_dropout"], "attention": cfg["attention_dropout"],
                             "how": "counter-based masks regenerated in the backward kernels (csrc/dropout.cuh)"},
                 "gpu_launches": int(m["launches_step"] * steps), "clocks": m["clocks"],

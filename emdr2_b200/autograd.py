@@ -37,23 +37,55 @@ def _splits(tokens, tiles):
     return max(1, min(want, (tokens + _SPLIT_TOKENS - 1) // _SPLIT_TOKENS))
 
 
-def _weight_grad(dy, x):
-    """dW[n, k] = dy[m, n]^T . x[m, k] in fp32 (split-K), returned in the parameter dtype."""
+# ---- gradient sinks ("main grads").  A trainer may attach to a parameter an fp32 buffer `main_grad` (a view of a
+# flat all-reduce bucket, emdr2_b200/data_parallel.py).  The backward kernels then ACCUMULATE straight into it —
+# the split-K weight-gradient GEMM, the bias column sums, the LayerNorm and embedding backward kernels all add
+# into fp32 in place anyway — and autograd is handed None for that parameter: no zero fill, no fp32 -> 16-bit
+# cast, no AccumulateGrad add, no later cast back for the optimizer (~4 small launches per parameter per step).
+# `_expect` / `_done` count a parameter's uses between forward and backward so that the trainer learns when the
+# LAST contribution has landed (`param._on_main_grad(param)`): that is what launches a bucket's all-reduce.
+def _sink(param):
+    return getattr(param, "main_grad", None)
+
+
+def _expect(*params):
+    for p in params:
+        if p is not None and getattr(p, "main_grad", None) is not None:
+            p._pending_main_grads = getattr(p, "_pending_main_grads", 0) + 1
+
+
+def _done(*params):
+    for p in params:
+        if p is None or getattr(p, "main_grad", None) is None:
+            continue
+        p._pending_main_grads = getattr(p, "_pending_main_grads", 1) - 1
+        if p._pending_main_grads <= 0:
+            cb = getattr(p, "_on_main_grad", None)
+            if cb is not None:
+                cb(p)
+
+
+def _weight_grad(dy, x, sink=None):
+    """dW[n, k] = dy[m, n]^T . x[m, k] in fp32 (split-K): added into `sink` (returns None) or returned in the
+    parameter dtype."""
     m, n = dy.shape
     k = x.shape[1]
-    acc = torch.zeros((n, k), dtype=torch.float32, device=dy.device)
     tiles = ((n + 127) // 128) * ((k + 255) // 256)
+    if sink is not None:
+        ops.gemm_ex(dy, x, a_mn=True, b_mn=True, accumulate_into=sink, splits=_splits(m, tiles))
+        return None
+    acc = torch.zeros((n, k), dtype=torch.float32, device=dy.device)
     ops.gemm_ex(dy, x, a_mn=True, b_mn=True, accumulate_into=acc, splits=_splits(m, tiles))
     return acc.to(dy.dtype)
 
 
-def _bias_grad(dy):
-    out = torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
+def _bias_grad(dy, sink=None):
+    out = sink if sink is not None else torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
     lib = _lib.load()
     with torch.cuda.device(dy.device):
         _lib.check(lib.emdr2_colsum(_DT[dy.dtype], ops._ptr(dy), dy.stride(0), ops._ptr(out), dy.shape[0],
                                     dy.shape[1], ops._stream(dy.device)), "emdr2_colsum")
-    return out.to(dy.dtype)
+    return None if sink is not None else out.to(dy.dtype)
 
 
 def _c(t):
@@ -66,16 +98,20 @@ class _LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, residual):
         ctx.save_for_backward(x, weight)
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.params = (weight, bias)
+        _expect(weight, bias)
         return ops.linear(x, weight, bias, residual=residual)
 
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
+        wp, bp = ctx.params
         dy = _c(dy)
         dx = ops.gemm_ex(dy, weight, b_mn=True) if ctx.needs_input_grad[0] else None
-        dw = _weight_grad(dy, x) if ctx.needs_input_grad[1] else None
-        db = _bias_grad(dy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dw = _weight_grad(dy, x, _sink(wp)) if ctx.needs_input_grad[1] else None
+        db = _bias_grad(dy, _sink(bp)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        _done(wp, bp)
         return dx, dw, db, dres
 
 
@@ -83,6 +119,51 @@ def linear(x, weight, bias=None, residual=None):
     if _needs_grad(x, weight, bias, residual):
         return _LinearFn.apply(x, weight, bias, residual)
     return ops.linear(x, weight, bias, residual=residual)
+
+
+class _PackedLinearFn(torch.autograd.Function):
+    """y = x W_k^T + b_k for a fused projection whose PARAMETER keeps the reference's [np, hn, splits] row order
+    (transformer.py:232-240, checkpoint compatibility) while the kernels use the [splits, np, hn] copy W_k.  The
+    permutation is not part of the autograd graph: the weight gradient is produced per split — dW[:, s, :] =
+    dy[:, s-th column block]^T x — straight into the parameter's row order (a strided [h, k] view of the
+    parameter-shaped buffer), i.e. into its main-grad sink when there is one."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_k, b_k, heads, hn, splits):
+        ctx.save_for_backward(x, w_k)
+        ctx.params, ctx.layout = (weight, bias), (heads, hn, splits)
+        _expect(weight, bias)
+        return ops.linear(x, w_k, b_k)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_k = ctx.saved_tensors
+        wp, bp = ctx.params
+        heads, hn, splits = ctx.layout
+        h, k = heads * hn, x.shape[1]
+        dy = _c(dy)
+        dx = ops.gemm_ex(dy, w_k, b_mn=True) if ctx.needs_input_grad[0] else None
+        sw, sb = _sink(wp), _sink(bp)
+        dw32 = sw if sw is not None else torch.zeros((splits * h, k), dtype=torch.float32, device=dy.device)
+        per_split = dw32.view(h, splits, k)
+        for s_i in range(splits):
+            _weight_grad(dy[:, s_i * h:(s_i + 1) * h], x, per_split[:, s_i, :])
+        db_k = _bias_grad(dy).float()                                  # [splits * h] in kernel order
+        if sb is not None:
+            sb.view(h, splits).add_(db_k.view(splits, h).t())
+        if sw is not None and sb is not None:
+            _done(wp, bp)
+            return (dx, None, None) + (None,) * 5
+        dw = None if sw is not None else dw32.to(dy.dtype)
+        db = None if sb is not None else db_k.view(splits, h).t().reshape(-1).to(dy.dtype)
+        _done(wp, bp)
+        return (dx, dw, db) + (None,) * 5
+
+
+def packed_linear(x, weight, bias, w_k, b_k, heads, hn, splits):
+    if _needs_grad(x, weight, bias):
+        return _PackedLinearFn.apply(x, weight, bias, w_k, b_k, heads, hn, splits)
+    return ops.linear(x, w_k, b_k)
 
 
 # ------------------------------------------------------------------------------------------ mlp
@@ -93,19 +174,23 @@ class _MlpFn(torch.autograd.Function):
         act = ops.gemm_ex(x, w1, bias=b1, gelu=True, preact_out=pre)
         ctx.save_for_backward(x, w1, w2, pre, act)
         ctx.has_res = residual is not None
+        ctx.params = (w1, b1, w2, b2)
+        _expect(w1, b1, w2, b2)
         return ops.linear(act, w2, b2, residual=residual)
 
     @staticmethod
     def backward(ctx, dy):
         x, w1, w2, pre, act = ctx.saved_tensors
+        p1, q1, p2, q2 = ctx.params
         dy = _c(dy)
         du = ops.gemm_ex(dy, w2, b_mn=True, gelu_bwd_aux=pre)        # (dy . W2) * GeLU'(pre)
-        dw2 = _weight_grad(dy, act) if ctx.needs_input_grad[3] else None
-        db2 = _bias_grad(dy) if ctx.needs_input_grad[4] else None
+        dw2 = _weight_grad(dy, act, _sink(p2)) if ctx.needs_input_grad[3] else None
+        db2 = _bias_grad(dy, _sink(q2)) if ctx.needs_input_grad[4] else None
         dx = ops.gemm_ex(du, w1, b_mn=True) if ctx.needs_input_grad[0] else None
-        dw1 = _weight_grad(du, x) if ctx.needs_input_grad[1] else None
-        db1 = _bias_grad(du) if ctx.needs_input_grad[2] else None
+        dw1 = _weight_grad(du, x, _sink(p1)) if ctx.needs_input_grad[1] else None
+        db1 = _bias_grad(du, _sink(q1)) if ctx.needs_input_grad[2] else None
         dres = dy if (ctx.has_res and ctx.needs_input_grad[5]) else None
+        _done(p1, q1, p2, q2)
         return dx, dw1, db1, dw2, db2, dres
 
 
@@ -152,22 +237,29 @@ class _LayerNormFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, eps):
         y, mean, rstd = ops.layernorm(x, gamma, beta, eps, return_stats=True)
         ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.params = (gamma, beta)
+        _expect(gamma, beta)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, gamma, mean, rstd = ctx.saved_tensors
+        gp, bp = ctx.params
         dy = _c(dy)
         rows, h = x.shape
         dx = torch.empty_like(x)
-        dgamma = torch.zeros(h, dtype=torch.float32, device=x.device)
-        dbeta = torch.zeros(h, dtype=torch.float32, device=x.device)
+        sunk = _sink(gp) is not None and _sink(bp) is not None
+        dgamma = _sink(gp) if sunk else torch.zeros(h, dtype=torch.float32, device=x.device)
+        dbeta = _sink(bp) if sunk else torch.zeros(h, dtype=torch.float32, device=x.device)
         lib = _lib.load()
         with torch.cuda.device(x.device):
             _lib.check(lib.emdr2_layernorm_bwd(
                 _DT[x.dtype], ops._ptr(dy), dy.stride(0), ops._ptr(x), x.stride(0), ops._ptr(gamma),
                 ops._ptr(mean), ops._ptr(rstd), None, 0, ops._ptr(dx), dx.stride(0), ops._ptr(dgamma),
                 ops._ptr(dbeta), rows, h, ops._stream(x.device)), "emdr2_layernorm_bwd")
+        if sunk:
+            _done(gp, bp)
+            return dx, None, None, None
         return dx, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None
 
 
@@ -407,6 +499,8 @@ class _EmbeddingFn(torch.autograd.Function):
     def forward(ctx, ids, word, pos, types, type_emb):
         ctx.save_for_backward(ids, types)
         ctx.shapes = (word.shape, pos.shape, None if type_emb is None else type_emb.shape, word.dtype)
+        ctx.params = (word, pos, type_emb)
+        _expect(word, pos, type_emb)
         return ops.embedding(ids, word, pos, types, type_emb)
 
     @staticmethod
@@ -415,9 +509,15 @@ class _EmbeddingFn(torch.autograd.Function):
         wshape, pshape, tshape, dtype = ctx.shapes
         dx = dx.contiguous()
         dev = dx.device
-        dword = torch.zeros(wshape, dtype=torch.float32, device=dev)
-        dpos = torch.zeros(pshape, dtype=torch.float32, device=dev)
-        dtyp = torch.zeros(tshape, dtype=torch.float32, device=dev) if (tshape is not None and types is not None) else None
+        wp, pp, tp = ctx.params
+        sunk = _sink(wp) is not None and _sink(pp) is not None and (tp is None or _sink(tp) is not None)
+        if sunk:
+            dword, dpos = _sink(wp), _sink(pp)
+            dtyp = _sink(tp) if (tp is not None and types is not None) else None
+        else:
+            dword = torch.zeros(wshape, dtype=torch.float32, device=dev)
+            dpos = torch.zeros(pshape, dtype=torch.float32, device=dev)
+            dtyp = torch.zeros(tshape, dtype=torch.float32, device=dev) if (tshape is not None and types is not None) else None
         ids2 = ids.to(torch.int64).contiguous()
         ty2 = None if types is None else types.to(torch.int64).contiguous()
         lib = _lib.load()
@@ -426,6 +526,9 @@ class _EmbeddingFn(torch.autograd.Function):
                 _DT[dtype], ops._ptr(dx), ops._ptr(ids2), ops._ptr(ty2), ops._ptr(dword), ops._ptr(dpos),
                 ops._ptr(dtyp), ids2.numel(), ids2.shape[-1], wshape[1], wshape[0],
                 0 if tshape is None else tshape[0], ops._stream(dev)), "emdr2_embedding_bwd")
+        if sunk:
+            _done(wp, pp, tp)
+            return None, None, None, None, None
         return (None, dword.to(dtype), dpos.to(dtype), None,
                 None if tshape is None else (dtyp.to(dtype) if dtyp is not None else torch.zeros(tshape, dtype=dtype, device=dev)))
 

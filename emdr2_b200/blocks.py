@@ -90,14 +90,10 @@ class _PackedProjection(nn.Module):
         return self._cache[1], self._cache[2]
 
     def forward(self, x):
-        if torch.is_grad_enabled() and (self.weight.requires_grad or x.requires_grad):
-            # training: the permutation is part of the graph so gradients land in the parameter's
-            # (reference) row order
-            w = _unpack_rows(self.weight, self.heads, self.hn, self.splits)
-            b = _unpack_rows(self.bias, self.heads, self.hn, self.splits)
-        else:
-            w, b = self._packed()
-        return ag.linear(x, w, b)
+        # the kernel-order copy is cached per parameter version; in training the weight gradient is produced
+        # directly in the parameter's (reference) row order (autograd._PackedLinearFn)
+        w, b = self._packed()
+        return ag.packed_linear(x, self.weight, self.bias, w, b, self.heads, self.hn, self.splits)
 
 
 class ParallelAttention(nn.Module):

@@ -8,6 +8,7 @@ laid out in reverse registration order — the order in which backward produces 
 NCCL all-reduce is launched asynchronously from an autograd hook the moment its last gradient has been
 accumulated, so it runs over NVLink underneath the rest of the backward pass.  `finish()` launches whatever
 is left (buckets whose parameters received no gradient this step) and makes the compute stream wait.
+With `main_grad=True` the buffers are fp32 sinks the backward kernels add into directly (see the class).
 
 Parameters themselves can be re-homed the same way (`flatten_parameters`), which turns the optimizer's
 master-weight copy-back into one copy per bucket.  torch.distributed (NCCL) is the transport; nothing here
@@ -21,8 +22,14 @@ class _Bucket(object):
 
 
 class GradientBuckets(object):
-    def __init__(self, params, group=None, bucket_bytes=64 << 20):
+    """main_grad=True: the flat buffers are fp32 and are attached to the parameters as `main_grad` sinks that the
+    backward kernels of emdr2_b200/autograd.py accumulate into directly (no `.grad` tensors, no zero fills, casts
+    or AccumulateGrad adds; the optimizer's fp32 master gradients ARE these buffers).  A gradient that still arrives
+    through `.grad` (a parameter used by a plain torch op) is folded into the sink by the hook."""
+
+    def __init__(self, params, group=None, bucket_bytes=64 << 20, main_grad=False):
         import torch.distributed as dist
+        self.main_grad = bool(main_grad)
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         params = [p for p in params if p.requires_grad]
@@ -32,7 +39,7 @@ class GradientBuckets(object):
         self._handles = []
         cur, size = [], 0
         for p in reversed(params):                       # backward reaches the last layers first
-            nbytes = p.numel() * p.element_size()
+            nbytes = p.numel() * (4 if self.main_grad else p.element_size())
             if cur and (size + nbytes > bucket_bytes or p.dtype != cur[0].dtype or p.device != cur[0].device):
                 self._seal(cur)
                 cur, size = [], 0
@@ -51,9 +58,14 @@ class GradientBuckets(object):
             b.offsets.append(off)
             off += -(-p.numel() // 8) * 8                # 16-byte aligned views
         b.numel = off
-        b.grad = torch.zeros(off, dtype=group_params[0].dtype, device=group_params[0].device)
+        dtype = torch.float32 if self.main_grad else group_params[0].dtype
+        b.grad = torch.zeros(off, dtype=dtype, device=group_params[0].device)
         for p, o in zip(b.params, b.offsets):
-            p.grad = b.grad[o:o + p.numel()].view_as(p)
+            view = b.grad[o:o + p.numel()].view_as(p)
+            if self.main_grad:
+                p.main_grad, p._on_main_grad, p.grad = view, self._on_main_grad, None
+            else:
+                p.grad = view
             self._bucket_of[p] = b
         b.pending, b.work = len(b.params), None
         self.buckets.append(b)
@@ -65,11 +77,23 @@ class GradientBuckets(object):
         for b in self.buckets:
             b.grad.zero_()
             b.pending, b.work = len(b.params), None
-            for p, o in zip(b.params, b.offsets):        # an optimizer or a caller may have dropped the views
-                if p.grad is None or p.grad.data_ptr() != b.grad.data_ptr() + o * b.grad.element_size():
-                    p.grad = b.grad[o:o + p.numel()].view_as(p)
+            for p, o in zip(b.params, b.offsets):
+                if self.main_grad:
+                    p._pending_main_grads, p.grad = 0, None
+                elif p.grad is None or p.grad.data_ptr() != b.grad.data_ptr() + o * b.grad.element_size():
+                    p.grad = b.grad[o:o + p.numel()].view_as(p)      # an optimizer or a caller dropped the view
 
     def _on_grad(self, p):
+        if self.main_grad:                               # arrived through autograd's .grad: fold it into the sink
+            if p.grad is not None:
+                p.main_grad.add_(p.grad)
+                p.grad = None
+        self._complete(p)
+
+    def _on_main_grad(self, p):                          # the last kernel contribution of this step has been enqueued
+        self._complete(p)
+
+    def _complete(self, p):
         b = self._bucket_of[p]
         b.pending -= 1
         if b.pending == 0:
@@ -103,7 +127,7 @@ def flatten_parameters(buckets):
     flats = []
     with torch.no_grad():
         for b in buckets.buckets:
-            flat = torch.zeros(b.numel, dtype=b.grad.dtype, device=b.grad.device)
+            flat = torch.zeros(b.numel, dtype=b.params[0].dtype, device=b.grad.device)
             for p, o in zip(b.params, b.offsets):
                 view = flat[o:o + p.numel()].view_as(p)
                 view.copy_(p.data)

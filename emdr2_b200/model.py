@@ -170,8 +170,9 @@ class EMDR2Model(nn.Module):
                 if not st.get("packed_states", True):
                     enc = enc.to_padded(self.language_model.language_model.trimmed_width(seq_length, len_ext))
             if hasattr(enc, "cross_plan"):
+                enc.group = topk
                 all_query_context_hidden_states = enc
-                all_query_context_ids_unflat = all_query_extended_context_ids
+                all_query_context_ids_unflat = all_query_extended_context_ids.view(bsize, topk, -1)
             else:
                 s_enc = enc.shape[1]
                 all_query_context_hidden_states = enc.reshape(bsize, topk * s_enc, hidden)

@@ -81,9 +81,25 @@ class PackedStates(object):
     """Encoder states of a packed batch: `states` [T, h], sequence i = rows [cu[i], cu[i+1]).  What the FiD
     decoder attends over: question q's keys are the rows of its `group` consecutive sequences, contiguous."""
 
-    def __init__(self, states, lens, cu):
+    def __init__(self, states, lens, cu, group=1):
         self.states, self.lens, self.cu = states, np.asarray(lens), np.asarray(cu)
+        self.group = int(group)          # sequences per key set (FiD: the top-k passages of one question)
         self._cross = {}
+
+    def index_select(self, dim, index):
+        """Key sets `index` (with repetition), like Tensor.index_select(0, ...) on the padded [sets, keys, h] states:
+        what the reference's beam search does to carry the encoder states of a question along with each of its
+        hypotheses (search_strategy.py:91-103).  The cached decode loop never needs it."""
+        if dim != 0:
+            raise ValueError("packed encoder states are selected by key set (dim 0)")
+        sets = np.asarray(index.tolist() if torch.is_tensor(index) else index, dtype=np.int64)
+        g = self.group
+        seqs = (sets[:, None] * g + np.arange(g)[None, :]).reshape(-1)
+        lens = self.lens[seqs]
+        cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        rows = np.repeat(self.cu[seqs] - cu[:-1], lens) + np.arange(int(cu[-1]))
+        picked = self.states.index_select(0, torch.from_numpy(rows).to(self.states.device))
+        return PackedStates(picked, lens, cu, group=g)
 
     @property
     def shape(self):

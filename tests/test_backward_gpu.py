@@ -209,3 +209,44 @@ def test_t5_reader_and_bert_tower_parameter_gradients(dtype):
     (oloss * mask.view(-1)).sum().backward()
     worst = worst_of(t5, w32)
     assert worst[0] < tol, worst
+
+
+def test_main_grad_sinks_equal_the_autograd_gradients():
+    """data_parallel.GradientBuckets(main_grad=True): the backward kernels accumulate straight into fp32 flat
+    buffers and autograd sees no parameter gradients; the result must equal the ordinary `.grad` path (which casts
+    each gradient to 16 bits) to that cast's rounding, for every parameter incl. the fused projections whose
+    parameters keep the reference's [np, hn, 3] row order.  Tolerance: relative Frobenius 1e-2 (bf16 cast)."""
+    from emdr2_b200.blocks import T5Reader
+    from emdr2_b200.data_parallel import GradientBuckets
+    dtype = torch.bfloat16
+    cfg = dict(TINY, dtype=dtype)
+    inp = tiny_inputs()
+    t5 = T5Reader(cfg).to(DEV)
+    with torch.no_grad():
+        for name, p in t5.named_parameters():
+            p.copy_(seeded_weights(name, tuple(p.shape)).to(dtype))
+    enc, dec = torch.from_numpy(inp["t5_enc_ids"]).to(DEV), torch.from_numpy(inp["t5_dec_ids"]).to(DEV)
+
+    def run():
+        loss, _ = t5(enc, dec, lm_labels=dec)
+        (loss * (dec > 0).float()).sum().backward()
+
+    run()
+    plain = {n: p.grad.float().clone() for n, p in t5.named_parameters() if p.grad is not None}
+    for p in t5.parameters():
+        p.grad = None
+    gb = GradientBuckets(list(t5.parameters()), bucket_bytes=1 << 20, main_grad=True)
+    for step in range(2):                                      # sinks are re-zeroed and reused
+        gb.start_step()
+        run()
+        gb.finish()
+        assert all(p.grad is None for p in t5.parameters())
+        assert all(getattr(p, "_pending_main_grads", 0) == 0 for p in t5.parameters())
+        worst = 0.0
+        for n, p in t5.named_parameters():
+            if n not in plain:
+                assert float(p.main_grad.abs().max()) == 0.0, n
+                continue
+            worst = max(worst, _rel(p.main_grad, plain[n]))
+        assert worst < 1e-2, worst
+    gb.close()

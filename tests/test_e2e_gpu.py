@@ -121,6 +121,11 @@ def test_retrieve_and_read_forward_tiny(tmp_path, dtype):
     assert np.array_equal(got_ids[ties == 0], want_i[ties == 0])
 
     torch.set_grad_enabled(False)
+    # the rectangular kernels first (token-packed execution off): exact equalities between the model's own paths
+    all_towers = (model.language_model.language_model, model.retriever_model.context_model.language_model,
+                  model.retriever_model.query_model.language_model)
+    for lm in all_towers:
+        lm.packed_varlen = False
     model.train()
     lm_logits, topk_log_probs, one_ctx = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV),
                                                torch.tensor(q_len).to(DEV), dec.to(DEV))
@@ -175,6 +180,25 @@ def test_retrieve_and_read_forward_tiny(tmp_path, dtype):
         del lm.bucket_min_rows, lm.length_buckets
     assert bucketed[2].shape == ev[2].shape
     assert torch.equal(bucketed[0][live], lm_logits[live]) and torch.equal(bucketed[1], topk_log_probs)
+
+    # ---- token-packed execution (the default of the no-grad eval path, emdr2_b200/packed.py): same logits to the
+    # rounding of the 16-bit probabilities / the range merge, encoder states come back packed, cached re-entry works
+    for lm in all_towers:
+        del lm.packed_varlen
+    pk = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV), torch.tensor(q_len).to(DEV), dec.to(DEV))
+    assert hasattr(pk[2], "cross_plan") and pk[2].states.shape[1] == TINY["hidden"]
+    tol = 3e-2 if dtype == torch.bfloat16 else 4e-3
+    assert (pk[0].float()[live] - lm_logits.float()[live]).abs().max().item() < tol
+    assert torch.allclose(pk[1], topk_log_probs, atol=tol, rtol=0)
+    pk_again = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV), torch.tensor(q_len).to(DEV),
+                     dec.to(DEV), all_query_context_hidden_states=pk[2], all_query_context_ids_unflat=pk[3],
+                     topk_log_probs=pk[1])
+    assert torch.equal(pk_again[0], pk[0])
+    model.settings["packed_states"] = False                  # padded FiD states on request (the reference's layout)
+    padded = model(uid.to(DEV), q_bert.to(DEV), q_types.to(DEV), None, q_t5.to(DEV), torch.tensor(q_len).to(DEV), dec.to(DEV))
+    del model.settings["packed_states"]
+    assert padded[2].dim() == 3 and padded[2].shape[0] == bsz
+    assert (padded[0].float()[live] - lm_logits.float()[live]).abs().max().item() < tol
 
     # ---- evaluation decoding (search_strategy.py) through the real model: greedy tokens equal a greedy
     # decode of the oracle reader wherever the oracle's top-2 logit margin exceeds the 16-bit tolerance
