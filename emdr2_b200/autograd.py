@@ -82,7 +82,7 @@ def _weight_grad(dy, x, sink=None):
 def _bias_grad(dy, sink=None):
     out = sink if sink is not None else torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
     lib = _lib.load()
-    with torch.cuda.device(dy.device):
+    with ops._OnDevice(dy.device):
         _lib.check(lib.emdr2_colsum(_DT[dy.dtype], ops._ptr(dy), dy.stride(0), ops._ptr(out), dy.shape[0],
                                     dy.shape[1], ops._stream(dy.device)), "emdr2_colsum")
     return None if sink is not None else out.to(dy.dtype)
@@ -252,7 +252,7 @@ class _LayerNormFn(torch.autograd.Function):
         dgamma = _sink(gp) if sunk else torch.zeros(h, dtype=torch.float32, device=x.device)
         dbeta = _sink(bp) if sunk else torch.zeros(h, dtype=torch.float32, device=x.device)
         lib = _lib.load()
-        with torch.cuda.device(x.device):
+        with ops._OnDevice(x.device):
             _lib.check(lib.emdr2_layernorm_bwd(
                 _DT[x.dtype], ops._ptr(dy), dy.stride(0), ops._ptr(x), x.stride(0), ops._ptr(gamma),
                 ops._ptr(mean), ops._ptr(rstd), None, 0, ops._ptr(dx), dx.stride(0), ops._ptr(dgamma),
@@ -276,7 +276,7 @@ def _attention_bwd(q, k, v, o, dout, dq, dk, dv, batch, heads, sq, sk, q_pad, k_
     lib = _lib.load()
     p = ops._ptr
     drop = dropout.c_args() if dropout is not None else (ctypes.c_float(0.0), ctypes.c_uint64(0), ctypes.c_uint64(0), None)
-    with torch.cuda.device(q.device):
+    with ops._OnDevice(q.device):
         _lib.check(lib.emdr2_attention_bwd_dropout(
             _DT[q.dtype], p(q), q.stride(0), p(k), k.stride(0), p(v), v.stride(0), p(o), o.stride(0),
             p(dout), dout.stride(0), p(dq), dq.stride(0), p(dk), dk.stride(0), p(dv), dv.stride(0),
@@ -521,7 +521,7 @@ class _EmbeddingFn(torch.autograd.Function):
         ids2 = ids.to(torch.int64).contiguous()
         ty2 = None if types is None else types.to(torch.int64).contiguous()
         lib = _lib.load()
-        with torch.cuda.device(dev):
+        with ops._OnDevice(dev):
             _lib.check(lib.emdr2_embedding_bwd(
                 _DT[dtype], ops._ptr(dx), ops._ptr(ids2), ops._ptr(ty2), ops._ptr(dword), ops._ptr(dpos),
                 ops._ptr(dtyp), ids2.numel(), ids2.shape[-1], wshape[1], wshape[0],
@@ -558,7 +558,7 @@ class _TokenLogprobFn(torch.autograd.Function):
         gg = g.to(torch.float32).reshape(-1).contiguous()
         dl = torch.empty((l2.shape[0], vocab), dtype=logits.dtype, device=logits.device)
         lib = _lib.load()
-        with torch.cuda.device(logits.device):
+        with ops._OnDevice(logits.device):
             _lib.check(lib.emdr2_token_logprob_bwd(
                 _DT[logits.dtype], ops._ptr(l2), max(vocab, l2.stride(0)), ops._ptr(lab), ops._ptr(lse.reshape(-1).contiguous()),
                 ops._ptr(gg), ops._ptr(dl), vocab, l2.shape[0], vocab, ops._stream(logits.device)),

@@ -17,7 +17,28 @@ def _ptr(t):
 
 
 def _stream(device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """Raw handle of the calling thread's current stream on `device` (no Stream object: this runs once per launch)."""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(device.index if device.index is not None
+                                                              else torch.cuda.current_device()))
+
+
+class _OnDevice(object):
+    """`with torch.cuda.device(d)` only when d is not already current (the usual case: one device per process,
+    one launch = one of these): entering the real context manager costs more host time than the launch itself."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        idx = device.index
+        self.ctx = None if (idx is None or idx == torch.cuda.current_device()) else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def _check_2d(name, t, dtype, device):
@@ -58,7 +79,7 @@ def linear(x, weight, bias=None, gelu=False, residual=None, out=None):
         flags |= GEMM_RESIDUAL
         ldr = residual.stride(0)
     lib = _lib.load()
-    with torch.cuda.device(device):
+    with _OnDevice(device):
         _lib.check(lib.emdr2_gemm(_DTYPES[dtype], _ptr(x), x.stride(0) if m > 1 else max(k, x.stride(0)),
                                   _ptr(weight), weight.stride(0) if n > 1 else max(k, weight.stride(0)),
                                   _ptr(out), out.stride(0) if m > 1 else max(n, out.stride(0)),
@@ -97,7 +118,7 @@ def dropout_add(y, residual, spec, out=None):
         out = torch.empty((rows, cols), dtype=dtype, device=device)
     _check_2d("out", out, dtype, device)
     lib = _lib.load()
-    with torch.cuda.device(device):
+    with _OnDevice(device):
         _lib.check(lib.emdr2_dropout_add(
             _DTYPES[dtype], _ptr(y), max(cols, y.stride(0)), _ptr(residual),
             0 if residual is None else max(cols, residual.stride(0)), _ptr(out), max(cols, out.stride(0)), rows, cols,
@@ -141,7 +162,7 @@ def attention(q, k, v, batch, heads, sq, sk, q_pad=None, k_pad=None, causal=Fals
         scale = 1.0 / 8.0
     lib = _lib.load()
     drop = dropout.c_args() if dropout is not None else (ctypes.c_float(0.0), ctypes.c_uint64(0), ctypes.c_uint64(0), None)
-    with torch.cuda.device(device):
+    with _OnDevice(device):
         _lib.check(lib.emdr2_attention_fwd_dropout(
             _DTYPES[dtype], _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
             _ptr(out), out.stride(0), batch, heads, sq, sk, _ptr(masks[0]), _ptr(masks[1]),
@@ -171,7 +192,7 @@ def attention_varlen(q, k, v, heads, items, n_items, scale=0.125, out=None, out_
     if items.dtype != torch.int32 or items.device != device or not items.is_contiguous():
         raise ValueError("items must be a contiguous int32 tensor on %s" % (device,))
     lib = _lib.load()
-    with torch.cuda.device(device):
+    with _OnDevice(device):
         _lib.check(lib.emdr2_attention_varlen_fwd(
             _DTYPES[dtype], _ptr(q), q.stride(0), q.shape[0], _ptr(k), k.stride(0), _ptr(v), v.stride(0), k.shape[0],
             _ptr(out), out.stride(0), out.shape[0], heads, _ptr(items), int(n_items), float(scale), _ptr(lse),
@@ -194,7 +215,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None, return_stats=False):
     mean = torch.empty(rows, dtype=torch.float32, device=device) if return_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=device) if return_stats else None
     lib = _lib.load()
-    with torch.cuda.device(device):
+    with _OnDevice(device):
         _lib.check(lib.emdr2_layernorm_fwd(
             _DTYPES[dtype], _ptr(x), max(h, x.stride(0)), _ptr(gamma.contiguous()), _ptr(beta.contiguous()),
             _ptr(out), max(h, out.stride(0)), rows, h, float(eps), _ptr(mean), _ptr(rstd), _stream(device)),
@@ -221,7 +242,7 @@ def embedding(ids, word, pos, types=None, type_emb=None, seq=None, pos_ids=None)
         types = types.to(device=device, dtype=torch.int64).contiguous()
     out = torch.empty((tokens, h), dtype=dtype, device=device)
     lib = _lib.load()
-    with torch.cuda.device(device):
+    with _OnDevice(device):
         _lib.check(lib.emdr2_embedding_fwd_pos(
             _DTYPES[dtype], _ptr(ids), _ptr(types), _ptr(word.contiguous()), _ptr(pos.contiguous()),
             _ptr(type_emb.contiguous()) if type_emb is not None else None, _ptr(out), tokens, int(seq), h,
@@ -247,7 +268,7 @@ def token_logprob(logits, labels):
     lp = torch.empty(rows, dtype=torch.float32, device=device)
     lse = torch.empty(rows, dtype=torch.float32, device=device)
     lib = _lib.load()
-    with torch.cuda.device(device):
+    with _OnDevice(device):
         _lib.check(lib.emdr2_token_logprob(_DTYPES[dtype], _ptr(l2), max(vocab, l2.stride(0)), _ptr(lab),
                                            _ptr(lp), _ptr(lse), rows, vocab, _stream(device)),
                    "emdr2_token_logprob")
@@ -345,7 +366,7 @@ def gemm_ex(a, b, a_mn=False, b_mn=False, out=None, bias=None, gelu=False, resid
         return t.stride(0) if t.shape[0] > 1 else max(inner, t.stride(0))
 
     lib = _lib.load()
-    with torch.cuda.device(device):
+    with _OnDevice(device):
         _lib.check(lib.emdr2_gemm_ex(
             _DTYPES[dtype], _ptr(a), ld(a, a.shape[1]), 1 if a_mn else 0, _ptr(b), ld(b, b.shape[1]),
             1 if b_mn else 0, _ptr(out), ld(out, n), _ptr(bias), _ptr(aux), ld_aux, _ptr(pre), ld_pre,
