@@ -83,10 +83,20 @@ static std::atomic<int> g_gemm_pair{[] {
   return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
 }()};
 
+// > 0: persistent GEMM grids use at most this many CTAs (SMs).  A trainer that overlaps NCCL all-reduces with the
+// backward pass sets it to sm_count - (NCCL's CTAs): a persistent grid that asks for ALL SMs while a few are held by a
+// collective kernel runs its last CTAs as a second wave and takes up to twice as long.
+static std::atomic<int> g_gemm_max_ctas{0};
+
 extern "C" {
 
 int emdr2_ops_set_option(const char* name, int64_t value) {
   if (!name) return fail(EMDR2_EINVAL, "NULL option name");
+  if (strcmp(name, "gemm_max_ctas") == 0) {
+    if (value < 0 || value > 4096) return fail(EMDR2_EINVAL, "gemm_max_ctas takes 0 (all SMs) or a CTA count");
+    g_gemm_max_ctas.store(static_cast<int>(value), std::memory_order_relaxed);
+    return EMDR2_OK;
+  }
   if (strcmp(name, "gemm_pair") == 0) {
     if (value < 0 || value > 2) return fail(EMDR2_EINVAL, "gemm_pair takes 0 (off), 1 (on) or 2 (auto)");
     g_gemm_pair.store(static_cast<int>(value), std::memory_order_relaxed);
@@ -99,6 +109,10 @@ int emdr2_ops_get_option(const char* name, int64_t* out_value) {
   if (!name || !out_value) return fail(EMDR2_EINVAL, "NULL argument");
   if (strcmp(name, "gemm_pair") == 0) {
     *out_value = g_gemm_pair.load(std::memory_order_relaxed);
+    return EMDR2_OK;
+  }
+  if (strcmp(name, "gemm_max_ctas") == 0) {
+    *out_value = g_gemm_max_ctas.load(std::memory_order_relaxed);
     return EMDR2_OK;
   }
   return fail(EMDR2_EINVAL, "unknown option '%s'", name);
@@ -190,11 +204,13 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
   ga.bias = bias;
   ga.out32 = accum ? static_cast<float*>(d) : nullptr;
   const uint32_t work = ga.tiles_m * ga.tiles_n * ga.splits;
-  const int grid = static_cast<int>(work < static_cast<uint32_t>(info.sm_count) ? work : info.sm_count);
+  const int cap = g_gemm_max_ctas.load(std::memory_order_relaxed);
+  const int sms = (cap > 0 && cap < info.sm_count) ? cap : info.sm_count;
+  const int grid = static_cast<int>(work < static_cast<uint32_t>(sms) ? work : sms);
   ScopedTimer timer(EMDR2_KIND_GEMM, static_cast<cudaStream_t>(cuda_stream), 2.0 * m * n * k);
   if (use_pair) {
     ga.idesc = emdr2::ptx::instr_desc_f16(dtype == EMDR2_DTYPE_BF16 ? 1 : 0, 2 * emdr2::kGemmBM, emdr2::kGemmBN);
-    const int pairs = info.sm_count / 2;
+    const int pairs = sms / 2;
     CUDA_TRY(emdr2::launch_gemm_pair(ta, tb, td, tr, tp, ga, dtype == EMDR2_DTYPE_BF16, 2 * pairs,
                                      static_cast<cudaStream_t>(cuda_stream)));
     return EMDR2_OK;

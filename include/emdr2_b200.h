@@ -330,6 +330,8 @@ EMDR2_API int emdr2_format_passages_flat(int32_t bsz, int32_t k_keep, const int6
  * CTA per 128 x 256 tile; 2 (default) = only where that is measured to win (residual / aux epilogues
  * over >= 100 k rows); 0 = never.  Results are bit-identical between the two kernels (same products, same fp32
  * accumulation order per element). */
+/* "gemm_max_ctas": > 0 caps the persistent GEMM grids at that many CTAs (0 = one per SM): leave SMs to a collective
+ * kernel that overlaps with the backward pass instead of running the grid's last CTAs as a second wave. */
 EMDR2_API int emdr2_ops_set_option(const char* name, int64_t value);
 EMDR2_API int emdr2_ops_get_option(const char* name, int64_t* out_value);
 
