@@ -42,17 +42,17 @@ int fail(int code, const char* fmt, ...) {
 const char* last_error() { return g_last_error.c_str(); }
 
 int make_tmap_2d(CUtensorMap* out, int dtype, const void* base, uint64_t rows, uint64_t cols,
-                 uint64_t ld, uint32_t box_rows) {
+                 uint64_t ld, uint32_t box_rows, bool half_width) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(EMDR2_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t gdim[2] = {cols, rows};
   const cuuint64_t gstride[1] = {ld * 2};
-  const cuuint32_t box[2] = {64u, box_rows};
+  const cuuint32_t box[2] = {half_width ? 32u : 64u, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt =
       dtype == EMDR2_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   half_width ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(EMDR2_ECUDA,

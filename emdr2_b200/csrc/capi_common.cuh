@@ -15,8 +15,9 @@ const char* last_error();
 
 // 2-D row-major [rows, cols] 16-bit tensor with a row pitch of `ld` elements; box = [box_rows, 64
 // columns], 128-byte swizzle, out-of-bounds elements read as zero / are clipped on store.
+// half_width: box = [box_rows, 32 columns] with the 64-byte swizzle instead.
 int make_tmap_2d(CUtensorMap* out, int dtype, const void* base, uint64_t rows, uint64_t cols,
-                 uint64_t ld, uint32_t box_rows);
+                 uint64_t ld, uint32_t box_rows, bool half_width = false);
 
 // 3-D view [batch, rows, cols] of a row-major 16-bit buffer: element (b, r, c) at
 // base + (b * rows + r) * ld + c.  Box = [1, box_rows, 64 columns], 128-byte swizzle.

@@ -83,6 +83,14 @@ static std::atomic<int> g_gemm_pair{[] {
   return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
 }()};
 
+// Sixteen epilogue warps (gemm.cu, kWide) for the one-CTA kernel's write-only epilogues (no aux tile, no fp32
+// accumulation).  0: never; 1: where the epilogue has arithmetic to hide (GeLU, pre-activation output) — measured
+// +16 % there and -8 % on bias-only epilogues (profiles/README.md, r2B); 2: whenever eligible.
+static std::atomic<int> g_gemm_wide{[] {
+  const char* e = getenv("EMDR2_GEMM_WIDE");
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+}()};
+
 // > 0: persistent GEMM grids use at most this many CTAs (SMs).  A trainer that overlaps NCCL all-reduces with the
 // backward pass sets it to sm_count - (NCCL's CTAs): a persistent grid that asks for ALL SMs while a few are held by a
 // collective kernel runs its last CTAs as a second wave and takes up to twice as long.
@@ -97,6 +105,11 @@ int emdr2_ops_set_option(const char* name, int64_t value) {
     g_gemm_max_ctas.store(static_cast<int>(value), std::memory_order_relaxed);
     return EMDR2_OK;
   }
+  if (strcmp(name, "gemm_wide") == 0) {
+    if (value < 0 || value > 2) return fail(EMDR2_EINVAL, "gemm_wide takes 0 (off), 1 (auto) or 2 (whenever eligible)");
+    g_gemm_wide.store(static_cast<int>(value), std::memory_order_relaxed);
+    return EMDR2_OK;
+  }
   if (strcmp(name, "gemm_pair") == 0) {
     if (value < 0 || value > 2) return fail(EMDR2_EINVAL, "gemm_pair takes 0 (off), 1 (on) or 2 (auto)");
     g_gemm_pair.store(static_cast<int>(value), std::memory_order_relaxed);
@@ -107,6 +120,10 @@ int emdr2_ops_set_option(const char* name, int64_t value) {
 
 int emdr2_ops_get_option(const char* name, int64_t* out_value) {
   if (!name || !out_value) return fail(EMDR2_EINVAL, "NULL argument");
+  if (strcmp(name, "gemm_wide") == 0) {
+    *out_value = g_gemm_wide.load(std::memory_order_relaxed);
+    return EMDR2_OK;
+  }
   if (strcmp(name, "gemm_pair") == 0) {
     *out_value = g_gemm_pair.load(std::memory_order_relaxed);
     return EMDR2_OK;
@@ -170,6 +187,10 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
   const bool pair_wins = has_aux && m >= 100000;
   const bool use_pair = (pair_mode == 1 || (pair_mode == 2 && pair_wins)) && !a_mn && !b_mn && !accum &&
                         splits == 1 && info.sm_count >= 2 && pair_tiles >= 2 * (info.sm_count / 2);
+  // write-only epilogues of the one-CTA kernel: sixteen epilogue warps, 32-column output boxes
+  const int wide_mode = g_gemm_wide.load(std::memory_order_relaxed);
+  const bool wide = !use_pair && !a_mn && !accum && !has_aux && splits == 1 &&
+                    (wide_mode == 2 || (wide_mode == 1 && (flags & (EMDR2_GEMM_GELU | EMDR2_GEMM_PREACT)) != 0));
   // K-major operand: [rows, k] with box rows x 64; MN-major: [k, rows] with 64 x 64 boxes
   rc = a_mn ? make_tmap_2d(&ta, dtype, a, k, m, lda, 64) : make_tmap_2d(&ta, dtype, a, m, k, lda, emdr2::kGemmBM);
   if (rc != EMDR2_OK) return rc;
@@ -178,14 +199,14 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
   if (rc != EMDR2_OK) return rc;
   if (accum) {
     td = tb;   // no 16-bit output map needed; any valid descriptor fills the unused slots
-  } else if ((rc = make_tmap_2d(&td, dtype, d, m, n, ldd, emdr2::kGemmBM)) != EMDR2_OK) {
+  } else if ((rc = make_tmap_2d(&td, dtype, d, m, n, ldd, emdr2::kGemmBM, wide)) != EMDR2_OK) {
     return rc;
   }
   tr = td;
   tp = td;
   if (has_aux && (rc = make_tmap_2d(&tr, dtype, aux, m, n, ld_aux, emdr2::kGemmBM)) != EMDR2_OK) return rc;
   if ((flags & EMDR2_GEMM_PREACT) &&
-      (rc = make_tmap_2d(&tp, dtype, preact, m, n, ld_preact, emdr2::kGemmBM)) != EMDR2_OK)
+      (rc = make_tmap_2d(&tp, dtype, preact, m, n, ld_preact, emdr2::kGemmBM, wide)) != EMDR2_OK)
     return rc;
   emdr2::GemmArgs ga;
   ga.M = m;
@@ -215,7 +236,7 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
                                      static_cast<cudaStream_t>(cuda_stream)));
     return EMDR2_OK;
   }
-  CUDA_TRY(emdr2::launch_gemm(ta, tb, td, tr, tp, ga, dtype == EMDR2_DTYPE_BF16, a_mn != 0, b_mn != 0, grid,
+  CUDA_TRY(emdr2::launch_gemm(ta, tb, td, tr, tp, ga, dtype == EMDR2_DTYPE_BF16, a_mn != 0, b_mn != 0, wide, grid,
                               static_cast<cudaStream_t>(cuda_stream)));
   return EMDR2_OK;
 }

@@ -47,6 +47,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 
+template <int kRegs>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -72,8 +81,16 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // [k, n] row-major, "MN-major"): its tile is fetched as 64x64-element boxes (one per 64-wide MN atom,
 // 8 KiB apart) and consumed through an MN-major UMMA descriptor — this is how the backward products
 // dX = dY.W and dW = dY^T.X read the forward's tensors without any transpose in memory.
-template <bool kBf16, bool kAMN, bool kBMN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+//
+// kWide: SIXTEEN epilogue warps (4 TMEM lane quadrants x 4 column quarters of the tile) instead of eight, for the
+// epilogues that only write (bias / GeLU / pre-activation; no aux tile, no fp32 accumulation).  The GeLU epilogue is
+// a dependent rcp -> polynomial -> ex2 chain of ~12 instructions per element: with two warps per scheduler it ran at
+// IPC 0.4 and took longer than the tile's MMAs at K = 768 (ncu: tensor pipe 58 %, the MMA thread polling
+// tmem_empty); four warps per scheduler hide that latency.  Each quarter stages 32 columns at a time through an
+// 8 KiB box (128 rows x 64 B, 64-byte swizzle; tmap_d / tmap_p carry 32-column boxes), so the four boxes fit in the
+// space of the narrow variant's two and the operand ring keeps its four stages.
+template <bool kBf16, bool kAMN, bool kBMN, bool kWide>
+__global__ void __launch_bounds__(kWide ? kGemmWideThreads : kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
             const __grid_constant__ CUtensorMap tmap_p, const GemmArgs a) {
@@ -99,7 +116,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bars->tmem_full[b]), 1);
-      mbar_init(smem_u32(&bars->tmem_empty[b]), 8);
+      mbar_init(smem_u32(&bars->tmem_empty[b]), kWide ? 16 : 8);
       mbar_init(smem_u32(&bars->res_full[b]), 1);
     }
     fence_mbar_init();
@@ -120,6 +137,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
+  if constexpr (kWide) {
+    // TMA / MMA / allocator / spare warps hand registers to the epilogue warps: the pool is 640 x 96 registers,
+    // 128 x 56 + 512 x 104 fits
+    if (warp < 4) reg_dealloc<56>();
+  }
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
@@ -190,6 +212,103 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         mma_commit(smem_u32(&bars->tmem_full[buf]));
       }
     }
+  } else if (kWide && warp >= 4) {
+    // ===================================================== epilogue, sixteen warps (write-only epilogues)
+    reg_alloc<104>();
+    const uint32_t quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const uint32_t cq = (warp - 4) >> 2;     // column quarter of the tile: columns [cq * 64, cq * 64 + 64)
+    const uint32_t row = quad * 32 + lane;   // tile row == TMEM lane
+    const uint32_t box_off = off_out + cq * (kGemmBM * 32 * 2);
+    uint8_t* box_row = smem + box_off + row * 64u;
+    const uint32_t swz = (row >> 1) & 3u;    // 64-byte swizzle: 16-byte slot index ^= address bits [7, 9)
+    const bool issuer = quad == 0 && lane == 0;
+    const uint32_t bar_id = 1 + cq;
+    const bool has_bias = (a.flags & kGemmBias) != 0;
+    const bool has_gelu = (a.flags & kGemmGelu) != 0;
+    const bool store_pre = (a.flags & kGemmPreact) != 0;
+    const uint16_t* bias = static_cast<const uint16_t*>(a.bias);
+    const uint32_t col0 = cq * 64;
+
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < num_work; t += gridDim.x, ++it) {   // splits == 1: work item == tile
+      const uint32_t buf = it & 1;
+      const uint32_t m0 = (t / a.tiles_n) * kGemmBM;
+      const uint32_t n0 = (t % a.tiles_n) * kGemmBN;
+      if (has_bias) {   // the first eight epilogue warps stage the tile's 256 bias values
+        const uint32_t e = threadIdx.x - 128;
+        if (e < kGemmBN) bars->bias_stage[buf][e] = n0 + e < a.N ? bias[n0 + e] : static_cast<uint16_t>(0);
+      }
+      mbar_wait(smem_u32(&bars->tmem_full[buf]), (it >> 1) & 1);
+      tc_fence_after();
+      if (has_bias) named_bar_sync(5, kGemmWideThreads - 128);
+      const uint32_t t_addr = tmem_base + ((quad * 32) << 16) + buf * kGemmBN + col0;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {       // the quarter's two 32-column halves
+        const uint32_t gcol = n0 + col0 + hh * 32;
+        const bool live = gcol < a.N;
+        uint32_t v[32];
+        if (live) {
+          tmem_ld_32x32b_x32(t_addr + hh * 32, v);
+          tmem_ld_wait();
+        }
+        if (hh == 1) {   // this warp has read everything it needs from the accumulator buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
+        }
+        if (!live) continue;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        if (has_bias) {   // columns past N read the zeros staged above
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 bv = *reinterpret_cast<const uint4*>(&bars->bias_stage[buf][col0 + hh * 32 + g * 8]);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack2<kBf16>(bw[j]);
+              x[g * 8 + 2 * j] += f.x;
+              x[g * 8 + 2 * j + 1] += f.y;
+            }
+          }
+        }
+        if (store_pre) {
+          // training forward of the h -> 4h projection: the pre-activation (bias added) goes out first
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, 128);       // the box's previous store has drained it
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(box_row + ((static_cast<uint32_t>(g) ^ swz) * 16u)) =
+                make_uint4(pack2<kBf16>(x[g * 8], x[g * 8 + 1]), pack2<kBf16>(x[g * 8 + 2], x[g * 8 + 3]),
+                           pack2<kBf16>(x[g * 8 + 4], x[g * 8 + 5]), pack2<kBf16>(x[g * 8 + 6], x[g * 8 + 7]));
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (issuer) {
+            tma_store_2d(&tmap_p, smem_base + box_off, static_cast<int32_t>(gcol), static_cast<int32_t>(m0));
+            tma_store_commit();
+          }
+        }
+        if (has_gelu) {   // arithmetic first: the previous store drains the box underneath it
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) gelu_erf_pair(x[j], x[j + 1]);
+        }
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(bar_id, 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(box_row + ((static_cast<uint32_t>(g) ^ swz) * 16u)) =
+              make_uint4(pack2<kBf16>(x[g * 8], x[g * 8 + 1]), pack2<kBf16>(x[g * 8 + 2], x[g * 8 + 3]),
+                         pack2<kBf16>(x[g * 8 + 4], x[g * 8 + 5]), pack2<kBf16>(x[g * 8 + 6], x[g * 8 + 7]));
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (issuer) {
+          tma_store_2d(&tmap_d, smem_base + box_off, static_cast<int32_t>(gcol), static_cast<int32_t>(m0));
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait<0>();
   } else if (warp >= 4) {
     // ===================================================== epilogue
     const uint32_t quad = warp & 3;          // TMEM lane quadrant this warp may read
@@ -407,38 +526,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
 }  // namespace
 
-template <bool kBf16, bool kAMN, bool kBMN>
+template <bool kBf16, bool kAMN, bool kBMN, bool kWide>
 cudaError_t prepare_one() {
-  return cudaFuncSetAttribute(gemm_kernel<kBf16, kAMN, kBMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(gemm_kernel<kBf16, kAMN, kBMN, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               kGemmSmemBytes);
 }
 
 cudaError_t gemm_prepare() {
   cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = prepare_one<true, false, false>();
-  if (e == cudaSuccess) e = prepare_one<true, false, true>();
-  if (e == cudaSuccess) e = prepare_one<true, true, true>();
-  if (e == cudaSuccess) e = prepare_one<false, false, false>();
-  if (e == cudaSuccess) e = prepare_one<false, false, true>();
-  if (e == cudaSuccess) e = prepare_one<false, true, true>();
+  if (e == cudaSuccess) e = prepare_one<true, false, false, false>();
+  if (e == cudaSuccess) e = prepare_one<true, false, true, false>();
+  if (e == cudaSuccess) e = prepare_one<true, true, true, false>();
+  if (e == cudaSuccess) e = prepare_one<false, false, false, false>();
+  if (e == cudaSuccess) e = prepare_one<false, false, true, false>();
+  if (e == cudaSuccess) e = prepare_one<false, true, true, false>();
+  if (e == cudaSuccess) e = prepare_one<true, false, false, true>();
+  if (e == cudaSuccess) e = prepare_one<true, false, true, true>();
+  if (e == cudaSuccess) e = prepare_one<false, false, false, true>();
+  if (e == cudaSuccess) e = prepare_one<false, false, true, true>();
   return e;
 }
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
                         const CUtensorMap& tmap_r, const CUtensorMap& tmap_p, const GemmArgs& args,
-                        bool bf16, bool a_mn, bool b_mn, int grid, cudaStream_t stream) {
-#define EMDR2_GEMM_LAUNCH(BF, AMN, BMN)                                                           \
-  gemm_kernel<BF, AMN, BMN><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(tmap_a, tmap_b, tmap_d, \
-                                                                           tmap_r, tmap_p, args)
+                        bool bf16, bool a_mn, bool b_mn, bool wide, int grid, cudaStream_t stream) {
+#define EMDR2_GEMM_LAUNCH(BF, AMN, BMN, WIDE)                                                                   \
+  gemm_kernel<BF, AMN, BMN, WIDE><<<grid, WIDE ? kGemmWideThreads : kGemmThreads, kGemmSmemBytes, stream>>>(    \
+      tmap_a, tmap_b, tmap_d, tmap_r, tmap_p, args)
   if (a_mn && !b_mn) return cudaErrorInvalidValue;   // not needed by any forward/backward product
+  if (wide && (a_mn || args.splits != 1 || (args.flags & (kGemmResidual | kGemmGeluBwd | kGemmAccumF32))))
+    return cudaErrorInvalidValue;                    // the wide epilogue only writes
   if (bf16) {
-    if (a_mn) EMDR2_GEMM_LAUNCH(true, true, true);
-    else if (b_mn) EMDR2_GEMM_LAUNCH(true, false, true);
-    else EMDR2_GEMM_LAUNCH(true, false, false);
+    if (a_mn) EMDR2_GEMM_LAUNCH(true, true, true, false);
+    else if (b_mn && wide) EMDR2_GEMM_LAUNCH(true, false, true, true);
+    else if (b_mn) EMDR2_GEMM_LAUNCH(true, false, true, false);
+    else if (wide) EMDR2_GEMM_LAUNCH(true, false, false, true);
+    else EMDR2_GEMM_LAUNCH(true, false, false, false);
   } else {
-    if (a_mn) EMDR2_GEMM_LAUNCH(false, true, true);
-    else if (b_mn) EMDR2_GEMM_LAUNCH(false, false, true);
-    else EMDR2_GEMM_LAUNCH(false, false, false);
+    if (a_mn) EMDR2_GEMM_LAUNCH(false, true, true, false);
+    else if (b_mn && wide) EMDR2_GEMM_LAUNCH(false, false, true, true);
+    else if (b_mn) EMDR2_GEMM_LAUNCH(false, false, true, false);
+    else if (wide) EMDR2_GEMM_LAUNCH(false, false, false, true);
+    else EMDR2_GEMM_LAUNCH(false, false, false, false);
   }
 #undef EMDR2_GEMM_LAUNCH
   return cudaGetLastError();
