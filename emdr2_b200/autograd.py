@@ -315,29 +315,82 @@ class _SelfAttentionFn(torch.autograd.Function):
 
 
 class _CrossAttentionFn(torch.autograd.Function):
-    """ctx = attention(q, k, v) with k | v the two column blocks of one [batch*sk, 2h] tensor."""
+    """ctx = attention(q, k, v) with k | v the two column blocks of one [batch*sk, 2h] tensor.
+
+    A long key axis with few (batch, head) pairs (FiD: 8 questions x 12 heads over 25 600 keys) is cut into `splits`
+    key ranges that run as extra batch entries in the forward AND the backward kernels: 96 CTAs walking 200 key
+    blocks each become ~800 work items.  Forward: partial outputs merged by their log-sum-exp weights; the saved lse
+    is the merged one.  Backward: every range sees the merged output / lse (so P is the global softmax), dK / dV
+    come out per range — the ranges partition the keys — and dQ is the sum of the ranges' partial dQ.  The dropout
+    mask plane is indexed by (range entry, head, query, key within the range) in both directions."""
 
     @staticmethod
     def forward(ctx, q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, dropout):
         h = heads * 64
         q_pad, k_pad = _u8(q_pad, q.device), _u8(k_pad, q.device)
         q_live, k_live = _u8(q_live, q.device), _u8(k_live, q.device)
-        out, lse = ops.attention(q, kv[:, :h], kv[:, h:], batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad,
-                                 scale=scale, return_lse=True, q_live=q_live, k_live=k_live, dropout=dropout)
+        splits = _cross_splits(batch, heads, sk)
+        if splits > 1:
+            q_pad, k_pad, q_live, k_live = _split_masks(q_pad, k_pad, q_live, k_live, batch, sk, splits)
+            out_s, lse_s = ops.attention(_rep_rows(q, batch, splits, sq), kv[:, :h], kv[:, h:], batch * splits, heads,
+                                         sq, sk // splits, q_pad=q_pad, k_pad=k_pad, scale=scale, return_lse=True,
+                                         q_live=q_live, k_live=k_live, dropout=dropout)
+            out, lse = _merge_splits(out_s, lse_s, batch, splits, heads, sq, q.dtype)
+        else:
+            out, lse = ops.attention(q, kv[:, :h], kv[:, h:], batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad,
+                                     scale=scale, return_lse=True, q_live=q_live, k_live=k_live, dropout=dropout)
         ctx.save_for_backward(q, kv, out, lse, q_pad, k_pad, q_live, k_live)
-        ctx.cfg = (batch, heads, sq, sk, scale, dropout)
+        ctx.cfg = (batch, heads, sq, sk, scale, dropout, splits)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         q, kv, out, lse, q_pad, k_pad, q_live, k_live = ctx.saved_tensors
-        batch, heads, sq, sk, scale, dropout = ctx.cfg
+        batch, heads, sq, sk, scale, dropout, splits = ctx.cfg
         h = heads * 64
         dout = _c(dout)
-        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
-        _attention_bwd(q, kv[:, :h], kv[:, h:], out, dout, dq, dkv[:, :h], dkv[:, h:], batch, heads, sq, sk,
-                       q_pad, k_pad, q_live, k_live, False, scale, lse, dropout)
+        dkv = torch.empty_like(kv)
+        if splits > 1:
+            dq_s = torch.empty((batch * splits * sq, h), dtype=q.dtype, device=q.device)
+            lse_s = lse.view(batch, 1, heads, sq).expand(batch, splits, heads, sq).contiguous()
+            _attention_bwd(_rep_rows(q, batch, splits, sq), kv[:, :h], kv[:, h:], _rep_rows(out, batch, splits, sq),
+                           _rep_rows(dout, batch, splits, sq), dq_s, dkv[:, :h], dkv[:, h:], batch * splits, heads, sq,
+                           sk // splits, q_pad, k_pad, q_live, k_live, False, scale, lse_s, dropout)
+            dq = dq_s.view(batch, splits, sq * h).sum(dim=1, dtype=torch.float32).to(q.dtype).view(batch * sq, h)
+        else:
+            dq = torch.empty_like(q)
+            _attention_bwd(q, kv[:, :h], kv[:, h:], out, dout, dq, dkv[:, :h], dkv[:, h:], batch, heads, sq, sk,
+                           q_pad, k_pad, q_live, k_live, False, scale, lse, dropout)
         return (dq, dkv) + (None,) * 10
+
+
+def _rep_rows(x, batch, splits, sq):
+    """[batch*sq, h] -> [batch*splits*sq, h]: every question's rows once per key range."""
+    h = x.shape[1]
+    return x.reshape(batch, 1, sq, h).expand(batch, splits, sq, h).reshape(batch * splits * sq, h)
+
+
+def _split_masks(q_pad, k_pad, q_live, k_live, batch, sk, splits):
+    """The masks of a key-split launch: per-query masks repeat for the ranges of a question, per-key masks are
+    re-cut.  The kernels want one live key block per entry, so block 0 of every range is marked live; in an
+    all-padding range its keys are still masked (-10000) and the range weighs exp(-10000) = 0."""
+    sk_s = sk // splits
+    q_pad = None if q_pad is None else q_pad.repeat_interleave(splits, dim=0)
+    q_live = None if q_live is None else q_live.repeat_interleave(splits, dim=0)
+    k_pad = None if k_pad is None else k_pad.reshape(batch * splits, sk_s)
+    if k_live is not None:
+        k_live = k_live.reshape(batch * splits, sk_s // 128).clone()
+        k_live[:, 0] = 1
+    return q_pad, k_pad, q_live, k_live
+
+
+def _merge_splits(out_s, lse_s, batch, splits, heads, sq, dtype):
+    """Partial outputs [batch*splits*sq, h] and their lse [batch*splits, heads, sq] -> merged output, merged lse."""
+    lse_s = lse_s.view(batch, splits, heads, sq)
+    lse = torch.logsumexp(lse_s, dim=1)                                          # fp32 [B, heads, sq]
+    w = torch.exp(lse_s - lse.unsqueeze(1)).permute(0, 1, 3, 2).unsqueeze(-1)    # [B, splits, sq, heads, 1]
+    merged = (out_s.view(batch, splits, sq, heads, 64).float() * w).sum(dim=1)
+    return merged.to(dtype).view(batch * sq, heads * 64), lse.contiguous()
 
 
 class _GroupedSelfAttentionFn(torch.autograd.Function):
@@ -433,43 +486,30 @@ def _cross_splits(batch, heads, sk):
     return best
 
 
-def _cross_attention_split(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, splits):
+def _cross_attention_split(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, splits, dropout=None):
     h = heads * 64
     dev = q.device
-    sk_s = sk // splits
-    q_rep = q.reshape(batch, 1, sq, h).expand(batch, splits, sq, h).reshape(batch * splits * sq, h)
-
-    def rep(m):          # per-query masks are shared by the ranges of a question
-        return None if m is None else _u8(m, dev).repeat_interleave(splits, dim=0)
-
-    k_pad_s = None if k_pad is None else _u8(k_pad, dev).reshape(batch * splits, sk_s)
-    k_live_s = None
-    if k_live is not None:
-        k_live_s = _u8(k_live, dev).reshape(batch * splits, sk_s // 128).clone()
-        k_live_s[:, 0] = 1                         # the kernel wants one live block per entry; an
-        #                                            all-padding range then weighs exp(-10000) = 0
-    out, lse = ops.attention(q_rep, kv[:, :h], kv[:, h:], batch * splits, heads, sq, sk_s, q_pad=rep(q_pad),
-                             k_pad=k_pad_s, scale=scale, return_lse=True, q_live=rep(q_live), k_live=k_live_s)
-    w = torch.softmax(lse.view(batch, splits, heads, sq), dim=1)              # fp32 [B, splits, heads, sq]
-    w = w.permute(0, 1, 3, 2).unsqueeze(-1)                                    # [B, splits, sq, heads, 1]
-    merged = (out.view(batch, splits, sq, heads, 64).float() * w).sum(dim=1)
-    return merged.to(q.dtype).view(batch * sq, h)
+    q_pad, k_pad, q_live, k_live = _split_masks(_u8(q_pad, dev), _u8(k_pad, dev), _u8(q_live, dev), _u8(k_live, dev),
+                                                batch, sk, splits)
+    out, lse = ops.attention(_rep_rows(q, batch, splits, sq), kv[:, :h], kv[:, h:], batch * splits, heads, sq,
+                             sk // splits, q_pad=q_pad, k_pad=k_pad, scale=scale, return_lse=True, q_live=q_live,
+                             k_live=k_live, dropout=dropout)
+    return _merge_splits(out, lse, batch, splits, heads, sq, q.dtype)[0]
 
 
 def cross_attention(q, kv, batch, heads, sq, sk, q_pad=None, k_pad=None, q_live=None, k_live=None, scale=0.125,
                     dropout_p=0.0, dropout=None):
+    """A long key axis runs key-split (see _CrossAttentionFn) with or without autograd; a dropout mask plane is then
+    indexed by (range entry, head, query, key within the range)."""
     drop = dropout if dropout is not None else _attn_spec(dropout_p, q.device, sk)
     if _needs_grad(q, kv):
         return _CrossAttentionFn.apply(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, drop)
     h = heads * 64
-    if drop is not None:         # a dropped-out pass keeps the mask plane of the unsplit key axis
-        return ops.attention(q, kv[:, :h], kv[:, h:], batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad, scale=scale,
-                             q_live=q_live, k_live=k_live, dropout=drop)
     splits = _cross_splits(batch, heads, sk)
     if splits > 1:
-        return _cross_attention_split(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, splits)
+        return _cross_attention_split(q, kv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, scale, splits, drop)
     return ops.attention(q, kv[:, :h], kv[:, h:], batch, heads, sq, sk, q_pad=q_pad, k_pad=k_pad, scale=scale,
-                         q_live=q_live, k_live=k_live)
+                         q_live=q_live, k_live=k_live, dropout=drop)
 
 
 def cross_attention_packed(q, kv, heads, plan, scale=0.125):

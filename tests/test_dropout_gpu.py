@@ -141,6 +141,53 @@ def test_cross_attention_with_dropout_forward_and_backward_vs_replayed_reference
     assert _rel(kv.grad[live_k], rkv.grad[live_k]) < 2 * RTOL[dtype]
 
 
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_key_split_cross_attention_trains_like_the_unsplit_reference(p):
+    """A long key axis (>= CROSS_SPLIT_MIN_KEYS) runs as key ranges in the forward AND backward kernels
+    (autograd._CrossAttentionFn): outputs merged by lse, dK / dV per range, dQ summed over the ranges.  The mask
+    plane of the split launch is (range entry, head, query, key within the range); the fp32 reference replays it."""
+    from emdr2_b200 import autograd as ag, dropout
+    dtype = torch.bfloat16
+    b, heads, sq, sk = 2, 2, 40, 4096
+    h = heads * 64
+    splits = ag._cross_splits(b, heads, sk)
+    assert splits > 1 and sk % (128 * splits) == 0
+    sk_s = sk // splits
+    g = torch.Generator().manual_seed(13)
+    q = (torch.randn(b * sq, h, generator=g) * 0.7).to(dtype).to(DEV).requires_grad_(True)
+    kv = (torch.randn(b * sk, 2 * h, generator=g) * 0.7).to(dtype).to(DEV).requires_grad_(True)
+    k_pad = torch.zeros(b, sk, dtype=torch.bool)
+    k_pad[0, 3000:] = True                    # the last two ranges of question 0 are all padding
+    k_pad[1, 129:700] = True
+    k_live = ~k_pad.view(b, sk // 128, 128).all(dim=2)
+    spec = _spec(p, sk) if p else None
+    if p:
+        keep = dropout.mask(spec, b * splits * heads * sq, sk_s).float()
+        keep = keep.view(b, splits, heads, sq, sk_s).permute(0, 2, 3, 1, 4).reshape(b * heads * sq, sk)
+    else:
+        keep = torch.ones(b * heads * sq, sk, device=DEV)
+    out = ag.cross_attention(q, kv, b, heads, sq, sk, k_pad=k_pad.to(DEV), k_live=k_live.to(DEV), scale=0.125,
+                             dropout=spec)
+    rq, rkv = q.detach().float().requires_grad_(True), kv.detach().float().requires_grad_(True)
+    mask = k_pad[:, None, :].expand(b, sq, sk)
+    want = _reference_attention(rq.view(b, sq, h), rkv[:, :h].reshape(b, sk, h), rkv[:, h:].reshape(b, sk, h), heads,
+                                mask.to(DEV), keep, dropout.keep_scale(p) if p else 1.0, 0.125).view(b * sq, h)
+    assert _rel(out, want) < RTOL[dtype]
+    gout = torch.randn(b * sq, h, generator=g).to(dtype).to(DEV)
+    out.backward(gout)
+    want.backward(gout.float())
+    live_k = (~k_pad).view(-1).to(DEV)
+    assert _rel(q.grad, rq.grad) < 2 * RTOL[dtype]
+    assert _rel(kv.grad[live_k], rkv.grad[live_k]) < 2 * RTOL[dtype]
+    # padding keys receive no gradient (their probability is exactly 0)
+    assert kv.grad[~live_k].float().abs().max().item() == 0.0
+    # the no-grad path takes the same split and, with the same spec, the same mask
+    with torch.no_grad():
+        again = ag.cross_attention(q.detach(), kv.detach(), b, heads, sq, sk, k_pad=k_pad.to(DEV),
+                                   k_live=k_live.to(DEV), scale=0.125, dropout=spec)
+    assert torch.equal(again, out.detach())
+
+
 def test_modules_apply_dropout_in_training_mode_only_and_deterministically():
     """train(): embedding, attention-probability and bias-dropout-add masks are drawn (different outputs from
     eval, identical under the same seed, gradients flow); eval(): exactly the dropout-free path.
