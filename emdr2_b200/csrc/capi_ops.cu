@@ -83,9 +83,9 @@ static std::atomic<int> g_gemm_pair{[] {
   return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
 }()};
 
-// Sixteen epilogue warps (gemm.cu, kWide) for the one-CTA kernel's write-only epilogues (no aux tile, no fp32
-// accumulation).  0: never; 1: where the epilogue has arithmetic to hide (GeLU, pre-activation output) — measured
-// +16 % there and -8 % on bias-only epilogues (profiles/README.md, r2B); 2: whenever eligible.
+// Sixteen epilogue warps (gemm.cu, kEpi 1 / 2) for the one-CTA kernel's 16-bit outputs.  0: never; 1: where the
+// epilogue has arithmetic to hide (GeLU, pre-activation output, GeLU backward) — measured +16 % on GeLU and -8 % on
+// bias-only epilogues (profiles/README.md, r2B); 2: whenever eligible.
 static std::atomic<int> g_gemm_wide{[] {
   const char* e = getenv("EMDR2_GEMM_WIDE");
   return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
@@ -189,8 +189,11 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
                         splits == 1 && info.sm_count >= 2 && pair_tiles >= 2 * (info.sm_count / 2);
   // write-only epilogues of the one-CTA kernel: sixteen epilogue warps, 32-column output boxes
   const int wide_mode = g_gemm_wide.load(std::memory_order_relaxed);
-  const bool wide = !use_pair && !a_mn && !accum && !has_aux && splits == 1 &&
-                    (wide_mode == 2 || (wide_mode == 1 && (flags & (EMDR2_GEMM_GELU | EMDR2_GEMM_PREACT)) != 0));
+  const bool wide_ok = !use_pair && !a_mn && !accum && splits == 1 && !(has_aux && (flags & EMDR2_GEMM_PREACT)) &&
+                       (wide_mode == 2 || (wide_mode == 1 && (flags & (EMDR2_GEMM_GELU | EMDR2_GEMM_PREACT |
+                                                                       EMDR2_GEMM_GELU_BWD)) != 0));
+  const int epi = !wide_ok ? 0 : has_aux ? 2 : 1;
+  const bool wide = epi == 1;   // 32-column output boxes
   // K-major operand: [rows, k] with box rows x 64; MN-major: [k, rows] with 64 x 64 boxes
   rc = a_mn ? make_tmap_2d(&ta, dtype, a, k, m, lda, 64) : make_tmap_2d(&ta, dtype, a, m, k, lda, emdr2::kGemmBM);
   if (rc != EMDR2_OK) return rc;
@@ -236,7 +239,7 @@ int emdr2_gemm_ex(int dtype, const void* a, int64_t lda, int a_mn, const void* b
                                      static_cast<cudaStream_t>(cuda_stream)));
     return EMDR2_OK;
   }
-  CUDA_TRY(emdr2::launch_gemm(ta, tb, td, tr, tp, ga, dtype == EMDR2_DTYPE_BF16, a_mn != 0, b_mn != 0, wide, grid,
+  CUDA_TRY(emdr2::launch_gemm(ta, tb, td, tr, tp, ga, dtype == EMDR2_DTYPE_BF16, a_mn != 0, b_mn != 0, epi, grid,
                               static_cast<cudaStream_t>(cuda_stream)));
   return EMDR2_OK;
 }

@@ -17,7 +17,7 @@ struct GemmBars {
   uint64_t empty[kGemmStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t res_full[2];    // residual box landed in the staging buffer of column half 0 / 1
+  uint64_t res_full[4];    // aux box landed in the staging buffer of column half 0 / 1 (kEpi 2: quarter 0..3)
   uint32_t tmem_base;
   uint32_t pad_[3];
   // Bias slice of the current tile, double-buffered by tile parity: fetched by the epilogue threads
@@ -60,23 +60,6 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// d/dx GeLU(x) = Phi(x) + x phi(x), same erf approximation as gelu_erf.
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));   // exp(-x^2/2)
-  const float q = 0.5f * poly * e;                 // 1 - Phi(|x|)
-  const float cdf = x >= 0.f ? 1.0f - q : q;
-  return fmaf(x * 0.3989422804014327f, e, cdf);    // + x * exp(-x^2/2) / sqrt(2 pi)
-}
-
 // kAMN / kBMN: that operand is stored with the contraction index as the ROW index ([k, m] resp.
 // [k, n] row-major, "MN-major"): its tile is fetched as 64x64-element boxes (one per 64-wide MN atom,
 // 8 KiB apart) and consumed through an MN-major UMMA descriptor — this is how the backward products
@@ -89,16 +72,25 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // tmem_empty); four warps per scheduler hide that latency.  Each quarter stages 32 columns at a time through an
 // 8 KiB box (128 rows x 64 B, 64-byte swizzle; tmap_d / tmap_p carry 32-column boxes), so the four boxes fit in the
 // space of the narrow variant's two and the operand ring keeps its four stages.
-template <bool kBf16, bool kAMN, bool kBMN, bool kWide>
-__global__ void __launch_bounds__(kWide ? kGemmWideThreads : kGemmThreads, 1)
+//
+// kEpi: 0 = eight epilogue warps (everything, incl. fp32 accumulation); 1 = sixteen, write-only epilogues; 2 = sixteen
+// with an aux tile (residual / GeLU backward): THREE operand stages and four 16 KiB staging boxes (one 128 x 64
+// chunk per quarter per tile), the aux box of the quarter's NEXT tile fetched by TMA into the box as soon as this
+// tile's store has drained it — a whole tile ahead of its use, where the eight-warp variant serialises store drain
+// -> aux load -> use for every chunk (dU = (dA . W2) * GeLU'(u) ran at 0.6 PFLOP/s, epilogue-bound).
+template <bool kBf16, bool kAMN, bool kBMN, int kEpi>
+__global__ void __launch_bounds__(kEpi != 0 ? kGemmWideThreads : kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
             const __grid_constant__ CUtensorMap tmap_p, const GemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  constexpr uint32_t off_out = kGemmStages * kGemmStageBytes;
-  constexpr uint32_t off_bar = off_out + kGemmOutBytes;
+  constexpr bool kWide = kEpi != 0;
+  constexpr int kStages = kEpi == 2 ? kGemmAuxStages : kGemmStages;
+  constexpr uint32_t off_out = kStages * kGemmStageBytes;
+  constexpr uint32_t off_bar = off_out + (kEpi == 2 ? kGemmAuxOutBytes : kGemmOutBytes);
+  static_assert(off_bar + kGemmBarBytes + 1024 <= kGemmSmemBytes, "shared memory budget");
   GemmBars* bars = reinterpret_cast<GemmBars*>(smem + off_bar);
   const uint32_t smem_base = smem_u32(smem);
 
@@ -110,15 +102,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const uint32_t num_work = num_tiles * a.splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGemmStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(&bars->full[s]), 1);
       mbar_init(smem_u32(&bars->empty[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bars->tmem_full[b]), 1);
       mbar_init(smem_u32(&bars->tmem_empty[b]), kWide ? 16 : 8);
-      mbar_init(smem_u32(&bars->res_full[b]), 1);
     }
+    for (int b = 0; b < 4; ++b) mbar_init(smem_u32(&bars->res_full[b]), 1);
     fence_mbar_init();
     fence_proxy_async_smem();
   }
@@ -126,7 +118,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_d);
-    if (a.flags & kGemmResidual) prefetch_tmap(&tmap_r);
+    if (a.flags & (kGemmResidual | kGemmGeluBwd)) prefetch_tmap(&tmap_r);
   }
   if (warp == 2) {
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
@@ -172,7 +164,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           } else {
             tma_load_2d(sa + kGemmStageA, &tmap_b, fbar, k0, n0, kEvictLast);
           }
-          if (++stage == kGemmStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -204,7 +196,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             mma_f16_ss(d_tmem, adesc, bdesc, a.idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
           }
           mma_commit(smem_u32(&bars->empty[stage]));
-          if (++stage == kGemmStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -212,7 +204,133 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         mma_commit(smem_u32(&bars->tmem_full[buf]));
       }
     }
-  } else if (kWide && warp >= 4) {
+  } else if (kEpi == 2 && warp >= 4) {
+    // ===================================================== epilogue, sixteen warps, aux tile prefetched a tile ahead
+    reg_alloc<104>();
+    const uint32_t quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const uint32_t cq = (warp - 4) >> 2;     // column quarter of the tile: columns [cq * 64, cq * 64 + 64)
+    const uint32_t row = quad * 32 + lane;   // tile row == TMEM lane
+    const uint32_t stage_off = off_out + cq * (kGemmBM * 64 * 2);
+    uint8_t* stage_ptr = smem + stage_off;
+    const bool issuer = quad == 0 && lane == 0;
+    const uint32_t bar_id = 1 + cq;
+    const bool has_bias = (a.flags & kGemmBias) != 0;
+    const bool has_gelu = (a.flags & kGemmGelu) != 0;
+    const bool gelu_bwd = (a.flags & kGemmGeluBwd) != 0;
+    const uint16_t* bias = static_cast<const uint16_t*>(a.bias);
+    const uint32_t res_bar = smem_u32(&bars->res_full[cq]);
+    const uint32_t col0 = cq * 64;
+    uint32_t res_phase = 0;
+
+    auto chunk_live = [&](uint32_t t) { return (t % a.tiles_n) * kGemmBN + col0 < a.N; };
+    auto load_aux = [&](uint32_t t) {
+      mbar_arrive_expect_tx(res_bar, kGemmBM * 64 * 2);
+      tma_load_2d(smem_base + stage_off, &tmap_r, res_bar, static_cast<int32_t>((t % a.tiles_n) * kGemmBN + col0),
+                  static_cast<int32_t>((t / a.tiles_n) * kGemmBM), kEvictNormal);
+    };
+    // first tile at or after t whose chunk of this column quarter exists (ragged N); >= num_work if none
+    auto next_live = [&](uint32_t t) {
+      while (t < num_work && !chunk_live(t)) t += gridDim.x;
+      return t;
+    };
+    if (issuer) {
+      const uint32_t ft = next_live(blockIdx.x);
+      if (ft < num_work) load_aux(ft);
+    }
+
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < num_work; t += gridDim.x, ++it) {   // splits == 1: work item == tile
+      const uint32_t buf = it & 1;
+      const uint32_t m0 = (t / a.tiles_n) * kGemmBM;
+      const uint32_t n0 = (t % a.tiles_n) * kGemmBN;
+      if (has_bias) {
+        const uint32_t e = threadIdx.x - 128;
+        if (e < kGemmBN) bars->bias_stage[buf][e] = n0 + e < a.N ? bias[n0 + e] : static_cast<uint16_t>(0);
+      }
+      mbar_wait(smem_u32(&bars->tmem_full[buf]), (it >> 1) & 1);
+      tc_fence_after();
+      if (has_bias) named_bar_sync(5, kGemmWideThreads - 128);
+      const uint32_t gcol = n0 + col0;
+      const bool live = gcol < a.N;
+      const uint32_t t_addr = tmem_base + ((quad * 32) << 16) + buf * kGemmBN + col0;
+      if (live) {
+        mbar_wait(res_bar, res_phase);   // this chunk's aux box is in the staging box
+        res_phase ^= 1;
+      }
+      uint32_t packed[32];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {   // 32 accumulators in registers at a time
+        uint32_t v[32];
+        if (live) {
+          tmem_ld_32x32b_x32(t_addr + hh * 32, v);
+          tmem_ld_wait();
+        }
+        if (hh == 1) {   // this warp has read everything it needs from the accumulator buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
+        }
+        if (!live) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {   // 8 columns per group == one 16-byte slot
+          const int gg = hh * 4 + g;
+          const uint32_t phys = (static_cast<uint32_t>(gg) ^ (row & 7u)) * 16u;
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
+          if (has_bias) {   // columns past N read the zeros staged above
+            const uint4 bv = *reinterpret_cast<const uint4*>(&bars->bias_stage[buf][col0 + gg * 8]);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack2<kBf16>(bw[j]);
+              x[2 * j] += f.x;
+              x[2 * j + 1] += f.y;
+            }
+          }
+          if (has_gelu) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) gelu_erf_pair(x[j], x[j + 1]);
+          }
+          // out-of-range rows / columns of the aux box were zero-filled by the TMA load
+          const uint4 rv = *reinterpret_cast<const uint4*>(stage_ptr + row * 128u + phys);
+          const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2<kBf16>(rw[j]);
+            if (gelu_bwd) {   // aux = pre-activation u: dU = dA * GeLU'(u)
+              gelu_erf_grad_pair(f.x, f.y, x[2 * j], x[2 * j + 1]);
+            } else {
+              x[2 * j] += f.x;
+              x[2 * j + 1] += f.y;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) packed[gg * 4 + j] = pack2<kBf16>(x[2 * j], x[2 * j + 1]);
+        }
+      }
+      if (!live) continue;
+      // the box is this chunk's: every thread overwrites exactly the 16-byte slots it has read
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t phys = (static_cast<uint32_t>(g) ^ (row & 7u)) * 16u;
+        *reinterpret_cast<uint4*>(stage_ptr + row * 128u + phys) =
+            make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, 128);
+      if (issuer) {
+        tma_store_2d(&tmap_d, smem_base + stage_off, static_cast<int32_t>(gcol), static_cast<int32_t>(m0));
+        tma_store_commit();
+        const uint32_t nt = next_live(t + gridDim.x);   // aux of this quarter's next live chunk
+        if (nt < num_work) {
+          tma_store_wait_read<0>();
+          load_aux(nt);
+        }
+      }
+    }
+    if (issuer) tma_store_wait<0>();
+  } else if (kEpi == 1 && warp >= 4) {
     // ===================================================== epilogue, sixteen warps (write-only epilogues)
     reg_alloc<104>();
     const uint32_t quad = warp & 3;          // TMEM lane quadrant this warp may read
@@ -475,8 +593,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int j = 0; j < 4; ++j) {
               const float2 f = unpack2<kBf16>(rw[j]);
               if (gelu_bwd) {   // aux = pre-activation u: dU = dA * GeLU'(u)
-                x[2 * j] *= gelu_erf_grad(f.x);
-                x[2 * j + 1] *= gelu_erf_grad(f.y);
+                gelu_erf_grad_pair(f.x, f.y, x[2 * j], x[2 * j + 1]);
               } else {
                 x[2 * j] += f.x;
                 x[2 * j + 1] += f.y;
@@ -526,50 +643,59 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
 }  // namespace
 
-template <bool kBf16, bool kAMN, bool kBMN, bool kWide>
+template <bool kBf16, bool kAMN, bool kBMN, int kEpi>
 cudaError_t prepare_one() {
-  return cudaFuncSetAttribute(gemm_kernel<kBf16, kAMN, kBMN, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(gemm_kernel<kBf16, kAMN, kBMN, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               kGemmSmemBytes);
 }
 
-cudaError_t gemm_prepare() {
-  cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = prepare_one<true, false, false, false>();
-  if (e == cudaSuccess) e = prepare_one<true, false, true, false>();
-  if (e == cudaSuccess) e = prepare_one<true, true, true, false>();
-  if (e == cudaSuccess) e = prepare_one<false, false, false, false>();
-  if (e == cudaSuccess) e = prepare_one<false, false, true, false>();
-  if (e == cudaSuccess) e = prepare_one<false, true, true, false>();
-  if (e == cudaSuccess) e = prepare_one<true, false, false, true>();
-  if (e == cudaSuccess) e = prepare_one<true, false, true, true>();
-  if (e == cudaSuccess) e = prepare_one<false, false, false, true>();
-  if (e == cudaSuccess) e = prepare_one<false, false, true, true>();
+template <bool kBf16>
+cudaError_t prepare_dtype() {
+  cudaError_t e = prepare_one<kBf16, false, false, 0>();
+  if (e == cudaSuccess) e = prepare_one<kBf16, false, true, 0>();
+  if (e == cudaSuccess) e = prepare_one<kBf16, true, true, 0>();
+  if (e == cudaSuccess) e = prepare_one<kBf16, false, false, 1>();
+  if (e == cudaSuccess) e = prepare_one<kBf16, false, true, 1>();
+  if (e == cudaSuccess) e = prepare_one<kBf16, false, false, 2>();
+  if (e == cudaSuccess) e = prepare_one<kBf16, false, true, 2>();
   return e;
 }
 
+cudaError_t gemm_prepare() {
+  cudaError_t e = prepare_dtype<true>();
+  return e == cudaSuccess ? prepare_dtype<false>() : e;
+}
+
+namespace {
+
+template <bool kBf16>
+void launch_dtype(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d, const CUtensorMap& tmap_r,
+                  const CUtensorMap& tmap_p, const GemmArgs& args, bool a_mn, bool b_mn, int epi, int grid,
+                  cudaStream_t stream) {
+#define EMDR2_GEMM_LAUNCH(AMN, BMN, EPI)                                                                            \
+  gemm_kernel<kBf16, AMN, BMN, EPI><<<grid, EPI != 0 ? kGemmWideThreads : kGemmThreads, kGemmSmemBytes, stream>>>(  \
+      tmap_a, tmap_b, tmap_d, tmap_r, tmap_p, args)
+  if (a_mn) EMDR2_GEMM_LAUNCH(true, true, 0);
+  else if (b_mn && epi == 2) EMDR2_GEMM_LAUNCH(false, true, 2);
+  else if (b_mn && epi == 1) EMDR2_GEMM_LAUNCH(false, true, 1);
+  else if (b_mn) EMDR2_GEMM_LAUNCH(false, true, 0);
+  else if (epi == 2) EMDR2_GEMM_LAUNCH(false, false, 2);
+  else if (epi == 1) EMDR2_GEMM_LAUNCH(false, false, 1);
+  else EMDR2_GEMM_LAUNCH(false, false, 0);
+#undef EMDR2_GEMM_LAUNCH
+}
+
+}  // namespace
+
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
                         const CUtensorMap& tmap_r, const CUtensorMap& tmap_p, const GemmArgs& args,
-                        bool bf16, bool a_mn, bool b_mn, bool wide, int grid, cudaStream_t stream) {
-#define EMDR2_GEMM_LAUNCH(BF, AMN, BMN, WIDE)                                                                   \
-  gemm_kernel<BF, AMN, BMN, WIDE><<<grid, WIDE ? kGemmWideThreads : kGemmThreads, kGemmSmemBytes, stream>>>(    \
-      tmap_a, tmap_b, tmap_d, tmap_r, tmap_p, args)
+                        bool bf16, bool a_mn, bool b_mn, int epi, int grid, cudaStream_t stream) {
   if (a_mn && !b_mn) return cudaErrorInvalidValue;   // not needed by any forward/backward product
-  if (wide && (a_mn || args.splits != 1 || (args.flags & (kGemmResidual | kGemmGeluBwd | kGemmAccumF32))))
-    return cudaErrorInvalidValue;                    // the wide epilogue only writes
-  if (bf16) {
-    if (a_mn) EMDR2_GEMM_LAUNCH(true, true, true, false);
-    else if (b_mn && wide) EMDR2_GEMM_LAUNCH(true, false, true, true);
-    else if (b_mn) EMDR2_GEMM_LAUNCH(true, false, true, false);
-    else if (wide) EMDR2_GEMM_LAUNCH(true, false, false, true);
-    else EMDR2_GEMM_LAUNCH(true, false, false, false);
-  } else {
-    if (a_mn) EMDR2_GEMM_LAUNCH(false, true, true, false);
-    else if (b_mn && wide) EMDR2_GEMM_LAUNCH(false, false, true, true);
-    else if (b_mn) EMDR2_GEMM_LAUNCH(false, false, true, false);
-    else if (wide) EMDR2_GEMM_LAUNCH(false, false, false, true);
-    else EMDR2_GEMM_LAUNCH(false, false, false, false);
-  }
-#undef EMDR2_GEMM_LAUNCH
+  const bool has_aux = (args.flags & (kGemmResidual | kGemmGeluBwd)) != 0;
+  if (epi != 0 && (a_mn || args.splits != 1 || (args.flags & kGemmAccumF32))) return cudaErrorInvalidValue;
+  if ((epi == 1 && has_aux) || (epi == 2 && (!has_aux || (args.flags & kGemmPreact)))) return cudaErrorInvalidValue;
+  if (bf16) launch_dtype<true>(tmap_a, tmap_b, tmap_d, tmap_r, tmap_p, args, a_mn, b_mn, epi, grid, stream);
+  else launch_dtype<false>(tmap_a, tmap_b, tmap_d, tmap_r, tmap_p, args, a_mn, b_mn, epi, grid, stream);
   return cudaGetLastError();
 }
 

@@ -19,8 +19,9 @@
 //   warps 4-11  epilogue: tcgen05.ld -> bias/GeLU/residual in fp32 -> 16-bit -> swizzled smem
 //               staging -> TMA store (64-column boxes), two column halves in parallel; the residual
 //               tile is prefetched by TMA into the same staging buffer one chunk ahead
-//   warps 4-19  "wide" variant for write-only epilogues (bias / GeLU / pre-activation): four column quarters in
-//               parallel, 32-column boxes — four warps per scheduler hide the GeLU chain's latency
+//   warps 4-19  "wide" variants: four column quarters in parallel — four warps per scheduler hide the GeLU chain's
+//               latency; write-only epilogues (bias / GeLU / pre-activation) through 32-column boxes, aux epilogues
+//               (residual / GeLU backward) with three operand stages and the aux tile prefetched a tile ahead
 // Roofline: tensor pipe (2·M·N·K flop); DRAM traffic is A once + D once (B stays in L2).
 #pragma once
 #include <cuda.h>
@@ -40,7 +41,9 @@ constexpr int kGemmStageBytes = kGemmStageA + kGemmStageB;    // 48 KiB
 constexpr int kGemmOutBytes = 2 * kGemmBM * 64 * 2;           // two 128x64 staging boxes
 constexpr int kGemmBarBytes = 2048;                              // barriers + the staged bias slice
 constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + kGemmOutBytes + kGemmBarBytes + 1024;
-constexpr int kGemmWideThreads = 128 + 16 * 32;               // "wide" variant: sixteen epilogue warps (gemm.cu)
+constexpr int kGemmWideThreads = 128 + 16 * 32;               // "wide" variants: sixteen epilogue warps (gemm.cu)
+constexpr int kGemmAuxStages = 3;                             // wide variant with an aux tile: three operand stages and
+constexpr int kGemmAuxOutBytes = 4 * kGemmBM * 64 * 2;        // four 128x64 boxes (aux in, result out, in place)
 
 constexpr uint32_t kGemmBias = 1u;
 constexpr uint32_t kGemmGelu = 2u;
@@ -65,11 +68,12 @@ cudaError_t gemm_prepare();
 // tmap_r: residual / GeLU-backward aux [M, N] (box 128 x 64), read only with those flags; tmap_p:
 // pre-activation output, written only with kGemmPreact; pass tmap_d for the unused ones.
 // a_mn / b_mn: operand stored [k, m] / [k, n] row-major (tensor maps with 64 x 64 boxes).
-// wide: sixteen epilogue warps; only for write-only epilogues (no aux tile, no fp32 accumulation, splits == 1), and
-// tmap_d / tmap_p must then carry 128-row x 32-column boxes with the 64-byte swizzle.
+// epi: 0 = eight epilogue warps (any epilogue); 1 = sixteen, write-only epilogues (no aux tile): tmap_d / tmap_p
+// must carry 128-row x 32-column boxes with the 64-byte swizzle; 2 = sixteen with an aux tile (residual / GeLU
+// backward, no pre-activation output), the usual 64-column boxes.  1 and 2: no fp32 accumulation, splits == 1.
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
                         const CUtensorMap& tmap_r, const CUtensorMap& tmap_p, const GemmArgs& args,
-                        bool bf16, bool a_mn, bool b_mn, bool wide, int grid, cudaStream_t stream);
+                        bool bf16, bool a_mn, bool b_mn, int epi, int grid, cudaStream_t stream);
 
 // CTA-pair variant (gemm_pair.cu): K-major operands, 16-bit output, no split-K; 256 x 256 tiles shared by
 // two CTAs (tcgen05.mma.cta_group::2).  tmap_b_half: B [N, K] with a 128 x 64 box (each CTA stages half

@@ -72,22 +72,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-  const float q = 0.5f * poly * e;
-  const float cdf = x >= 0.f ? 1.0f - q : q;
-  return fmaf(x * 0.3989422804014327f, e, cdf);
-}
-
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -344,8 +328,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < 4; ++j) {
               const float2 f = unpack2<kBf16>(rw[j]);
               if (gelu_bwd) {
-                x[2 * j] *= gelu_erf_grad(f.x);
-                x[2 * j + 1] *= gelu_erf_grad(f.y);
+                gelu_erf_grad_pair(f.x, f.y, x[2 * j], x[2 * j + 1]);
               } else {
                 x[2 * j] += f.x;
                 x[2 * j + 1] += f.y;

@@ -96,14 +96,36 @@ def test_wide_epilogue_preact_output_strided_views_and_mn_major_operand(wide_swi
     assert torch.allclose(wide[:256].float(), dy[:256].float() @ w.float(), rtol=2 ** -8, atol=2 ** -6)
 
 
-def test_aux_and_accumulating_epilogues_stay_on_the_narrow_variant(wide_switch):
-    """Residual / GeLU-backward / fp32-accumulating products are not eligible: forcing the option changes nothing."""
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,n,k", [(9600, 3072, 768), (4100, 520, 200), (300, 40, 64)])
+def test_wide_epilogue_with_an_aux_tile(wide_switch, m, n, k, dtype):
+    """Residual and GeLU-backward epilogues (kEpi 2: three operand stages, the aux box of a quarter's next tile
+    prefetched into its staging box a tile ahead): same arithmetic as the eight-warp variant, same bits."""
+    ops = wide_switch
+    x, w = _rand((m, k), dtype, 21), _rand((n, k), dtype, 22, scale=k ** -0.5)
+    b = _rand((n,), dtype, 23)
+    big = _rand((m, n + 24), dtype, 24)
+    r = big[:, 16:16 + n]                                  # row pitch n + 24, 32-byte offset
+    narrow, wide = _both(ops, lambda: ops.linear(x, w, bias=b, residual=r))
+    assert torch.equal(narrow, wide)
+    tol = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    want = x[:300].float() @ w.float().T + b.float() + r[:300].float()
+    assert torch.allclose(wide[:300].float(), want, rtol=tol, atol=tol)
+    # dU = (dA . W2) * GeLU'(u), W2 [k, n] read in place as the [k', n'] operand
+    w2 = _rand((k, n), dtype, 25, scale=k ** -0.5)
+    narrow, wide = _both(ops, lambda: ops.gemm_ex(x, w2, b_mn=True, gelu_bwd_aux=r))
+    assert torch.equal(narrow, wide)
+    u = r[:300].float().requires_grad_(True)
+    torch.nn.functional.gelu(u).sum().backward()
+    want = (x[:300].float() @ w2.float()) * u.grad
+    assert torch.allclose(wide[:300].float(), want, rtol=4 * tol, atol=4 * tol)
+
+
+def test_accumulating_products_stay_on_the_narrow_variant(wide_switch):
+    """fp32-accumulating (split-K) products are not eligible: forcing the option changes nothing."""
     ops = wide_switch
     dtype = torch.float16
-    x, w = _rand((2048, 768), dtype, 11), _rand((768, 768), dtype, 12, scale=0.03)
-    r = _rand((2048, 768), dtype, 13)
-    narrow, wide = _both(ops, lambda: ops.linear(x, w, residual=r))
-    assert torch.equal(narrow, wide)
+    x, r = _rand((2048, 768), dtype, 11), _rand((2048, 768), dtype, 13)
 
     def dw():
         acc = torch.zeros((768, 768), dtype=torch.float32, device=DEV)
