@@ -31,10 +31,33 @@ def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
-def _splits(tokens, tiles):
-    """Split-K factor for dW: enough work items for the 148 SMs, slices of >= 4096 tokens."""
-    want = max(1, (148 * 2 + tiles - 1) // tiles)
-    return max(1, min(want, (tokens + _SPLIT_TOKENS - 1) // _SPLIT_TOKENS))
+_SM_COUNT = {}
+
+
+def _gemm_ctas(device):
+    """CTAs a persistent GEMM grid gets on `device`: the SM count, or the trainer's `gemm_max_ctas` cap."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    sms = _SM_COUNT.get(key)
+    if sms is None:
+        sms = _SM_COUNT[key] = torch.cuda.get_device_properties(key).multi_processor_count
+    cap = ops.get_option("gemm_max_ctas")
+    return cap if 0 < cap < sms else sms
+
+
+def _splits(tokens, tiles, ctas=148):
+    """Split-K factor for dW.  The persistent grid hands work items (tile, split) round-robin to `ctas` CTAs, so the
+    step takes ceil(items / ctas) item-times: pick the factor whose item count fills whole waves (54 tiles x 6
+    splits = 324 items ran as 3 waves at 73 % occupancy; x 8 = 432 items fill 2.92), at least ~2 waves unless one
+    already fills the machine, slices of >= 4096 tokens, preferring fewer splits (fewer fp32 atomics) on ties."""
+    max_s = max(1, min(32, (tokens + _SPLIT_TOKENS - 1) // _SPLIT_TOKENS))
+    best, best_score = 1, -1.0
+    for s in range(1, max_s + 1):
+        items = tiles * s
+        waves = -(-items // ctas)
+        score = items / float(waves * ctas) - 0.004 * s
+        if score > best_score:
+            best, best_score = s, score
+    return best
 
 
 # ---- gradient sinks ("main grads").  A trainer may attach to a parameter an fp32 buffer `main_grad` (a view of a
@@ -72,10 +95,10 @@ def _weight_grad(dy, x, sink=None):
     k = x.shape[1]
     tiles = ((n + 127) // 128) * ((k + 255) // 256)
     if sink is not None:
-        ops.gemm_ex(dy, x, a_mn=True, b_mn=True, accumulate_into=sink, splits=_splits(m, tiles))
+        ops.gemm_ex(dy, x, a_mn=True, b_mn=True, accumulate_into=sink, splits=_splits(m, tiles, _gemm_ctas(dy.device)))
         return None
     acc = torch.zeros((n, k), dtype=torch.float32, device=dy.device)
-    ops.gemm_ex(dy, x, a_mn=True, b_mn=True, accumulate_into=acc, splits=_splits(m, tiles))
+    ops.gemm_ex(dy, x, a_mn=True, b_mn=True, accumulate_into=acc, splits=_splits(m, tiles, _gemm_ctas(dy.device)))
     return acc.to(dy.dtype)
 
 
