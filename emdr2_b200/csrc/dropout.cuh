@@ -10,10 +10,10 @@
 //   key(seed, offset)          two 32-bit words, mixed on the host once per launch
 //   A(row)  = fmix32(fmix32(key_a ^ row_lo) ^ row_hi ^ key_b) | 1         once per row per thread
 //   B(col)  = fmix32(fmix32(seed_lo ^ C ^ col) + seed_hi) | 1             a per-seed table in HBM
-//   r       = hi32(A * B) ^ lo32(A * B)                                   one IMAD.WIDE + one LOP3
+//   r       = lo32(A * B)                                                 one IMAD (A, B odd: a bijection of either)
 //   keep    = r >= threshold,  threshold = round(p * 2^32)
 //
-// so an element costs four issue slots (multiply, fold, compare, select) in whichever orientation a
+// so an element costs three issue slots (multiply, compare, select) in whichever orientation a
 // kernel walks the (row, column) plane — the dK/dV kernel owns KEY rows and walks queries, the
 // forward and dQ kernels own QUERY rows and walk keys; a block cipher over 16-element strips
 // (Philox) would be cheap in one orientation and 16x the work in the other.  Kept values are scaled
@@ -49,8 +49,7 @@ __host__ __device__ __forceinline__ uint32_t dropout_col_hash(uint64_t seed, uin
 }
 
 __host__ __device__ __forceinline__ bool dropout_keep(uint32_t a, uint32_t b, uint32_t threshold) {
-  const uint64_t p = static_cast<uint64_t>(a) * b;
-  return (static_cast<uint32_t>(p >> 32) ^ static_cast<uint32_t>(p)) >= threshold;
+  return a * b >= threshold;   // the comparison is decided by the product's high bits, which depend on every bit of a and b
 }
 
 inline DropoutArgs make_dropout_args(float p, uint64_t seed, uint64_t offset, const uint32_t* colhash) {

@@ -25,15 +25,14 @@ def launch_key(seed, offset):
 
 
 def keep_mask(seed, offset, rows, cols, p):
-    """bool [rows, cols]: the mask of make_dropout_args(p, seed, offset) — row/col hashes, multiply-fold, threshold."""
+    """bool [rows, cols]: the mask of make_dropout_args(p, seed, offset) — row/col hashes, 32-bit multiply, threshold."""
     ka, kb = launch_key(seed, offset)
     r = np.arange(rows, dtype=np.uint64)
     a = fmix32(fmix32(ka ^ (r & M32)) ^ (r >> np.uint64(32)) ^ kb) | np.uint64(1)
     c = np.arange(cols, dtype=np.uint64)
     b = fmix32(fmix32(np.uint64((seed & 0xFFFFFFFF) ^ 0x632BE5AB) ^ c) + np.uint64(seed >> 32)) | np.uint64(1)
-    prod = a[:, None] * b[None, :]
-    folded = ((prod >> np.uint64(32)) ^ (prod & M32)) & M32
-    return folded >= np.uint64(min(int(p * 4294967296.0 + 0.5), 4294967295))
+    prod = (a[:, None] * b[None, :]) & M32                      # low 32 bits of the product
+    return prod >= np.uint64(min(int(p * 4294967296.0 + 0.5), 4294967295))
 
 
 def _corr(a, b):
