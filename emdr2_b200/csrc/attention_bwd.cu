@@ -174,7 +174,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tma_load_3d(smem_base + off_do, &tmap_do, fb, col_h, static_cast<int32_t>(q0), static_cast<int32_t>(b), kEvictNormal);
         uint32_t stage = 0, phase = 0;
         for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1)) {
-          mbar_wait(smem_u32(&bars->ring_empty[stage]), phase ^ 1);
+          mbar_wait_backoff<100>(smem_u32(&bars->ring_empty[stage]), phase ^ 1);   // sleeps between polls: a tight loop takes issue slots from the row warps
           const uint32_t fbar = smem_u32(&bars->ring_full[stage]);
           mbar_arrive_expect_tx(fbar, 2 * kHalfTile);
           const uint32_t dst = smem_base + off_ring + stage * 2 * kHalfTile;
@@ -218,7 +218,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (uint32_t j = next_live(0); j < nblk; ++n) {
           j = next_live(j + 1);
           if (j < nblk) issue_sdp(n + 1);          // overlaps the row threads' work on block n
-          mbar_wait(smem_u32(&bars->pds_full), n & 1);
+          mbar_wait_backoff<32>(smem_u32(&bars->pds_full), n & 1);
           tc_fence_after();
           const uint32_t kbase = smem_base + off_ring + stage * 2 * kHalfTile;
 #pragma unroll
@@ -278,36 +278,50 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         if (lane == 0) mbar_arrive(smem_u32(&bars->sdp_empty));   // S/dP may be overwritten now
         if (n > 0) mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);   // dS buffer consumed
         const uint32_t kmw = ch ? km[1] : km[0];
+        // Two copies of the element loop behind ONE warp-uniform branch: a block without padding, causal cut or
+        // ragged end in any of the warp's 32 rows (the common case) runs without the per-element mask logic.
+        // dS is written WITHOUT the softmax scale; dQ is multiplied by it once, at the end.
+        auto block = [&](auto fast_c) {
+          constexpr bool kFast = decltype(fast_c)::value;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float ds[8];
-          uint32_t cb[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-          if constexpr (kDrop) {   // column hashes of this group's 8 keys: the same address in every lane
-            const uint4* src = reinterpret_cast<const uint4*>(a.drop.colhash + kb0 + ch * 32 + g * 8);
-            const uint4 c0 = __ldg(src), c1 = __ldg(src + 1);
-            cb[0] = c0.x; cb[1] = c0.y; cb[2] = c0.z; cb[3] = c0.w;
-            cb[4] = c1.x; cb[5] = c1.y; cb[6] = c1.z; cb[7] = c1.w;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int c = g * 8 + i;
-            const float p = ex2(fmaf(__uint_as_float(s[c]), a.scale_log2, -lse2));
-            float dpv = __uint_as_float(dp[c]);
-            if constexpr (kDrop)     // dP = keep / (1 - p_drop) * (dO . V^T): the forward's mask, regenerated
-              dpv = dropout_keep(drop_row, cb[i], a.drop.threshold) ? dpv * a.drop.inv_keep : 0.f;
-            float d = p * (dpv - dsum) * a.scale;
-            if (!plain) {
-              const uint32_t cc = ch * 32 + c;
-              const bool masked = row_dead || ((kmw >> c) & 1u) || (a.causal && kb0 + cc > qi) || cc >= valid;
-              d = masked ? 0.f : d;
+          for (int g = 0; g < 4; ++g) {
+            float ds[8];
+            uint32_t cb[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if constexpr (kDrop) {   // column hashes of this group's 8 keys: the same address in every lane
+              const uint4* src = reinterpret_cast<const uint4*>(a.drop.colhash + kb0 + ch * 32 + g * 8);
+              const uint4 c0 = __ldg(src), c1 = __ldg(src + 1);
+              cb[0] = c0.x; cb[1] = c0.y; cb[2] = c0.z; cb[3] = c0.w;
+              cb[4] = c1.x; cb[5] = c1.y; cb[6] = c1.z; cb[7] = c1.w;
             }
-            ds[i] = d;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = g * 8 + i;
+              const float p = ex2(fmaf(__uint_as_float(s[c]), a.scale_log2, -lse2));
+              float x;
+              if constexpr (kDrop) {   // dP = keep / (1 - p_drop) * (dO . V^T): the forward's mask, regenerated
+                const float m = dropout_keep(drop_row, cb[i], a.drop.threshold) ? a.drop.inv_keep : 0.f;
+                x = fmaf(__uint_as_float(dp[c]), m, -dsum);
+              } else {
+                x = __uint_as_float(dp[c]) - dsum;
+              }
+              float d = p * x;
+              if constexpr (!kFast) {
+                if (!plain) {
+                  const uint32_t cc = ch * 32 + c;
+                  const bool masked = row_dead || ((kmw >> c) & 1u) || (a.causal && kb0 + cc > qi) || cc >= valid;
+                  d = masked ? 0.f : d;
+                }
+              }
+              ds[i] = d;
+            }
+            const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
+            *reinterpret_cast<uint4*>(ds_row + phys) =
+                make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
+                           pack2<kBf16>(ds[6], ds[7]));
           }
-          const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
-          *reinterpret_cast<uint4*>(ds_row + phys) =
-              make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
-                         pack2<kBf16>(ds[6], ds[7]));
-        }
+        };
+        if (__all_sync(kFull, plain)) block(std::true_type{});
+        else block(std::false_type{});
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->pds_full));
@@ -319,6 +333,8 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         uint32_t o[32];
         tmem_ld_32x32b_x32(tmem_dq + lane_tmem + ch * 32, o);
         tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * a.scale);   // dQ = scale * dS . K
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
@@ -405,7 +421,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tma_load_3d(smem_base + off_v, &tmap_v, fb, col_h, static_cast<int32_t>(k0), static_cast<int32_t>(b), kEvictNormal);
         uint32_t stage = 0, phase = 0;
         for (uint32_t i = next_live(0); i < nqblk; i = next_live(i + 1)) {
-          mbar_wait(smem_u32(&bars->ring_empty[stage]), phase ^ 1);
+          mbar_wait_backoff<100>(smem_u32(&bars->ring_empty[stage]), phase ^ 1);   // sleeps between polls: a tight loop takes issue slots from the row warps
           const uint32_t fbar = smem_u32(&bars->ring_full[stage]);
           mbar_arrive_expect_tx(fbar, 2 * kHalfTile);
           const uint32_t dst = smem_base + off_ring + stage * 2 * kHalfTile;
@@ -449,7 +465,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         for (uint32_t i = next_live(0); i < nqblk; ++n) {
           i = next_live(i + 1);
           if (i < nqblk) issue_sdp(n + 1);
-          mbar_wait(smem_u32(&bars->pds_full), n & 1);
+          mbar_wait_backoff<32>(smem_u32(&bars->pds_full), n & 1);
           tc_fence_after();
           const uint32_t qbase = smem_base + off_ring + stage * 2 * kHalfTile;
 #pragma unroll
@@ -524,54 +540,68 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         if (lane == 0) mbar_arrive(smem_u32(&bars->sdp_empty));
         if (n > 0) mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
         const uint32_t qmw = ch ? qm[1] : qm[0];
+        // As in the dQ kernel: one warp-uniform branch selects the element loop without mask logic when no row of
+        // the warp needs any; dS^T carries no softmax scale (dK is multiplied by it once, at the end).
+        auto block = [&](auto fast_c) {
+          constexpr bool kFast = decltype(fast_c)::value;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8], ds[8];
-          const float* lp = st + ch * 32 + g * 8;
-          const float4 l0 = *reinterpret_cast<const float4*>(lp);
-          const float4 l1 = *reinterpret_cast<const float4*>(lp + 4);
-          const float4 d0 = *reinterpret_cast<const float4*>(lp + 64);
-          const float4 d1 = *reinterpret_cast<const float4*>(lp + 68);
-          const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-          const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-          uint32_t rh[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-          if constexpr (kDrop) {
-            const uint4 r0 = *reinterpret_cast<const uint4*>(lp + 128);
-            const uint4 r1 = *reinterpret_cast<const uint4*>(lp + 132);
-            rh[0] = r0.x; rh[1] = r0.y; rh[2] = r0.z; rh[3] = r0.w;
-            rh[4] = r1.x; rh[5] = r1.y; rh[6] = r1.z; rh[7] = r1.w;
-          }
-#pragma unroll
-          for (int i2 = 0; i2 < 8; ++i2) {
-            const int c = g * 8 + i2;                 // column inside this thread's 32
-            const uint32_t cc = ch * 32 + c;          // query column inside the 64-query block
-            float t = __uint_as_float(s[c]) * a.scale_log2;
-            bool masked = false;
-            if (!plain) {
-              masked = k_is_pad || ((qmw >> c) & 1u) || (a.causal && kj > qb0 + cc);
-              t = masked ? kMaskedLog2 : t;
-            }
-            float p = ex2(t - lv[i2]);
-            if (!plain) p = (cc < valid && row_active) ? p : 0.f;
-            float dpv = __uint_as_float(dp[c]);
-            float pd = p;            // what multiplied V in the forward: the dropped, rescaled probability
+          for (int g = 0; g < 4; ++g) {
+            float pv[8], ds[8];
+            const float* lp = st + ch * 32 + g * 8;
+            const float4 l0 = *reinterpret_cast<const float4*>(lp);
+            const float4 l1 = *reinterpret_cast<const float4*>(lp + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(lp + 64);
+            const float4 d1 = *reinterpret_cast<const float4*>(lp + 68);
+            const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            uint32_t rh[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             if constexpr (kDrop) {
-              const bool keep = dropout_keep(rh[i2], drop_col, a.drop.threshold);
-              dpv = keep ? dpv * a.drop.inv_keep : 0.f;
-              pd = keep ? p * a.drop.inv_keep : 0.f;
+              const uint4 r0 = *reinterpret_cast<const uint4*>(lp + 128);
+              const uint4 r1 = *reinterpret_cast<const uint4*>(lp + 132);
+              rh[0] = r0.x; rh[1] = r0.y; rh[2] = r0.z; rh[3] = r0.w;
+              rh[4] = r1.x; rh[5] = r1.y; rh[6] = r1.z; rh[7] = r1.w;
             }
-            const float d = p * (dpv - dv[i2]) * a.scale;
-            pv[i2] = pd;
-            ds[i2] = masked ? 0.f : d;
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) {
+              const int c = g * 8 + i2;                 // column inside this thread's 32
+              const uint32_t cc = ch * 32 + c;          // query column inside the 64-query block
+              bool masked = false;
+              float p;
+              if constexpr (kFast) {
+                p = ex2(fmaf(__uint_as_float(s[c]), a.scale_log2, -lv[i2]));
+              } else {
+                float t = __uint_as_float(s[c]) * a.scale_log2;
+                if (!plain) {
+                  masked = k_is_pad || ((qmw >> c) & 1u) || (a.causal && kj > qb0 + cc);
+                  t = masked ? kMaskedLog2 : t;
+                }
+                p = ex2(t - lv[i2]);
+                if (!plain) p = (cc < valid && row_active) ? p : 0.f;
+              }
+              float pd = p;            // what multiplied V in the forward: the dropped, rescaled probability
+              float x;
+              if constexpr (kDrop) {
+                const float m = dropout_keep(rh[i2], drop_col, a.drop.threshold) ? a.drop.inv_keep : 0.f;
+                pd = p * m;
+                x = fmaf(__uint_as_float(dp[c]), m, -dv[i2]);
+              } else {
+                x = __uint_as_float(dp[c]) - dv[i2];
+              }
+              const float d = p * x;
+              pv[i2] = pd;
+              ds[i2] = masked ? 0.f : d;
+            }
+            const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
+            *reinterpret_cast<uint4*>(p_row + phys) =
+                make_uint4(pack2<kBf16>(pv[0], pv[1]), pack2<kBf16>(pv[2], pv[3]), pack2<kBf16>(pv[4], pv[5]),
+                           pack2<kBf16>(pv[6], pv[7]));
+            *reinterpret_cast<uint4*>(ds_row + phys) =
+                make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
+                           pack2<kBf16>(ds[6], ds[7]));
           }
-          const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
-          *reinterpret_cast<uint4*>(p_row + phys) =
-              make_uint4(pack2<kBf16>(pv[0], pv[1]), pack2<kBf16>(pv[2], pv[3]), pack2<kBf16>(pv[4], pv[5]),
-                         pack2<kBf16>(pv[6], pv[7]));
-          *reinterpret_cast<uint4*>(ds_row + phys) =
-              make_uint4(pack2<kBf16>(ds[0], ds[1]), pack2<kBf16>(ds[2], ds[3]), pack2<kBf16>(ds[4], ds[5]),
-                         pack2<kBf16>(ds[6], ds[7]));
-        }
+        };
+        if (__all_sync(kFull, plain)) block(std::true_type{});
+        else block(std::false_type{});
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->pds_full));
@@ -585,6 +615,10 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         uint32_t o[32];
         tmem_ld_32x32b_x32(taddr, o);
         tmem_ld_wait();
+        if (which == 1) {   // dK = scale * dS^T . Q
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * a.scale);
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
