@@ -191,20 +191,12 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       // which issues the P.V products.  Order of issue: S(0); then per block g: S(g+1) once S(g) is in registers,
       // P.V(g) once P(g) is in TMEM.
       struct Cursor {
-        uint32_t idx, n, j, nblk, k_len;
+        uint32_t idx, n, j, nblk;
         bool ok;
-        // keys of the current block that exist (the last block of a range may be partial) ...
-        __device__ uint32_t valid() const { return min(static_cast<uint32_t>(kAttnBK), k_len - j * kAttnBK); }
-        // ... rounded up to the 16-key granularity of the tensor core: a partial block runs a narrower score
-        // product (N) and fewer P.V steps (K); the softmax warps neither read nor write columns past it
-        __device__ uint32_t valid16() const { return (valid() + 15u) & ~15u; }
       };
       auto load = [&](Cursor& c) {
         c.ok = c.idx < a.n_items;
-        if (c.ok) {
-          c.k_len = static_cast<uint32_t>(load_item(a.items, c.idx).k_len);
-          c.nblk = (c.k_len + kAttnBK - 1) / kAttnBK;
-        }
+        if (c.ok) c.nblk = (static_cast<uint32_t>(load_item(a.items, c.idx).k_len) + kAttnBK - 1) / kAttnBK;
       };
       auto advance = [&](Cursor& c) {
         if (++c.j == c.nblk) {
@@ -214,7 +206,7 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           load(c);
         }
       };
-      Cursor sc{blockIdx.x, 0, 0, 0, 0, false}, pc{blockIdx.x, 0, 0, 0, 0, false};
+      Cursor sc{blockIdx.x, 0, 0, 0, false}, pc{blockIdx.x, 0, 0, 0, false};
       load(sc);
       load(pc);
       uint32_t s_stage = 0, s_phase = 0;   // K/V ring position of the next S product
@@ -229,11 +221,10 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tc_fence_after();
         const uint64_t qdesc = smem_desc_sw128(smem_base + kOffQ + buf * kAttnTileBytes);
         const uint64_t kdesc = smem_desc_sw128(smem_base + kOffKV + s_stage * 2 * kAttnTileBytes);
-        const uint32_t idesc = (a.idesc_s & ~(0x3Fu << 17)) | ((sc.valid16() >> 3) << 17);   // N = keys of this block
 #pragma unroll
         for (int kk = 0; kk < kAttnHeadDim / 16; ++kk)
           mma_f16_ss(tmem_base, qdesc + static_cast<uint64_t>(kk * 2), kdesc + static_cast<uint64_t>(kk * 2),
-                     idesc, kk != 0 ? 1u : 0u);
+                     a.idesc_s, kk != 0 ? 1u : 0u);
         mma_commit(smem_u32(&bars->s_full));
         if (sc.j + 1 == sc.nblk) mma_commit(smem_u32(&bars->q_empty[buf]));   // Q is only read by the S products
         if (++s_stage == kAttnStages) {
@@ -252,15 +243,12 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         mbar_wait(smem_u32(&bars->p_full), g & 1);
         tc_fence_after();
         const uint32_t vbase = smem_base + kOffKV + pv_stage * 2 * kAttnTileBytes + kAttnTileBytes;
-        const uint32_t ksteps = pc.valid16() / 16;
 #pragma unroll
         for (int ks = 0; ks < kAttnBK / 16; ++ks) {
           // A = P in TMEM: row = lane, 16 keys = 8 packed 32-bit columns; B = V MN-major, 16 keys =
           // two 8-row groups of 1024 B
-          if (static_cast<uint32_t>(ks) < ksteps) {
-            const uint64_t vdesc = smem_desc_sw128_mn(vbase + ks * 2048, 1024, 1024);
-            mma_f16_ts(tmem_o, tmem_p + ks * 8, vdesc, a.idesc_o, (pc.j != 0 || ks != 0) ? 1u : 0u);
-          }
+          const uint64_t vdesc = smem_desc_sw128_mn(vbase + ks * 2048, 1024, 1024);
+          mma_f16_ts(tmem_o, tmem_p + ks * 8, vdesc, a.idesc_o, (pc.j != 0 || ks != 0) ? 1u : 0u);
         }
         mma_commit(smem_u32(&bars->kv_empty[pv_stage]));
         mma_commit(smem_u32(&bars->pv_done));
@@ -300,12 +288,10 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         if (warp_active) {
           uint32_t t[kAttnBK];   // scores as raw fp32 bits (tcgen05.ld output registers)
           const uint32_t s_addr = tmem_base + lane_tmem;
-          // 32-key chunks wholly past the end of the range are neither read, exponentiated nor written back: the
-          // score product did not compute them and the P.V product does not read them (block-uniform branches)
           tmem_ld_32x32b_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&t[0]));
-          if (valid > 32) tmem_ld_32x32b_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&t[32]));
-          if (valid > 64) tmem_ld_32x32b_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&t[64]));
-          if (valid > 96) tmem_ld_32x32b_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&t[96]));
+          tmem_ld_32x32b_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&t[32]));
+          tmem_ld_32x32b_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&t[64]));
+          tmem_ld_32x32b_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&t[96]));
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
@@ -395,7 +381,6 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
           for (int c = 0; c < kAttnBK / 32; ++c) {
-            if (static_cast<uint32_t>(c * 32) >= valid) continue;
             const float mul = mul_c[c];
             const float negm = bias_c[c] - m_run;
             uint32_t w[16];
