@@ -218,7 +218,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (uint32_t j = next_live(0); j < nblk; ++n) {
           j = next_live(j + 1);
           if (j < nblk) issue_sdp(n + 1);          // overlaps the row threads' work on block n
-          mbar_wait_backoff<32>(smem_u32(&bars->pds_full), n & 1);
+          mbar_wait_backoff<96>(smem_u32(&bars->pds_full), n & 1);
           tc_fence_after();
           const uint32_t kbase = smem_base + off_ring + stage * 2 * kHalfTile;
 #pragma unroll
@@ -254,8 +254,28 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       uint32_t drop_row = 0;
       if constexpr (kDrop)
         drop_row = dropout_row_hash(a.drop.key_a, a.drop.key_b, (static_cast<uint64_t>(b) * a.heads + head) * a.sq + qi);
+      // a warp whose 32 query rows are all padding (the tail of the sequence's last tile) contributes dS = 0 to
+      // every block: it writes its rows of the dS buffer once and then only keeps the barrier protocol going
+      const bool warp_dead = __all_sync(kFull, row_dead);
+      if (warp_dead) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(ds_row + (ch * 4 + g) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+      }
       uint32_t n = 0;
       for (uint32_t j = next_live(0); j < nblk; j = next_live(j + 1), ++n) {
+        if (warp_dead) {
+          mbar_wait(smem_u32(&bars->sdp_full), n & 1);
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(smem_u32(&bars->sdp_empty));
+            mbar_arrive(smem_u32(&bars->pds_full));
+          }
+          // the next score tile can land before the working warps have finished this block: without this wait the
+          // warp would run a block ahead and its next arrival would complete THIS block's pds_full phase early
+          mbar_wait_backoff<64>(smem_u32(&bars->pds_full), n & 1);
+          continue;
+        }
         const uint32_t kb0 = j * kBwdBlk;
         uint32_t km[2];
 #pragma unroll
@@ -360,9 +380,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 }
 
 // ============================================================================ dK, dV
-// smem: K 16K | V 16K | ring 2 x (Q 8K + dO 8K) | P^T 16K | dS^T 16K | stats 2 x 512 B | bars
+// smem: K 16K | V 16K | ring 2 x (Q 8K + dO 8K) | P^T 16K | dS^T 16K | stats 8 warps x 384 B | bars
 // TMEM: S^T [0,64) dP^T [64,128) dV [128,192) dK [192,256)
-constexpr int kDkvSmem = 2 * kTile + 2 * 2 * kHalfTile + 2 * kTile + 2048 + 256;
+constexpr int kDkvSmem = 2 * kTile + 2 * 2 * kHalfTile + 2 * kTile + 3072 + 256;
 
 template <bool kBf16, bool kDrop>
 __global__ void __launch_bounds__(kBwdThreads, 2)
@@ -372,9 +392,9 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                          const AttnBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr uint32_t off_k = 0, off_v = kTile, off_ring = 2 * kTile, off_p = off_ring + 4 * kHalfTile,
-                     off_ds = off_p + kTile, off_stat = off_ds + kTile, off_bar = off_stat + 2048;
+                     off_ds = off_p + kTile, off_stat = off_ds + kTile, off_bar = off_stat + 3072;
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + off_bar);
-  float* stat_smem = reinterpret_cast<float*>(smem + off_stat);   // [2][64] x {lse*log2e, D, dropout row hash}
+  float* stat_smem = reinterpret_cast<float*>(smem + off_stat);   // per row-warp: 32 x {lse*log2e, D, dropout row hash}
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t k0 = blockIdx.x * kAttnBK, head = blockIdx.y, b = blockIdx.z;
@@ -465,7 +485,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         for (uint32_t i = next_live(0); i < nqblk; ++n) {
           i = next_live(i + 1);
           if (i < nqblk) issue_sdp(n + 1);
-          mbar_wait_backoff<32>(smem_u32(&bars->pds_full), n & 1);
+          mbar_wait_backoff<96>(smem_u32(&bars->pds_full), n & 1);
           tc_fence_after();
           const uint32_t qbase = smem_base + off_ring + stage * 2 * kHalfTile;
 #pragma unroll
@@ -504,31 +524,51 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       const bool k_is_pad = row_active && a.k_pad && a.k_pad[static_cast<size_t>(b) * a.sk + kj] != 0;
       uint32_t drop_col = 0;   // this thread's key column of the dropout plane (table covers roundup(sk, 128))
       if constexpr (kDrop) drop_col = __ldg(a.drop.colhash + kj);
+      // a warp whose 32 keys are all padding / past the end contributes P = dS = 0 to every block: it writes its
+      // rows of the two buffers once and then only keeps the barrier protocol going
+      const bool warp_dead = __all_sync(kFull, !row_active || k_is_pad);
+      if (warp_dead) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          *reinterpret_cast<uint4*>(p_row + (ch * 4 + g) * 16) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(ds_row + (ch * 4 + g) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+      }
+      // per-query statistics of the block's 32 queries this warp walks: every warp stages ITS OWN copy (three
+      // coalesced loads, a __syncwarp) — a CTA-wide barrier per block was the kernel's top stall reason
+      float* st = stat_smem + (warp - 4) * 96;   // {lse * log2e, D, dropout row hash} x 32
       uint32_t n = 0;
       for (uint32_t i = next_live(0); i < nqblk; i = next_live(i + 1), ++n) {
+        if (warp_dead) {
+          mbar_wait(smem_u32(&bars->sdp_full), n & 1);
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(smem_u32(&bars->sdp_empty));
+            mbar_arrive(smem_u32(&bars->pds_full));
+          }
+          // the next score tile can land before the working warps have finished this block: without this wait the
+          // warp would run a block ahead and its next arrival would complete THIS block's pds_full phase early
+          mbar_wait_backoff<64>(smem_u32(&bars->pds_full), n & 1);
+          continue;
+        }
         const uint32_t qb0 = i * kBwdBlk;
-        // per-query statistics of this block -> shared memory (threads 0..63 load query qb0 + row)
-        float* st = stat_smem + (n & 1) * 192;
-        if (ch == 0 && row < kBwdBlk) {
-          const uint32_t qi = qb0 + row;
-          const size_t sidx = (static_cast<size_t>(b) * a.heads + head) * a.sq + (qi < a.sq ? qi : 0);
-          st[row] = a.lse[sidx] * kLog2e;
-          st[64 + row] = a.dvec[sidx];
+        const uint32_t qcol = qb0 + ch * 32 + lane;          // the query this lane stages
+        {
+          const size_t sidx = (static_cast<size_t>(b) * a.heads + head) * a.sq + (qcol < a.sq ? qcol : 0);
+          const float lse2 = a.lse[sidx] * kLog2e, dsum = a.dvec[sidx];
+          __syncwarp();                                       // the previous block's reads are done
+          st[lane] = lse2;
+          st[32 + lane] = dsum;
           if constexpr (kDrop)
-            st[128 + row] = __uint_as_float(dropout_row_hash(
-                a.drop.key_a, a.drop.key_b, (static_cast<uint64_t>(b) * a.heads + head) * a.sq + qi));
+            st[64 + lane] = __uint_as_float(dropout_row_hash(
+                a.drop.key_a, a.drop.key_b, (static_cast<uint64_t>(b) * a.heads + head) * a.sq + qcol));
+          __syncwarp();
         }
-        uint32_t qm[2];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t idx = qb0 + c * 32 + lane;
-          const bool f = a.q_pad && idx < a.sq && a.q_pad[static_cast<size_t>(b) * a.sq + idx] != 0;
-          qm[c] = __ballot_sync(kFull, f);
-        }
+        const uint32_t qmw = __ballot_sync(
+            kFull, a.q_pad && qcol < a.sq && a.q_pad[static_cast<size_t>(b) * a.sq + qcol] != 0);
         const uint32_t valid = min(static_cast<uint32_t>(kBwdBlk), a.sq - qb0);
-        const bool plain = row_active && !k_is_pad && valid == kBwdBlk && (qm[0] | qm[1]) == 0u &&
-                           !(a.causal && kj > qb0);
-        asm volatile("bar.sync 2, 256;" ::: "memory");   // statistics visible to all row threads
+        const bool plain = row_active && !k_is_pad && valid == kBwdBlk && qmw == 0u && !(a.causal && kj > qb0);
         mbar_wait(smem_u32(&bars->sdp_full), n & 1);
         tc_fence_after();
         uint32_t s[32], dp[32];
@@ -539,7 +579,6 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->sdp_empty));
         if (n > 0) mbar_wait(smem_u32(&bars->acc_done), (n - 1) & 1);
-        const uint32_t qmw = ch ? qm[1] : qm[0];
         // As in the dQ kernel: one warp-uniform branch selects the element loop without mask logic when no row of
         // the warp needs any; dS^T carries no softmax scale (dK is multiplied by it once, at the end).
         auto block = [&](auto fast_c) {
@@ -547,17 +586,17 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float pv[8], ds[8];
-            const float* lp = st + ch * 32 + g * 8;
+            const float* lp = st + g * 8;
             const float4 l0 = *reinterpret_cast<const float4*>(lp);
             const float4 l1 = *reinterpret_cast<const float4*>(lp + 4);
-            const float4 d0 = *reinterpret_cast<const float4*>(lp + 64);
-            const float4 d1 = *reinterpret_cast<const float4*>(lp + 68);
+            const float4 d0 = *reinterpret_cast<const float4*>(lp + 32);
+            const float4 d1 = *reinterpret_cast<const float4*>(lp + 36);
             const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
             const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
             uint32_t rh[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             if constexpr (kDrop) {
-              const uint4 r0 = *reinterpret_cast<const uint4*>(lp + 128);
-              const uint4 r1 = *reinterpret_cast<const uint4*>(lp + 132);
+              const uint4 r0 = *reinterpret_cast<const uint4*>(lp + 64);
+              const uint4 r1 = *reinterpret_cast<const uint4*>(lp + 68);
               rh[0] = r0.x; rh[1] = r0.y; rh[2] = r0.z; rh[3] = r0.w;
               rh[4] = r1.x; rh[5] = r1.y; rh[6] = r1.z; rh[7] = r1.w;
             }
