@@ -72,7 +72,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-gpu-reference", action="store_true")
     p.add_argument("--no-train-step", action="store_true", help="skip the train_step block of the default line")
-    p.add_argument("--train-steps", type=int, default=6, help="timed training steps of the train_step block")
+    p.add_argument("--train-steps", type=int, default=8, help="timed training steps of the train_step block")
     p.add_argument("--no-dropout", action="store_true", help="train with hidden/attention dropout 0 (A/B only)")
     p.add_argument("--refresh-rows", type=int, default=32768,
                    help="passages each GPU re-encodes in the index_refresh block (BASELINE config 5, bounded sample); 0 = skip")
@@ -1041,7 +1041,7 @@ def run_retrieve_read(a):
     if not a.train and not a.no_gpu_reference:
         line["gpu_reference"] = gpu_reference_read_leg(a, d, model, rows, all_q, dev)
     if not a.train and not a.no_train_step:
-        line["train_step"] = train_block(a.train_steps, 2)
+        line["train_step"] = train_block(a.train_steps, 3)
     if "train_step" in line and a.refresh_rows > 0:
         try:
             line["index_refresh"] = refresh_block(line["train_step"]["ms_per_step"])
