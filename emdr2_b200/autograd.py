@@ -292,6 +292,55 @@ def layernorm(x, gamma, beta, eps=1e-5):
     return ops.layernorm(x, gamma, beta, eps)
 
 
+class _LayerNormForkFn(torch.autograd.Function):
+    """(LN(x), x): the sublayer input AND the residual branch of a pre-LN block (transformer.py:524-560 — the hidden
+    state feeds the LayerNorm and, unchanged, the bias-dropout-add behind the sublayer).  With two separate consumers
+    autograd sums the two gradients of x in an extra elementwise pass over [tokens, h]; here the backward kernel adds
+    the residual-branch gradient while it writes dx (`dres` of emdr2_layernorm_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        y, mean, rstd = ops.layernorm(x, gamma, beta, eps, return_stats=True)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.params = (gamma, beta)
+        _expect(gamma, beta)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        gp, bp = ctx.params
+        rows, h = x.shape
+        sunk = _sink(gp) is not None and _sink(bp) is not None
+        if dy is None:                      # only the residual branch was used
+            if sunk:
+                _done(gp, bp)
+            return dres, None, None, None
+        dy = _c(dy)
+        dres = None if dres is None else _c(dres)
+        dx = torch.empty_like(x)
+        dgamma = _sink(gp) if sunk else torch.zeros(h, dtype=torch.float32, device=x.device)
+        dbeta = _sink(bp) if sunk else torch.zeros(h, dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        with ops._OnDevice(x.device):
+            _lib.check(lib.emdr2_layernorm_bwd(
+                _DT[x.dtype], ops._ptr(dy), dy.stride(0), ops._ptr(x), x.stride(0), ops._ptr(gamma),
+                ops._ptr(mean), ops._ptr(rstd), ops._ptr(dres), dres.stride(0) if dres is not None else 0,
+                ops._ptr(dx), dx.stride(0), ops._ptr(dgamma), ops._ptr(dbeta), rows, h, ops._stream(x.device)),
+                "emdr2_layernorm_bwd")
+        if sunk:
+            _done(gp, bp)
+            return dx, None, None, None
+        return dx, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None
+
+
+def layernorm_fork(x, gamma, beta, eps=1e-5):
+    """(LN(x), x) for a pre-LN residual block; see _LayerNormForkFn."""
+    if _needs_grad(x) and x.dim() == 2:
+        return _LayerNormForkFn.apply(x, gamma, beta, eps)
+    return layernorm(x, gamma, beta, eps), x
+
+
 # ------------------------------------------------------------------------------------ attention
 def _attention_bwd(q, k, v, o, dout, dq, dk, dv, batch, heads, sq, sk, q_pad, k_pad, q_live, k_live, causal,
                    scale, lse, dropout=None):

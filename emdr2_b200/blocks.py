@@ -63,6 +63,11 @@ class LayerNorm(nn.Module):
     def forward(self, x):
         return ag.layernorm(x, self.weight, self.bias, self.eps)
 
+    def fork(self, x):
+        """(LN(x), x) — the sublayer input and the residual branch; under autograd the two gradients of x are
+        summed inside the LayerNorm backward kernel instead of a separate elementwise pass."""
+        return ag.layernorm_fork(x, self.weight, self.bias, self.eps)
+
 
 def _unpack_rows(t, heads, hn, splits):
     """[np*hn*splits (np,hn,splits order), ...] -> [splits*np*hn (splits,np,hn order), ...]."""
@@ -175,14 +180,15 @@ class ParallelTransformerLayer(nn.Module):
 
     def forward(self, x, batch, seq, pad, causal=False, encoder_output=None, enc_seq=None, enc_pad=None,
                 q_live=None, enc_live=None, groups=None, packed=None, cross_plan=None):
-        x = self.self_attention(self.input_layernorm(x), batch, seq, pad, residual=x, causal=causal,
+        ln, x = self.input_layernorm.fork(x)
+        x = self.self_attention(ln, batch, seq, pad, residual=x, causal=causal,
                                 q_live=q_live, groups=groups, packed=packed)
-        ln = self.post_attention_layernorm(x)
+        ln, x = self.post_attention_layernorm.fork(x)
         if self.layer_type == "decoder":
             x = self.inter_attention(ln, batch, seq, pad, residual=x, encoder_output=encoder_output,
                                      sk=enc_seq, k_pad=enc_pad, q_live=q_live, k_live=enc_live,
                                      cross_plan=cross_plan)
-            ln = self.post_inter_attention_layernorm(x)
+            ln, x = self.post_inter_attention_layernorm.fork(x)
         return self.mlp(ln, residual=x)
 
 

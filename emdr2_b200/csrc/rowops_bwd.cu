@@ -66,11 +66,13 @@ layernorm_bwd_kernel(const uint16_t* __restrict__ dy, int64_t ldy, const uint16_
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const float mu = mean[row], rs = rstd[row];
     float g[kMaxChunks][8], xh[kMaxChunks][8];
+    uint4 rraw[kMaxChunks];   // the residual-branch gradient, fetched with dy and x (not behind the row reductions)
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < kMaxChunks; ++c) {
       const int col = (c * 32 + lane) * 8;
       if (col < h) {
+        if (dres) rraw[c] = __ldg(reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * ldr + col));
         float d[8], xv[8];
         unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * ldy + col)), d);
         unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx + col)), xv);
@@ -96,7 +98,7 @@ layernorm_bwd_kernel(const uint16_t* __restrict__ dy, int64_t ldy, const uint16_
         for (int i = 0; i < 8; ++i) o[i] = rs * (g[c][i] - c1 - xh[c][i] * c2);
         if (dres) {
           float r[8];
-          unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * ldr + col)), r);
+          unpack8<kBf16>(rraw[c], r);
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] += r[i];
         }
