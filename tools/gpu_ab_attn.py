@@ -12,7 +12,7 @@ from emdr2_b200.packed import PackedBatch
 
 DEV = torch.device("cuda:0")
 new = _lib.load()
-old = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ab", "libemdr2_old.so"))
+old = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ab", os.environ.get("AB_OLD", "libemdr2_old.so")))
 for name, (restype, argtypes) in _lib._SIGNATURES.items():
     if hasattr(old, name):
         fn = getattr(old, name)

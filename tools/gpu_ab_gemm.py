@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 DEV = "cuda:0"
 dtype = torch.bfloat16
 new = _lib.load()
-old = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ab", "libemdr2_old.so"))
+old = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ab", os.environ.get("AB_OLD", "libemdr2_old.so")))
 for name, (restype, argtypes) in _lib._SIGNATURES.items():
     if hasattr(old, name):
         fn = getattr(old, name)
