@@ -42,7 +42,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NCCL_CTAS = 8                      # SMs left to NCCL while gradient all-reduces overlap the backward pass
+NCCL_CTAS = int(os.environ.get("EMDR2_NCCL_CTAS", "4"))   # SMs left to NCCL while gradient all-reduces overlap the backward pass
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 L2_BYTES = 126 * 1024 * 1024
 
@@ -782,15 +782,16 @@ def run_retrieve_read(a):
         gb = trainer["buckets"]
         gb.start_step()
         lm_logits, topk_log_probs, one_ctx = forward(x)
-        if world > 1:      # leave NCCL's CTAs their SMs while all-reduces overlap the backward GEMMs
+        if world > 1 or os.environ.get("EMDR2_BENCH_FORCE_GEMM_CAP"):   # (the env switch: A/B of the cap alone at N = 1)
+            # leave NCCL's CTAs their SMs while all-reduces overlap the backward GEMMs
             ops.set_option("gemm_max_ctas", sm_count - NCCL_CTAS)
         mask = (x["labels"] > 0).float()
         lm_loss = losses.reader_cross_entropy(lm_logits, x["labels"], mask)
         r_loss, _, _ = losses.get_loss_and_retriever_utility(one_ctx, topk_log_probs, x["labels"], mask, 30523)
         (lm_loss + r_loss).backward()
         gb.finish()
+        ops.set_option("gemm_max_ctas", 0)
         if world > 1:
-            ops.set_option("gemm_max_ctas", 0)
             for b in gb.buckets:
                 b.grad.mul_(1.0 / world)
         trainer["opt"].step()
@@ -1041,7 +1042,7 @@ def run_retrieve_read(a):
     if not a.train and not a.no_gpu_reference:
         line["gpu_reference"] = gpu_reference_read_leg(a, d, model, rows, all_q, dev)
     if not a.train and not a.no_train_step:
-        line["train_step"] = train_block(a.train_steps, 3)
+        line["train_step"] = train_block(a.train_steps, 5)
     if "train_step" in line and a.refresh_rows > 0:
         try:
             line["index_refresh"] = refresh_block(line["train_step"]["ms_per_step"])

@@ -48,13 +48,15 @@ def _splits(tokens, tiles, ctas=148):
     """Split-K factor for dW.  The persistent grid hands work items (tile, split) round-robin to `ctas` CTAs, so the
     step takes ceil(items / ctas) item-times: pick the factor whose item count fills whole waves (54 tiles x 6
     splits = 324 items ran as 3 waves at 73 % occupancy; x 8 = 432 items fill 2.92), at least ~2 waves unless one
-    already fills the machine, slices of >= 4096 tokens, preferring fewer splits (fewer fp32 atomics) on ties."""
+    already fills the machine, slices of >= 4096 tokens.  Every extra split costs a pass of fp32 atomics over the
+    output tile (measured ~2-4 % of the product per split at 204 800 tokens: 72 tiles x 15 splits ran 1.15 ms against
+    0.77 ms for x 2), hence the penalty per split."""
     max_s = max(1, min(32, (tokens + _SPLIT_TOKENS - 1) // _SPLIT_TOKENS))
     best, best_score = 1, -1.0
     for s in range(1, max_s + 1):
         items = tiles * s
         waves = -(-items // ctas)
-        score = items / float(waves * ctas) - 0.004 * s
+        score = items / float(waves * ctas) - 0.015 * s
         if score > best_score:
             best, best_score = s, score
     return best

@@ -35,6 +35,9 @@ def run_interleaved(fns, iters=30):
 
 
 M = 204800
+CAP = int(os.environ.get("CAP", "0"))
+ops.set_option("gemm_max_ctas", CAP)
+print("gemm_max_ctas", CAP)
 for (n_out, k_in, gelu_bwd) in [(2304, 768, False), (768, 768, False), (3072, 768, False), (768, 3072, True)]:
     # forward y[M, n_out] = x[M, k_in] . W[n_out, k_in]^T
     dy = torch.randn(M, n_out, generator=g, device=DEV).to(dtype)
