@@ -331,3 +331,26 @@ def test_k_above_the_kernel_limit_row_sharded_world2_gloo(tmp_path):
         r = np.load(str(tmp_path / ("k%d.npz" % rank)))
         assert np.array_equal(r["scores"], want_s)
         assert np.array_equal(r["ids"][ties == 0], want_i[ties == 0])
+
+
+def test_split_k_factor_fills_whole_waves_of_the_persistent_grid():
+    """autograd._splits: the weight-gradient product hands (tile, split) items round-robin to `ctas` persistent CTAs;
+    the factor must fill whole waves (items / (waves * ctas) high) without buying balance with many splits (each split
+    is a pass of fp32 atomics over the output tile), and keep slices of >= 4096 tokens."""
+    from emdr2_b200.autograd import _splits
+
+    def occupancy(tiles, s, ctas):
+        items = tiles * s
+        return items / float(-(-items // ctas) * ctas)
+
+    # the step's tile counts on 148 SMs, and on the 144 a trainer leaves when NCCL holds 4
+    for ctas in (148, 144):
+        assert _splits(204800, 18, ctas) == 8 and _splits(204800, 54, ctas) == 8 and _splits(204800, 72, ctas) == 2
+    for tiles in (9, 18, 36, 54, 72, 720):
+        for ctas in (148, 144, 140, 132):
+            s = _splits(204800, tiles, ctas)
+            assert 1 <= s <= 32
+            assert occupancy(tiles, s, ctas) >= 0.85, (tiles, ctas, s)
+            assert occupancy(tiles, s, ctas) + 1e-9 >= occupancy(tiles, 1, ctas) - 0.015 * s   # never worse than no split
+    assert _splits(204800, 72, 140) <= 8          # not the 15 splits a balance-only rule picks
+    assert _splits(2048, 18) == 1 and _splits(12800, 18) <= 4      # slices of at least 4096 tokens
