@@ -77,6 +77,21 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Debug build only (-DEMDR2_VARLEN_TRACE, tools/gpu_trace_varlen.py): clock stamps of CTA 0's first softmax warp and
+// of its MMA thread at the hand-over points of every key block, read back with emdr2_varlen_trace_read.
+#ifdef EMDR2_VARLEN_TRACE
+constexpr int kTraceBlocks = 64, kTraceSlots = 8;
+__device__ long long g_varlen_trace[2][kTraceBlocks][kTraceSlots];
+#define VTRACE(role, blk, slot)                                                                   \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && (blk) < kTraceBlocks) g_varlen_trace[role][blk][slot] = clock64();     \
+  } while (0)
+#else
+#define VTRACE(role, blk, slot) \
+  do {                          \
+  } while (0)
+#endif
+
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   if constexpr (kBf16) {
@@ -235,13 +250,17 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       };
       if (sc.ok) issue_s();
       for (uint32_t g = 0; pc.ok; ++g) {
+        VTRACE(1, g, 0);
         if (sc.ok && a.sched == 0) {
           mbar_wait(smem_u32(&bars->s_free), g & 1);     // S(g) is in the softmax warps' registers
           tc_fence_after();
+          VTRACE(1, g, 1);
           issue_s();                                     // S(g+1)
         }
+        VTRACE(1, g, 2);
         mbar_wait(smem_u32(&bars->p_full), g & 1);
         tc_fence_after();
+        VTRACE(1, g, 3);
         const uint32_t vbase = smem_base + kOffKV + pv_stage * 2 * kAttnTileBytes + kAttnTileBytes;
 #pragma unroll
         for (int ks = 0; ks < kAttnBK / 16; ++ks) {
@@ -254,6 +273,7 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         mma_commit(smem_u32(&bars->pv_done));
         if (pc.j + 1 == pc.nblk) mma_commit(smem_u32(&bars->o_full));
         if (++pv_stage == kAttnStages) pv_stage = 0;
+        VTRACE(1, g, 4);
         advance(pc);
         if (sc.ok && a.sched != 0) issue_s();            // conservative order (debug): S(g+1) behind P.V(g)
       }
@@ -283,8 +303,10 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
       for (uint32_t j = 0; j < nblk; ++j, ++blk) {
         const uint32_t valid = min(static_cast<uint32_t>(kAttnBK), k_len - j * kAttnBK);
+        if (threadIdx.x == 128) VTRACE(0, blk, 0);
         mbar_wait(smem_u32(&bars->s_full), blk & 1);
         tc_fence_after();
+        if (threadIdx.x == 128) VTRACE(0, blk, 1);
         if (warp_active) {
           uint32_t t[kAttnBK];   // scores as raw fp32 bits (tcgen05.ld output registers)
           const uint32_t s_addr = tmem_base + lane_tmem;
@@ -293,6 +315,7 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           tmem_ld_32x32b_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&t[64]));
           tmem_ld_32x32b_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&t[96]));
           tmem_ld_wait();
+          if (threadIdx.x == 128) VTRACE(0, blk, 2);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->s_free));   // the tensor core may overwrite S now
@@ -352,10 +375,12 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           }
           // P.V of the previous block (of this item or the one before) must have completed before O is rescaled
           // or P overwritten; it was issued ~a block ago, so this wait is normally free
+          if (threadIdx.x == 128) VTRACE(0, blk, 3);
           if (blk > 0) {
             mbar_wait(smem_u32(&bars->pv_done), (blk - 1) & 1);
             tc_fence_after();
           }
+          if (threadIdx.x == 128) VTRACE(0, blk, 4);
           // ---- running maximum: raised only when the block exceeds it by more than 2^8
           const bool first = j == 0;
           const bool raise = first || mx > m_run + kLazyRescale;
@@ -396,6 +421,7 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           }
           l_run += sum0 + sum1;
           tmem_st_wait();
+          if (threadIdx.x == 128) VTRACE(0, blk, 5);
         } else {
           // a warp whose 32 rows are all past the end of the tile: its rows of P / O are never stored (the tensor
           // core computes them from whatever the lanes hold; rows are independent) — it only keeps the barriers going
@@ -413,8 +439,10 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
 
       // ---- item epilogue: O / l -> 16-bit row
+      if (threadIdx.x == 128) VTRACE(0, blk - 1, 6);
       mbar_wait(smem_u32(&bars->o_full), n & 1);
       tc_fence_after();
+      if (threadIdx.x == 128) VTRACE(0, blk - 1, 7);
       if (warp_active) {
         const float inv_l = 1.0f / l_run;
 #pragma unroll
@@ -469,6 +497,13 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 }
 
 }  // namespace
+
+#ifdef EMDR2_VARLEN_TRACE
+extern "C" __attribute__((visibility("default"))) int emdr2_varlen_trace_read(long long* out, int n) {
+  const size_t bytes = sizeof(long long) * static_cast<size_t>(n < 2 * kTraceBlocks * kTraceSlots ? n : 2 * kTraceBlocks * kTraceSlots);
+  return static_cast<int>(cudaMemcpyFromSymbol(out, g_varlen_trace, bytes));
+}
+#endif
 
 cudaError_t attention_varlen_prepare() {
   cudaError_t e = cudaFuncSetAttribute(attention_varlen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
