@@ -830,16 +830,27 @@ def run_retrieve_read(a):
         its stream (emdr2_ops_timing) -> the per-kernel-kind split and the rooflines.  The split is taken in a pass
         of its own because two event records and a mutex per launch cost host time that a launch-bound step (the
         training step at N = 8) would pay in its headline number."""
+        import gc
         for i in range(warm):
             resident_step(i)
         e2e_step(0)
         torch.cuda.synchronize()
-        with ClockSampler(d.local_rank) as clocks:
-            ms_total = d.timed(resident_step, steps)
-            ms_e2e = d.timed(e2e_step, steps)
-        searcher.set_option("timing", 1)
-        ops.timing(True)
-        ms_inst = d.timed(resident_step, steps)
+        # Python's cyclic collector stays out of the timed regions (collected between them): a full collection walks
+        # the millions of objects of the synthetic corpus / title maps and showed up as a sporadic +25 % on one region
+        # of the launch-heavy training step (the same reason trainers collect manually between steps).
+        gc.collect()
+        gc.disable()
+        try:
+            with ClockSampler(d.local_rank, period=0.05) as clocks:
+                ms_total = d.timed(resident_step, steps)
+                gc.collect()
+                ms_e2e = d.timed(e2e_step, steps)
+            gc.collect()
+            searcher.set_option("timing", 1)
+            ops.timing(True)
+            ms_inst = d.timed(resident_step, steps)
+        finally:
+            gc.enable()
         roof_mips = mips_roofline(a, d, searcher, hi - lo, nq_search)
         gemm_s, gemm_n, gemm_fl = ops.timing_read(ops.KIND_GEMM)
         attn_s, attn_n, attn_fl = ops.timing_read(ops.KIND_ATTENTION)
