@@ -878,6 +878,23 @@ def run_retrieve_read(a):
         model.settings["update_retriever"] = True
         m = measure(train_resident_step, train_e2e_step, steps, warm_steps)
         gb = trainer["buckets"]
+        # host time to ENQUEUE one step on an idle GPU (no synchronisation inside): how far the launching thread runs
+        # ahead of the device — a step whose enqueue time approaches its device time is exposed to host noise
+        torch.cuda.synchronize()
+        t_host = time.perf_counter()
+        train_resident_step(0)
+        host_enqueue_ms = (time.perf_counter() - t_host) * 1e3
+        torch.cuda.synchronize()
+        if os.environ.get("EMDR2_BENCH_PROFILE_HOST") and rank == 0:      # where the launching thread's time goes
+            import cProfile
+            import pstats
+            prof = cProfile.Profile()
+            prof.enable()
+            for i in range(2):
+                train_resident_step(i)
+            prof.disable()
+            torch.cuda.synchronize()
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(45)
         ar_ms = None
         if world > 1:          # the exchange alone: all buckets back to back, nothing to hide behind
             torch.cuda.synchronize()
@@ -890,7 +907,7 @@ def run_retrieve_read(a):
             torch.cuda.synchronize()
             ar_ms = d.max_over_ranks(e0.elapsed_time(e1) / 3)
         return {"value": a.batch * world / (m["ms_step"] * 1e-3), "unit": "queries/s", "ms_per_step": m["ms_step"],
-                "steps": steps, "warmup": warm_steps,
+                "steps": steps, "warmup": warm_steps, "host_enqueue_ms_per_step": host_enqueue_ms,
                 "e2e": {"value": a.batch * world / (m["ms_e2e_step"] * 1e-3), "unit": "queries/s",
                         "h2d_bytes_per_step": in_bytes + fmt_h2d, "d2h_bytes_per_step": 8 + a.batch * a.k * 4},
                 "kernel_time_ms_per_step": {"gemm": m["gemm_ms"], "attention": m["attn_ms"], "rowops": m["row_ms"],

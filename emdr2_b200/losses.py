@@ -34,7 +34,13 @@ def loss_and_retriever_utility_from_gold(gold, topk_log_probs, labels, loss_mask
     lm_loss = -1 * torch.sum(marginal * loss_mask) / torch.sum(loss_mask)
     utility = marginal - gold[:, -1, :]
     utility_mask = loss_mask.masked_fill(labels >= eos_id, 0)
-    if not torch.sum(utility_mask) > 0:
+    # the reference asserts this on the host (:116), which stalls the launching thread until the whole forward has run
+    # and leaves the backward pass to be enqueued against an idle GPU; on a CUDA tensor the same condition is checked by
+    # a device-side assertion instead (it fails just as loudly, at the next synchronisation)
+    nonempty = torch.sum(utility_mask) > 0
+    if nonempty.is_cuda:
+        torch._assert_async(nonempty, "retriever-utility mask is empty")
+    elif not nonempty:
         raise AssertionError("retriever-utility mask is empty")
     utility = torch.sum(utility * utility_mask) / torch.sum(utility_mask)
     null_block_lm_loss = -1 * torch.sum(gold[:, -1, :] * loss_mask) / torch.sum(loss_mask)
