@@ -1070,7 +1070,7 @@ def run_retrieve_read(a):
     if not a.train and not a.no_gpu_reference:
         line["gpu_reference"] = gpu_reference_read_leg(a, d, model, rows, all_q, dev)
     if not a.train and not a.no_train_step:
-        line["train_step"] = train_block(a.train_steps, 5)
+        line["train_step"] = train_block(a.train_steps, 12)   # the first seconds of training on a fresh box run ~10 % slow
     if "train_step" in line and a.refresh_rows > 0:
         try:
             line["index_refresh"] = refresh_block(line["train_step"]["ms_per_step"])
