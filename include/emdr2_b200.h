@@ -330,8 +330,13 @@ EMDR2_API int emdr2_format_passages_flat(int32_t bsz, int32_t k_keep, const int6
  * CTA per 128 x 256 tile; 2 (default) = only where that is measured to win (residual / aux epilogues
  * over >= 100 k rows); 0 = never.  Results are bit-identical between the two kernels (same products, same fp32
  * accumulation order per element). */
+/* "gemm_wide" (EMDR2_GEMM_WIDE): sixteen instead of eight epilogue warps in the one-CTA kernel for 16-bit outputs —
+ * 1 (default) = where the epilogue has arithmetic or an aux tile's latency to hide (GeLU, pre-activation side output,
+ * GeLU backward), 2 = whenever eligible (no fp32 accumulation, no split-K), 0 = never.  Bit-identical results. */
 /* "gemm_max_ctas": > 0 caps the persistent GEMM grids at that many CTAs (0 = one per SM): leave SMs to a collective
- * kernel that overlaps with the backward pass instead of running the grid's last CTAs as a second wave. */
+ * kernel that overlaps with the backward pass instead of running the grid's last CTAs as a second wave.  The cap also
+ * decides how well the weight-gradient products fill the machine (output tiles x split-K factor vs CTAs): with the
+ * step's 18 / 54 / 72-tile products 144 CTAs (4 SMs for NCCL, NCCL_MAX_CTAS=4) are filled exactly, 140 are not. */
 EMDR2_API int emdr2_ops_set_option(const char* name, int64_t value);
 EMDR2_API int emdr2_ops_get_option(const char* name, int64_t* out_value);
 
