@@ -354,3 +354,45 @@ def test_split_k_factor_fills_whole_waves_of_the_persistent_grid():
             assert occupancy(tiles, s, ctas) + 1e-9 >= occupancy(tiles, 1, ctas) - 0.015 * s   # never worse than no split
     assert _splits(204800, 72, 140) <= 8          # not the 15 splits a balance-only rule picks
     assert _splits(2048, 18) == 1 and _splits(12800, 18) <= 4      # slices of at least 4096 tokens
+
+
+def test_key_split_merge_reproduces_the_unsplit_softmax():
+    """autograd._merge_splits / _split_masks / _rep_rows (pure torch, runs on the CPU): attention over a long key axis
+    computed range by range — each range with its own softmax normalisation and log-sum-exp, as the kernels return
+    them — and merged by the lse weights equals attention over the whole axis; the merged lse is the global one.  One
+    range is all padding (weight exp(-10000 - lse) = 0)."""
+    from emdr2_b200 import autograd as ag
+    torch.manual_seed(3)
+    b, heads, sq, sk, splits = 2, 3, 5, 1024, 4
+    h, sk_s = heads * 64, sk // splits
+    q = torch.randn(b * sq, h)
+    k, v = torch.randn(b * sk, h), torch.randn(b * sk, h)
+    k_pad = torch.zeros(b, sk, dtype=torch.uint8)
+    k_pad[0, 700:] = 1                           # question 0: the last range is all padding
+    k_pad[1, 100:300] = 1
+    k_live = (k_pad.view(b, sk // 128, 128) == 0).any(dim=2).to(torch.uint8)
+
+    def attend(qx, kx, vx, nb, nk, pad):        # fp32 reference of one launch: masked_fill(-10000) semantics
+        qh = qx.view(nb, sq, heads, 64).permute(0, 2, 1, 3)
+        kh = kx.view(nb, nk, heads, 64).permute(0, 2, 1, 3)
+        vh = vx.view(nb, nk, heads, 64).permute(0, 2, 1, 3)
+        s = torch.matmul(qh, kh.transpose(-1, -2)) * 0.125
+        s = s.masked_fill(pad.bool()[:, None, None, :], -10000.0)
+        lse = torch.logsumexp(s, dim=-1)                                      # [nb, heads, sq]
+        out = torch.matmul(torch.softmax(s, dim=-1), vh).permute(0, 2, 1, 3).reshape(nb * sq, h)
+        return out, lse
+
+    want, want_lse = attend(q, k, v, b, sk, k_pad)
+    q_pad_s, k_pad_s, q_live_s, k_live_s = ag._split_masks(None, k_pad, None, k_live, b, sk, splits)
+    assert q_pad_s is None and q_live_s is None
+    assert k_pad_s.shape == (b * splits, sk_s) and k_live_s.shape == (b * splits, sk_s // 128)
+    assert bool((k_live_s[:, 0] == 1).all())                                  # one live block per entry, always
+    q_rep = ag._rep_rows(q, b, splits, sq)
+    assert q_rep.shape == (b * splits * sq, h) and torch.equal(q_rep[sq:2 * sq], q[:sq])
+    out_s, lse_s = attend(q_rep, k, v, b * splits, sk_s, k_pad_s)
+    got, got_lse = ag._merge_splits(out_s, lse_s, b, splits, heads, sq, torch.float32)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(got_lse, want_lse, rtol=1e-6, atol=1e-5)
+    # the number of ranges is a divisor of the 128-key block count, >= 4 blocks per range, 1 below the threshold
+    assert ag._cross_splits(8, 12, 25600) in (8, 10) and 200 % ag._cross_splits(8, 12, 25600) == 0
+    assert ag._cross_splits(8, 12, 2048) == 1 and ag._cross_splits(400, 12, 25600) == 1
