@@ -22,6 +22,7 @@
 
 #include <type_traits>
 
+#include "gelu.cuh"   // packed fp32 helpers (f2_fma / f2_mul: two IEEE fp32 operations per issued instruction)
 #include "ptx.cuh"
 
 namespace emdr2 {
@@ -313,26 +314,47 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
               cb[0] = c0.x; cb[1] = c0.y; cb[2] = c0.z; cb[3] = c0.w;
               cb[4] = c1.x; cb[5] = c1.y; cb[6] = c1.z; cb[7] = c1.w;
             }
+            if constexpr (kFast) {
+              // the mask-free loop on PAIRS: scale-and-shift, the dropout rescale and the product are one packed
+              // instruction per two elements each
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int c = g * 8 + i;
-              const float p = ex2(fmaf(__uint_as_float(s[c]), a.scale_log2, -lse2));
-              float x;
-              if constexpr (kDrop) {   // dP = keep / (1 - p_drop) * (dO . V^T): the forward's mask, regenerated
-                const float m = dropout_keep(drop_row, cb[i], a.drop.threshold) ? a.drop.inv_keep : 0.f;
-                x = fmaf(__uint_as_float(dp[c]), m, -dsum);
-              } else {
-                x = __uint_as_float(dp[c]) - dsum;
+              for (int i = 0; i < 8; i += 2) {
+                const int c = g * 8 + i;
+                float t0, t1;
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), f2_splat(a.scale_log2),
+                                 f2_splat(-lse2)), t0, t1);
+                const uint64_t p2 = f2_pack(ex2(t0), ex2(t1));
+                uint64_t x2;
+                if constexpr (kDrop) {
+                  const float m0 = dropout_keep(drop_row, cb[i], a.drop.threshold) ? a.drop.inv_keep : 0.f;
+                  const float m1 = dropout_keep(drop_row, cb[i + 1], a.drop.threshold) ? a.drop.inv_keep : 0.f;
+                  x2 = f2_fma(f2_pack(__uint_as_float(dp[c]), __uint_as_float(dp[c + 1])), f2_pack(m0, m1),
+                              f2_splat(-dsum));
+                } else {
+                  x2 = f2_add(f2_pack(__uint_as_float(dp[c]), __uint_as_float(dp[c + 1])), f2_splat(-dsum));
+                }
+                f2_unpack(f2_mul(p2, x2), ds[i], ds[i + 1]);
               }
-              float d = p * x;
-              if constexpr (!kFast) {
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int c = g * 8 + i;
+                const float p = ex2(fmaf(__uint_as_float(s[c]), a.scale_log2, -lse2));
+                float x;
+                if constexpr (kDrop) {   // dP = keep / (1 - p_drop) * (dO . V^T): the forward's mask, regenerated
+                  const float m = dropout_keep(drop_row, cb[i], a.drop.threshold) ? a.drop.inv_keep : 0.f;
+                  x = fmaf(__uint_as_float(dp[c]), m, -dsum);
+                } else {
+                  x = __uint_as_float(dp[c]) - dsum;
+                }
+                float d = p * x;
                 if (!plain) {
                   const uint32_t cc = ch * 32 + c;
                   const bool masked = row_dead || ((kmw >> c) & 1u) || (a.causal && kb0 + cc > qi) || cc >= valid;
                   d = masked ? 0.f : d;
                 }
+                ds[i] = d;
               }
-              ds[i] = d;
             }
             const uint32_t phys = (static_cast<uint32_t>(ch * 4 + g) ^ (row & 7u)) * 16u;
             *reinterpret_cast<uint4*>(ds_row + phys) =
@@ -600,8 +622,32 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
               rh[0] = r0.x; rh[1] = r0.y; rh[2] = r0.z; rh[3] = r0.w;
               rh[4] = r1.x; rh[5] = r1.y; rh[6] = r1.z; rh[7] = r1.w;
             }
+            if constexpr (kFast) {
 #pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) {
+              for (int i2 = 0; i2 < 8; i2 += 2) {       // the mask-free loop on pairs (packed fp32 instructions)
+                const int c = g * 8 + i2;
+                float t0, t1;
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), f2_splat(a.scale_log2),
+                                 f2_pack(-lv[i2], -lv[i2 + 1])), t0, t1);
+                const uint64_t p2 = f2_pack(ex2(t0), ex2(t1));
+                uint64_t pd2 = p2, x2;
+                const uint64_t dp2 = f2_pack(__uint_as_float(dp[c]), __uint_as_float(dp[c + 1]));
+                const uint64_t ndv2 = f2_pack(-dv[i2], -dv[i2 + 1]);
+                if constexpr (kDrop) {
+                  const float m0 = dropout_keep(rh[i2], drop_col, a.drop.threshold) ? a.drop.inv_keep : 0.f;
+                  const float m1 = dropout_keep(rh[i2 + 1], drop_col, a.drop.threshold) ? a.drop.inv_keep : 0.f;
+                  const uint64_t m2 = f2_pack(m0, m1);
+                  pd2 = f2_mul(p2, m2);
+                  x2 = f2_fma(dp2, m2, ndv2);
+                } else {
+                  x2 = f2_add(dp2, ndv2);
+                }
+                f2_unpack(pd2, pv[i2], pv[i2 + 1]);
+                f2_unpack(f2_mul(p2, x2), ds[i2], ds[i2 + 1]);
+              }
+            }
+#pragma unroll
+            for (int i2 = 0; i2 < (kFast ? 0 : 8); ++i2) {
               const int c = g * 8 + i2;                 // column inside this thread's 32
               const uint32_t cc = ch * 32 + c;          // query column inside the 64-query block
               bool masked = false;
