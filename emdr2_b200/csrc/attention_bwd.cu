@@ -57,32 +57,52 @@ __device__ __forceinline__ float2 unpack2(uint32_t v) {
 }
 
 // D[b, h, i] = sum_d dO[b, i, h, d] * O[b, i, h, d]
+// Eight lanes per (token, head): each loads ONE 16-byte chunk of the head's 128-byte rows of dO and O (a warp
+// instruction covers four whole rows: fully coalesced) and the eight partial sums are folded by shuffles; four
+// (token, head) units per thread keep eight independent loads in flight.  (One thread per unit with eight strided
+// 16-byte loads ran at half of the copy bandwidth, latency-bound.)
+constexpr int kPrepUnroll = 4;
 template <bool kBf16>
 __global__ void __launch_bounds__(256)
 attention_bwd_prep_kernel(const uint16_t* __restrict__ dout, int64_t lddo, const uint16_t* __restrict__ out,
                           int64_t ldo, float* __restrict__ dvec, int batch, int heads, int sq) {
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;   // (token, head)
-  const int64_t total = static_cast<int64_t>(batch) * sq * heads;
-  if (idx >= total) return;
-  const int64_t tok = idx / heads;
-  const int h = static_cast<int>(idx % heads);
-  const uint16_t* a = dout + tok * lddo + h * 64;
-  const uint16_t* b = out + tok * ldo + h * 64;
-  float acc = 0.f;
+  const uint32_t total = static_cast<uint32_t>(batch) * sq * heads;            // (token, head) units, < 2^31 (checked on the host)
+  const uint32_t chunk = threadIdx.x & 7u;
+  const uint32_t unit0 = (blockIdx.x * 256u + threadIdx.x) >> 3;
+  const uint32_t stride = (gridDim.x * 256u) >> 3;
+  const uint32_t uheads = static_cast<uint32_t>(heads), usq = static_cast<uint32_t>(sq);
+  uint4 x[kPrepUnroll], y[kPrepUnroll];
+  uint32_t tok[kPrepUnroll], hd[kPrepUnroll];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 x = __ldg(reinterpret_cast<const uint4*>(a + c * 8));
-    const uint4 y = __ldg(reinterpret_cast<const uint4*>(b + c * 8));
-    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+  for (int j = 0; j < kPrepUnroll; ++j) {
+    const uint32_t u = unit0 + j * stride;
+    tok[j] = u / uheads;
+    hd[j] = u - tok[j] * uheads;
+    if (u < total) {
+      x[j] = __ldg(reinterpret_cast<const uint4*>(dout + static_cast<int64_t>(tok[j]) * lddo + hd[j] * 64 + chunk * 8));
+      y[j] = __ldg(reinterpret_cast<const uint4*>(out + static_cast<int64_t>(tok[j]) * ldo + hd[j] * 64 + chunk * 8));
+    } else {
+      x[j] = y[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kPrepUnroll; ++j) {
+    const uint32_t xw[4] = {x[j].x, x[j].y, x[j].z, x[j].w}, yw[4] = {y[j].x, y[j].y, y[j].z, y[j].w};
+    float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 p = unpack2<kBf16>(xw[i]), q = unpack2<kBf16>(yw[i]);
       acc = fmaf(p.x, q.x, acc);
       acc = fmaf(p.y, q.y, acc);
     }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (chunk == 0 && unit0 + j * stride < total) {
+      const uint32_t bi = tok[j] / usq, i = tok[j] - bi * usq;
+      dvec[(static_cast<int64_t>(bi) * heads + hd[j]) * sq + i] = acc;
+    }
   }
-  const int64_t bi = tok / sq, i = tok % sq;
-  dvec[(bi * heads + h) * sq + i] = acc;
 }
 
 struct BwdBars {
@@ -753,7 +773,9 @@ cudaError_t launch_attention_bwd_prep(bool bf16, const void* dout, int64_t lddo,
                                       float* dvec, int batch, int heads, int sq, cudaStream_t stream) {
   const int64_t total = static_cast<int64_t>(batch) * sq * heads;
   if (total <= 0) return cudaSuccess;
-  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (total >= (int64_t{1} << 31)) return cudaErrorInvalidValue;
+  const int64_t per_block = 256 / 8 * kPrepUnroll;                      // (token, head) units per block
+  const unsigned grid = static_cast<unsigned>((total + per_block - 1) / per_block);
   if (bf16)
     attention_bwd_prep_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(dout), lddo,
                                                               static_cast<const uint16_t*>(out), ldo, dvec, batch,
