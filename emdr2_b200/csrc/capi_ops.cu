@@ -354,7 +354,7 @@ int emdr2_layernorm_fwd(int dtype, const void* x, int64_t ldx, const void* gamma
   if (rc != EMDR2_OK) return rc;
   ScopedTimer timer(EMDR2_KIND_ROWOP, static_cast<cudaStream_t>(cuda_stream), 0.0);
   CUDA_TRY(emdr2::launch_layernorm_fwd(dtype == EMDR2_DTYPE_BF16, x, ldx, gamma, beta, y, ldy, rows, h,
-                                       eps, mean, rstd, static_cast<cudaStream_t>(cuda_stream)));
+                                       eps, mean, rstd, info.sm_count, static_cast<cudaStream_t>(cuda_stream)));
   return EMDR2_OK;
 }
 

@@ -43,57 +43,69 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// One warp per row, rows handed out with a grid stride over resident blocks: gamma and beta are staged ONCE per block
+// in shared memory (they used to be fetched from global memory per row, behind the two reductions).
 template <bool kBf16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 layernorm_fwd_kernel(const uint16_t* __restrict__ x, int64_t ldx, const uint16_t* __restrict__ gamma,
                      const uint16_t* __restrict__ beta, uint16_t* __restrict__ y, int64_t ldy,
                      int rows, int h, float eps, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const uint16_t* xr = x + static_cast<size_t>(row) * ldx;
-  float v[kMaxChunks][8];
-  float sum = 0.f;
-#pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int col = (c * 32 + lane) * 8;
-    if (col < h) {
-      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(xr + col)), v[c]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sum += v[c][i];
+  __shared__ uint4 s_gamma[kMaxChunks * 32], s_beta[kMaxChunks * 32];
+  for (int i = threadIdx.x; i < kMaxChunks * 32; i += blockDim.x) {
+    if (i * 8 < h) {
+      s_gamma[i] = __ldg(reinterpret_cast<const uint4*>(gamma + i * 8));
+      s_beta[i] = __ldg(reinterpret_cast<const uint4*>(beta + i * 8));
     }
   }
-  const float mean = warp_sum(sum) / static_cast<float>(h);
-  float sq = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int stride = gridDim.x * warps_per_block;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += stride) {
+    const uint16_t* xr = x + static_cast<size_t>(row) * ldx;
+    float v[kMaxChunks][8];
+    float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int col = (c * 32 + lane) * 8;
-    if (col < h) {
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < h) {
+        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(xr + col)), v[c]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = v[c][i] - mean;
-        sq = fmaf(d, d, sq);
+        for (int i = 0; i < 8; ++i) sum += v[c][i];
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(h) + eps);
-  uint16_t* yr = y + static_cast<size_t>(row) * ldy;
+    const float mean = warp_sum(sum) / static_cast<float>(h);
+    float sq = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int col = (c * 32 + lane) * 8;
-    if (col < h) {
-      float g[8], bt[8], o[8];
-      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(gamma + col)), g);
-      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(beta + col)), bt);
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < h) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf((v[c][i] - mean) * rstd, g[i], bt[i]);
-      *reinterpret_cast<uint4*>(yr + col) = pack8<kBf16>(o);
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[c][i] - mean;
+          sq = fmaf(d, d, sq);
+        }
+      }
     }
-  }
-  if (lane == 0) {
-    if (mean_out) mean_out[row] = mean;
-    if (rstd_out) rstd_out[row] = rstd;
+    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(h) + eps);
+    uint16_t* yr = y + static_cast<size_t>(row) * ldy;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < h) {
+        float g[8], bt[8], o[8];
+        unpack8<kBf16>(s_gamma[c * 32 + lane], g);
+        unpack8<kBf16>(s_beta[c * 32 + lane], bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf((v[c][i] - mean) * rstd, g[i], bt[i]);
+        *reinterpret_cast<uint4*>(yr + col) = pack8<kBf16>(o);
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
   }
 }
 
@@ -224,11 +236,12 @@ cudaError_t launch_token_logprob(bool bf16, const void* logits, int64_t ld, cons
 
 cudaError_t launch_layernorm_fwd(bool bf16, const void* x, int64_t ldx, const void* gamma,
                                  const void* beta, void* y, int64_t ldy, int rows, int h, float eps,
-                                 float* mean, float* rstd, cudaStream_t stream) {
+                                 float* mean, float* rstd, int sm_count, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   if (h % 8 || h > kMaxChunks * 256) return cudaErrorInvalidValue;
   const int warps = 8;
-  const int grid = (rows + warps - 1) / warps;
+  int grid = (rows + warps - 1) / warps;
+  if (sm_count > 0 && grid > sm_count * 8) grid = sm_count * 8;   // two waves of resident blocks; warps stride over the rows
   auto xs = static_cast<const uint16_t*>(x);
   auto gs = static_cast<const uint16_t*>(gamma);
   auto bs = static_cast<const uint16_t*>(beta);

@@ -11,7 +11,7 @@ namespace emdr2 {
 // mean / rstd ([rows] fp32) are optional outputs for the backward pass.
 cudaError_t launch_layernorm_fwd(bool bf16, const void* x, int64_t ldx, const void* gamma,
                                  const void* beta, void* y, int64_t ldy, int rows, int h, float eps,
-                                 float* mean, float* rstd, cudaStream_t stream);
+                                 float* mean, float* rstd, int sm_count, cudaStream_t stream);
 
 // out[t,:] = word[ids[t],:] + pos[t % seq,:] (+ type[types[t],:]): Embedding.forward with dropout
 // off (reference megatron/model/language_model.py:169-181; position ids = arange(seq),
