@@ -46,43 +46,57 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = dy * gamma, xhat = (x - mean) * rstd
 // dgamma += sum_rows dy * xhat, dbeta += sum_rows dy.
-template <bool kBf16>
-__global__ void __launch_bounds__(256)
+// One warp per row, rows handed out with a grid stride over RESIDENT blocks (two per SM).  Register budget is what
+// bounds this kernel: the per-thread dgamma / dbeta accumulators are 2 x 8 floats per 256-column chunk, so the kernel
+// is instantiated for the number of chunks the width needs (three for h = 768), keeps dy / x / dres of the row as the
+// raw 16-byte words across the two warp reductions and unpacks them again for dx, and keeps gamma packed — 120 instead
+// of 213 registers, two blocks per SM instead of one (measured 2.0 -> see profiles/README.md TB/s at 185 600 x 768).
+template <bool kBf16, int kChunks>
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const uint16_t* __restrict__ dy, int64_t ldy, const uint16_t* __restrict__ x, int64_t ldx,
                      const uint16_t* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const uint16_t* __restrict__ dres, int64_t ldr,
                      uint16_t* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, int rows, int h) {
-  __shared__ float s_red[8][kMaxChunks * 256 + 8];
+  __shared__ float s_red[8][kChunks * 256 + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float acc_g[kMaxChunks][8], acc_b[kMaxChunks][8], gam[kMaxChunks][8];
+  float acc_g[kChunks][8], acc_b[kChunks][8];
+  uint4 gam_raw[kChunks];
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < kChunks; ++c) {
     const int col = (c * 32 + lane) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc_g[c][i] = acc_b[c][i] = 0.f;
-    if (col < h) unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(gamma + col)), gam[c]);
+    gam_raw[c] = col < h ? __ldg(reinterpret_cast<const uint4*>(gamma + col)) : make_uint4(0u, 0u, 0u, 0u);
   }
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
-    const float mu = mean[row], rs = rstd[row];
-    float g[kMaxChunks][8], xh[kMaxChunks][8];
-    uint4 rraw[kMaxChunks];   // the residual-branch gradient, fetched with dy and x (not behind the row reductions)
-    float s1 = 0.f, s2 = 0.f;
+    uint4 d_raw[kChunks], x_raw[kChunks], r_raw[kChunks];
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < kChunks; ++c) {     // all of the row's loads first
       const int col = (c * 32 + lane) * 8;
       if (col < h) {
-        if (dres) rraw[c] = __ldg(reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * ldr + col));
-        float d[8], xv[8];
-        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * ldy + col)), d);
-        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx + col)), xv);
+        d_raw[c] = __ldg(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * ldy + col));
+        x_raw[c] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx + col));
+        if (dres) r_raw[c] = __ldg(reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * ldr + col));
+      }
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < h) {
+        float d[8], xv[8], gm[8];
+        unpack8<kBf16>(d_raw[c], d);
+        unpack8<kBf16>(x_raw[c], xv);
+        unpack8<kBf16>(gam_raw[c], gm);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          xh[c][i] = (xv[i] - mu) * rs;
-          g[c][i] = d[i] * gam[c][i];
-          s1 += g[c][i];
-          s2 = fmaf(g[c][i], xh[c][i], s2);
-          acc_g[c][i] = fmaf(d[i], xh[c][i], acc_g[c][i]);
+          const float xh = (xv[i] - mu) * rs;
+          const float g = d[i] * gm[i];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          acc_g[c][i] = fmaf(d[i], xh, acc_g[c][i]);
           acc_b[c][i] += d[i];
         }
       }
@@ -90,15 +104,22 @@ layernorm_bwd_kernel(const uint16_t* __restrict__ dy, int64_t ldy, const uint16_
     const float c1 = warp_sum(s1) / static_cast<float>(h);
     const float c2 = warp_sum(s2) / static_cast<float>(h);
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < kChunks; ++c) {
       const int col = (c * 32 + lane) * 8;
       if (col < h) {
-        float o[8];
+        float d[8], xv[8], gm[8], o[8];
+        unpack8<kBf16>(d_raw[c], d);
+        unpack8<kBf16>(x_raw[c], xv);
+        unpack8<kBf16>(gam_raw[c], gm);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rs * (g[c][i] - c1 - xh[c][i] * c2);
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (xv[i] - mu) * rs;       // the same expressions as above: bit-identical g and xhat
+          const float g = d[i] * gm[i];
+          o[i] = rs * (g - c1 - xh * c2);
+        }
         if (dres) {
           float r[8];
-          unpack8<kBf16>(rraw[c], r);
+          unpack8<kBf16>(r_raw[c], r);
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] += r[i];
         }
@@ -110,7 +131,7 @@ layernorm_bwd_kernel(const uint16_t* __restrict__ dy, int64_t ldy, const uint16_
   for (int pass = 0; pass < 2; ++pass) {
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < kChunks; ++c) {
       const int col = (c * 32 + lane) * 8;
       if (col < h) {
 #pragma unroll
@@ -275,14 +296,24 @@ cudaError_t launch_layernorm_bwd(bool bf16, const void* dy, int64_t ldy, const v
   if (rows <= 0) return cudaSuccess;
   if (h % 8 || h > kMaxChunks * 256) return cudaErrorInvalidValue;
   int grid = (rows + 7) / 8;
-  if (grid > sm_count * 4) grid = sm_count * 4;
+  if (grid > sm_count * 2) grid = sm_count * 2;      // resident blocks (two per SM): one parameter-gradient fold each
   auto p = [](const void* v) { return static_cast<const uint16_t*>(v); };
-  if (bf16)
-    layernorm_bwd_kernel<true><<<grid, 256, 0, stream>>>(p(dy), ldy, p(x), ldx, p(gamma), mean, rstd, p(dres), ldr,
-                                                         static_cast<uint16_t*>(dx), lddx, dgamma, dbeta, rows, h);
-  else
-    layernorm_bwd_kernel<false><<<grid, 256, 0, stream>>>(p(dy), ldy, p(x), ldx, p(gamma), mean, rstd, p(dres), ldr,
-                                                          static_cast<uint16_t*>(dx), lddx, dgamma, dbeta, rows, h);
+  const int chunks = (h + 255) / 256;
+#define EMDR2_LN_BWD(BF, CH)                                                                                       \
+  layernorm_bwd_kernel<BF, CH><<<grid, 256, 0, stream>>>(p(dy), ldy, p(x), ldx, p(gamma), mean, rstd, p(dres), ldr, \
+                                                         static_cast<uint16_t*>(dx), lddx, dgamma, dbeta, rows, h)
+  if (bf16) {
+    if (chunks <= 1) EMDR2_LN_BWD(true, 1);
+    else if (chunks == 2) EMDR2_LN_BWD(true, 2);
+    else if (chunks == 3) EMDR2_LN_BWD(true, 3);
+    else EMDR2_LN_BWD(true, 4);
+  } else {
+    if (chunks <= 1) EMDR2_LN_BWD(false, 1);
+    else if (chunks == 2) EMDR2_LN_BWD(false, 2);
+    else if (chunks == 3) EMDR2_LN_BWD(false, 3);
+    else EMDR2_LN_BWD(false, 4);
+  }
+#undef EMDR2_LN_BWD
   return cudaGetLastError();
 }
 

@@ -53,3 +53,20 @@ for rows in (185600, 66000, 256):
     ref = torch.nn.functional.layer_norm(x.float(), (768,), g.float(), b.float(), 1e-5)
     err = (ops.layernorm(x, g, b).float() - ref).abs().max().item()
     print("rows=%d forward %.4f ms %.0f GB/s (max|err| vs fp32 torch %.3e)" % (rows, ms, 2 * x.numel() * 2 / ms / 1e6, err))
+
+for rows in (185600, 66000):
+    x = torch.randn(rows, 768, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    g = torch.randn(768, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(768, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    dy = torch.randn(rows, 768, device=DEV).to(torch.bfloat16)
+
+    def bwd():
+        x.grad = g.grad = b.grad = None
+        y = ag.layernorm(x, g, b)
+        y.backward(dy)
+
+    ms_fb = med(bwd)
+    ms_f = med(lambda: ops.layernorm(x.detach(), g.detach(), b.detach(), return_stats=True))
+    ms_b = ms_fb - ms_f
+    print("rows=%d backward ~%.4f ms (forward+backward %.4f - forward %.4f) %.0f GB/s of 3 x rows x h x 2 B"
+          % (rows, ms_b, ms_fb, ms_f, 3 * x.numel() * 2 / ms_b / 1e6))
